@@ -1,0 +1,153 @@
+/* tosemscan.h - C ABI of libtosemscan.so, the B200-native corpus-scan hot path.
+ *
+ * Drop-in boundary.  The reference package (openjamoses/TOSEM-2021-Replication) ships NO code, hence
+ * no plugin / operator / FFI interface to mirror: the only observable contract is
+ * its file formats.  Each entry point below therefore cites the reference ARTEFACT whose
+ * producing stage it replaces; docs/SPEC.md gives the byte-level rules, INTEGRATION.md the
+ * bindings (ctypes / C++ CLI) a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no exceptions, no global state; every call returns
+ * TSM_OK (0) or a negative tsm_status; caller owns all host memory; a tsm_ctx owns device memory
+ * and is bound to one CUDA device; calls on one ctx must be serialised by the caller, calls on
+ * different ctxs are independent (one host thread / process per GPU).  `stream` is a cudaStream_t
+ * passed as void* (NULL = the legacy default stream).  There is no CPU fallback: without a usable
+ * CUDA device tsm_create() fails with TSM_E_CUDA.
+ */
+#ifndef TOSEMSCAN_H
+#define TOSEMSCAN_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSM_ABI_VERSION 1
+#define TSM_NUM_CATEGORIES 128   /* K of docs/SPEC.md section 6 */
+#define TSM_ALIGN 128            /* file start alignment inside the arena */
+
+typedef enum {
+  TSM_OK = 0,
+  TSM_E_ARG = -1,        /* null / negative / inconsistent argument */
+  TSM_E_LAYOUT = -2,     /* corpus violates SPEC section 1 (alignment, bounds, grp >= n_groups) */
+  TSM_E_CAPACITY = -3,   /* corpus or event count exceeds what the ctx was created for */
+  TSM_E_CUDA = -4,       /* CUDA runtime error (no device, launch failure, ...) */
+  TSM_E_NOMEM = -5,
+  TSM_E_STATE = -6       /* call order (e.g. scan_resident before upload) */
+} tsm_status;
+
+/* ext tags (S1: value census of the `extension` column, Important-files/ML-Testing-v1.xlsx) */
+enum { TSM_EXT_OTHER = 0, TSM_EXT_PY = 1, TSM_EXT_CC = 2, TSM_EXT_CPP = 3, TSM_EXT_JAVA = 4, TSM_EXT_C = 5, TSM_EXT_H = 6 };
+
+/* scan flags */
+#define TSM_SCAN_ASSERT_EVENTS 1u  /* produce assertion events (raw scan rows need them) */
+#define TSM_SCAN_HEADER_EVENTS 2u  /* produce header events (method column needs them) */
+
+/* Per-file record; replaces the per-file summary stage (S6: `total assert` of
+ * selection/completed-labels/Release-Meta-tpot.csv:1-2). */
+typedef struct tsm_file_stat {
+  uint32_t n_lines, n_assert, n_headers, n_fixture;
+  uint64_t digest;
+} tsm_file_stat;
+
+/* One assertion line; the raw-row stage (fileName,extension,test_name,method,statement,counts,
+ * category: Important-files/ML-Testing-v1.xlsx!apollo_tests:R1) groups these. Offsets are
+ * relative to the file start. */
+typedef struct tsm_assert_event {
+  uint32_t file, line_off, stmt_off;
+  uint16_t stmt_len, cat;
+  uint32_t ident_off;
+  uint16_t ident_len, pad;
+  uint64_t stmt_hash;
+} tsm_assert_event;
+
+typedef struct tsm_header_event { uint32_t file, line_off, line_len, kind; } tsm_header_event; /* kind bit0 = TEST_F */
+
+/* Packed corpus (SPEC section 1). All pointers host memory for the host-path calls. */
+typedef struct tsm_corpus {
+  const uint8_t* arena;   /* off[n_files] bytes */
+  const int32_t* off;     /* [n_files+1], multiples of TSM_ALIGN, ascending */
+  const int32_t* len;     /* [n_files], off[i]+len[i] <= off[i+1] */
+  const uint8_t* ext;     /* [n_files] TSM_EXT_* */
+  const uint16_t* grp;    /* [n_files] < n_groups; NULL = all 0 */
+  int32_t n_files;
+  int32_t n_groups;       /* >= 1 */
+} tsm_corpus;
+
+/* Host-side result buffers. Any pointer may be NULL (that output is skipped). */
+typedef struct tsm_result {
+  tsm_file_stat* stats;          /* [n_files] */
+  int64_t* group_counts;         /* [n_groups][TSM_NUM_CATEGORIES] */
+  int64_t* global_counts;        /* [TSM_NUM_CATEGORIES] */
+  tsm_assert_event* aev; int64_t aev_cap; int64_t n_aev;   /* canonical order (file, line_off) */
+  tsm_header_event* hev; int64_t hev_cap; int64_t n_hev;
+  int64_t totals[4];             /* lines, assertion lines, headers, fixture headers */
+} tsm_result;
+
+typedef struct tsm_ctx tsm_ctx;
+
+int tsm_abi_version(void);
+const char* tsm_strerror(int status);
+const char* tsm_category_name(int id);   /* "" for 0/reserved, "<other>" for 127 */
+
+/* Context sized for corpora up to (max_arena_bytes, max_files, max_groups) and max_events events
+ * of each kind (0 = derive from max_arena_bytes). */
+int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, int32_t max_files,
+               int32_t max_groups, int64_t max_events);
+void tsm_destroy(tsm_ctx* ctx);
+
+/* Host path, end to end: H2D of the corpus (overlapped slab by slab with the scan), the scan and
+ * classify/aggregate kernels, D2H of the requested results, stream-synchronised on return.
+ * Replaces stage (C) "corpus scan" of SURVEY.md section 1 for one packed batch. */
+int tsm_scan(tsm_ctx* ctx, const tsm_corpus* corpus, tsm_result* result, uint32_t flags, void* stream);
+
+/* Resident path (what bench.py's `value` times): upload once, scan many times, fetch once. */
+int tsm_upload(tsm_ctx* ctx, const tsm_corpus* corpus, void* stream);
+int tsm_scan_resident(tsm_ctx* ctx, uint32_t flags, void* stream);       /* kernels only, async */
+int tsm_download(tsm_ctx* ctx, tsm_result* result, void* stream);        /* synchronises */
+/* Device address of the [n_groups+1][K] int64 count table of the last scan (row n_groups = global),
+ * for the single multi-GPU allreduce; valid until the next scan. */
+int tsm_device_counts(tsm_ctx* ctx, void** dptr, int64_t* n_int64);
+/* Kernel launches issued by the last tsm_scan / tsm_scan_resident call. */
+int tsm_last_launch_count(tsm_ctx* ctx);
+/* Device time (CUDA events on the launching stream) of the kernels of the last scan, in launch
+ * order: k_plan, k_scan, k_classify, k_totals.  Synchronises on the last of them. */
+int tsm_last_kernel_ms(tsm_ctx* ctx, float* ms4);
+/* Per-kernel device time summed over every scan since the last reset (event ring, no host sync
+ * inside a back-to-back series); waits for scans still in flight. */
+int tsm_kernel_ms_stats(tsm_ctx* ctx, double* sum_ms4, int64_t* n_scans, int reset);
+
+/* S8 revision-pair churn (Important-files/ML-Testing-v1.xlsx!projects:R1 `cloc, added, removed`):
+ * pair i = (olds file i, news file i); added/removed [n_pairs] host arrays. */
+int tsm_diff_pairs(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
+                   int64_t* added, int64_t* removed, void* stream);
+
+/* S10 reduce (RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/
+ * tests_methods_v2.csv): out[f*n_repos+r] = distinct case ids with flags[row*n_flags+f] != 0 in
+ * repo r; cases_per_repo[r] = distinct case ids of repo r. Host arrays; integer work on device. */
+int tsm_reduce(tsm_ctx* ctx, const uint8_t* flags, const int32_t* repo, const int32_t* case_id,
+               int32_t n_rows, int32_t n_flags, int32_t n_repos, int32_t n_cases,
+               int64_t* out, int64_t* cases_per_repo, void* stream);
+
+/* ---- host-only helpers (no CUDA context needed) ------------------------------------------- */
+/* Pinned host memory for arenas/results (cudaHostAlloc); returns NULL on failure. */
+void* tsm_host_alloc(int64_t bytes);
+void tsm_host_free(void* p);
+/* Arena size (multiple of TSM_ALIGN) for files of the given sizes; fills off[n+1]. <0 on overflow. */
+int64_t tsm_layout(const int32_t* len, int32_t n_files, int32_t* off);
+/* Deterministic synthetic corpus (std::mt19937_64, one engine per file).
+ * size_law 0: every file exactly fixed_size bytes; 1: truncated power law pdf ~ x^-1.5 on
+ * [128 B, 1 MiB] rounded up to whole lines.  Slot i holds logical file first_index + i*index_stride,
+ * so ranks generate disjoint round-robin shards of one logical corpus.  Two steps: tsm_gen_sizes
+ * -> tsm_layout -> tsm_gen_fill. */
+int tsm_gen_sizes(uint64_t seed, int32_t n_files, int size_law, int32_t fixed_size, int32_t first_index,
+                  int32_t index_stride, int32_t* len, uint8_t* ext, uint16_t* grp, int32_t n_groups);
+int tsm_gen_fill(uint64_t seed, int32_t n_files, int size_law, int32_t first_index, int32_t index_stride,
+                 const int32_t* off, const int32_t* len, const uint8_t* ext, uint8_t* arena);
+/* new = old with Poisson(lambda) line edits (insert/delete/replace of Geometric(0.4) runs). Returns
+ * bytes written to dst (<= cap) or <0. */
+int64_t tsm_gen_edit(uint64_t seed, const uint8_t* src, int32_t src_len, double lambda,
+                     uint8_t* dst, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,182 @@
+"""GPU parity tests: the sm_100a product path, through the C ABI, against the CPU oracle on the
+same seeded inputs.  Integer / byte work: the bar is bit-exact equality of every output."""
+import numpy as np
+import pytest
+
+import corpus_util as cu
+import orc
+import tosemscan as ts
+
+pytestmark = pytest.mark.gpu
+
+FLAGS = ts.SCAN_ASSERT_EVENTS | ts.SCAN_HEADER_EVENTS
+
+
+@pytest.fixture(scope="module")
+def scanner():
+    s = ts.Scanner(device=0, max_arena_bytes=1 << 28, max_files=1 << 18, max_groups=16)
+    yield s
+    s.close()
+
+
+def check_against_oracle(scanner, corpus, flags=FLAGS, resident=False):
+    want = orc.scan(corpus.arena, corpus.off, corpus.len, corpus.ext, corpus.grp, corpus.n_groups)
+    if resident:
+        scanner.upload(corpus)
+        scanner.scan_resident(flags)
+        got = scanner.download(flags)
+    else:
+        got = scanner.scan(corpus, flags)
+    for f in ("n_lines", "n_assert", "n_headers", "n_fixture", "digest"):
+        bad = np.nonzero(got["stats"][f] != want["stats"][f])[0]
+        assert bad.size == 0, (f, bad[:10], got["stats"][bad[:5]], want["stats"][bad[:5]],
+                               [corpus.len[i] for i in bad[:5]], [corpus.ext[i] for i in bad[:5]])
+    assert np.array_equal(got["group_counts"], want["group_counts"])
+    assert np.array_equal(got["global_counts"], want["global_counts"])
+    st = want["stats"]
+    assert got["totals"].tolist() == [int(st[k].astype(np.int64).sum()) for k in ("n_lines", "n_assert", "n_headers", "n_fixture")]
+    if flags & ts.SCAN_ASSERT_EVENTS:
+        a, b = got["assert_events"], want["assert_events"]
+        assert len(a) == len(b)
+        for f in a.dtype.names:
+            bad = np.nonzero(a[f] != b[f])[0]
+            assert bad.size == 0, (f, a[bad[:5]], b[bad[:5]])
+    if flags & ts.SCAN_HEADER_EVENTS:
+        a, b = got["header_events"], want["header_events"]
+        assert len(a) == len(b)
+        assert np.array_equal(a, b), (a[:5], b[:5])
+    return got
+
+
+def test_edge_cases(scanner):
+    files, exts, grps = cu.edge_corpus()
+    check_against_oracle(scanner, ts.pack(files, exts, grps, 3))
+
+
+def test_single_files_one_by_one(scanner):
+    """Each edge file alone (so that a failure names the file) and with every extension tag."""
+    files, exts, _ = cu.edge_corpus()
+    for i, f in enumerate(files):
+        for e in {int(exts[i]), 1, 2, 4}:
+            check_against_oracle(scanner, ts.pack([f], [e]))
+
+
+def test_empty_corpus_and_empty_files(scanner):
+    got = scanner.scan(ts.pack([], []), FLAGS)
+    assert got["totals"].tolist() == [0, 0, 0, 0] and got["global_counts"].sum() == 0
+    check_against_oracle(scanner, ts.pack([b""] * 70, [1] * 70))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_small_files(scanner, seed):
+    files, exts, grps = cu.fuzz_corpus(seed, 600, 3000)
+    check_against_oracle(scanner, ts.pack(files, exts, grps, 5))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_fuzz_multi_chunk_files_and_long_lines(scanner, seed):
+    files, exts, grps = cu.fuzz_corpus(seed, 150, 60000, long_lines=True)
+    check_against_oracle(scanner, ts.pack(files, exts, grps, 5))
+
+
+def test_chunk_edge_alignment_sweep(scanner):
+    """A statement sliding across the 4 KiB chunk edge and across the 240-byte look-ahead."""
+    files = []
+    for pad in list(range(4060, 4120)) + list(range(4096 + 200, 4096 + 260)) + [8180, 8192, 8200]:
+        files.append(b"x" * pad + b"\n  self.assertEqual(a, b)\nEXPECT_NEAR(q, r, 1e-3);\n" + b"y" * 300)
+        files.append(b"def test_a(self):\n" + b"z" * (pad - 18) + b" assert not q\r\n")
+    check_against_oracle(scanner, ts.pack(files, [1, 2] * (len(files) // 2)))
+
+
+def test_newline_storms(scanner):
+    """More lines per chunk than the 1024-entry line table holds (mid-chunk drains)."""
+    files = [b"\n" * 20000, b"a\n" * 9000, (b"assert x\n" + b"\n" * 700) * 9, b"\n" * 4096 + b"assert y", b"\r\n" * 5000]
+    check_against_oracle(scanner, ts.pack(files, [1, 2, 1, 4, 3]))
+
+
+def test_synthetic_c2_shape(scanner):
+    c = ts.gen_corpus(0x7053454D0002, 3000, size_law=0, fixed_size=4096, n_groups=9, pinned=True)
+    check_against_oracle(scanner, c)
+    check_against_oracle(scanner, c, flags=0, resident=True)
+
+
+def test_synthetic_c4_zipf_shape(scanner):
+    c = ts.gen_corpus(0x7053454D0004, 2500, size_law=1, n_groups=9, pinned=True)
+    assert c.len.max() > 100000
+    check_against_oracle(scanner, c)
+
+
+def test_resident_rescans_are_identical_and_launch_count(scanner):
+    c = ts.gen_corpus(5, 1500, 0, 4096, n_groups=4)
+    scanner.upload(c)
+    outs = []
+    for _ in range(3):
+        scanner.scan_resident(0)
+        outs.append(scanner.download(0))
+    assert scanner.last_launch_count() == 4
+    for o in outs[1:]:
+        assert np.array_equal(o["stats"], outs[0]["stats"]) and np.array_equal(o["group_counts"], outs[0]["group_counts"])
+    ms = scanner.last_kernel_ms()
+    assert len(ms) == 4 and all(m >= 0 for m in ms)
+
+
+def test_shards_add_up_to_the_whole(scanner):
+    """Size-independent property used at full scale: counts of round-robin shards sum to the whole."""
+    n, w = 4000, 4
+    whole = scanner.scan(ts.gen_corpus(9, n, 0, 4096, n_groups=9))
+    acc = np.zeros_like(whole["group_counts"])
+    dig = np.uint64(0)
+    for r in range(w):
+        part = scanner.scan(ts.gen_corpus(9, n // w, 0, 4096, first_index=r, index_stride=w, n_groups=9))
+        acc += part["group_counts"]
+        dig ^= np.bitwise_xor.reduce(part["stats"]["digest"])
+    assert np.array_equal(acc, whole["group_counts"])
+    assert dig == np.bitwise_xor.reduce(whole["stats"]["digest"])
+
+
+def test_full_size_c2_properties(scanner):
+    """BASELINE config C2 at full size (100k x 4 KiB): oracle-free invariants + a sampled oracle check."""
+    big = ts.Scanner(device=0, max_arena_bytes=100000 * 4096 + 4096, max_files=100000, max_groups=16)
+    c = ts.gen_corpus(0x7053454D0002, 100000, 0, 4096, n_groups=9)
+    got = big.scan(c, 0)
+    st = got["stats"]
+    assert got["totals"].tolist() == [int(st[k].astype(np.int64).sum()) for k in ("n_lines", "n_assert", "n_headers", "n_fixture")]
+    assert int(got["global_counts"].sum()) == got["totals"][1]
+    assert np.array_equal(got["group_counts"].sum(axis=0), got["global_counts"])
+    for g in range(9):
+        assert int(got["group_counts"][g].sum()) == int(st["n_assert"][c.grp == g].astype(np.int64).sum())
+    # sampled files against the oracle
+    idx = np.arange(0, 100000, 97)
+    sub = ts.pack([c.file_bytes(int(i)) for i in idx], c.ext[idx], c.grp[idx], 9)
+    want = orc.scan(sub.arena, sub.off, sub.len, sub.ext, sub.grp, 9, events=False)
+    assert np.array_equal(st[idx], want["stats"])
+    big.close()
+
+
+def test_reduce_matches_oracle_and_golden(scanner):
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g3_reduce.npz"))
+    n_cases = int(d["case_id"].max()) + 1
+    out, cpr = scanner.reduce(d["flags"], d["repo"], d["case_id"], len(d["repo_names"]), n_cases)
+    assert np.array_equal(out, d["oracle_distinct"]) and np.array_equal(cpr, d["oracle_cases_per_repo"])
+    rng = np.random.default_rng(3)
+    for rows, nf, nr, nc in [(0, 3, 2, 5), (1, 1, 1, 1), (5000, 40, 7, 3000), (20000, 5, 3, 40000)]:
+        flags = (rng.random((rows, nf)) < 0.2).astype(np.uint8)
+        repo = rng.integers(0, nr, rows).astype(np.int32)
+        case = rng.integers(0, nc, rows).astype(np.int32)
+        o1, c1 = scanner.reduce(flags, repo, case, nr, nc)
+        o2, c2 = orc.reduce(flags, repo, case, nr, nc)
+        assert np.array_equal(o1, o2) and np.array_equal(c1, c2)
+
+
+def test_errors_are_reported_not_swallowed(scanner):
+    c = ts.pack([b"assert x\n"], [1])
+    bad = ts.Corpus(c.arena, np.array([64, 128], np.int32), c.len, c.ext)
+    with pytest.raises(ts.TsmError) as e:
+        scanner.scan(bad)
+    assert e.value.status == -2
+    small = ts.Scanner(device=0, max_arena_bytes=4096, max_files=4, max_groups=1)
+    with pytest.raises(ts.TsmError) as e:
+        small.scan(ts.pack([b"x" * 9000], [1]))
+    assert e.value.status == -3
+    small.close()

@@ -1,0 +1,219 @@
+"""CPU tests: the oracle against the reference's golden vectors and against independent
+pure-Python restatements of docs/SPEC.md (no GPU needed)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import corpus_util as cu
+import orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+M61 = (1 << 61) - 1
+MASK = (1 << 64) - 1
+
+
+def py_bytes_hash(b: bytes) -> int:
+    """SPEC section 3 with Python big integers."""
+    h = int.from_bytes(b, "little") % M61
+    x = h ^ ((len(b) * 0x9E3779B97F4A7C15) & MASK)
+    x ^= x >> 30
+    x = (x * 0xBF58476D1CE4E5B9) & MASK
+    x ^= x >> 27
+    x = (x * 0x94D049BB133111EB) & MASK
+    x ^= x >> 31
+    return x
+
+
+def py_lines(data: bytes):
+    """SPEC section 2."""
+    if not data:
+        return []
+    parts = data.split(b"\n")
+    if parts[-1] == b"":
+        parts.pop()
+    return parts
+
+
+def test_hash_matches_bigint_definition():
+    rng = random.Random(1)
+    cases = [b"", b"\x00", b"\x00\x00", b"a", b"\xff" * 61, b"\xff" * 122, bytes(range(256)),
+             b"x" * 8, b"x" * 7, b"x" * 9, b"\xff" * 7 + b"\x1f"]
+    cases += [bytes(rng.randrange(256) for _ in range(rng.randrange(0, 300))) for _ in range(300)]
+    for c in cases:
+        assert orc.bytes_hash(c) == py_bytes_hash(c), c
+    assert orc.line_hash(b"abc\r") == py_bytes_hash(b"abc")
+    assert orc.line_hash(b"abc\r\r") == py_bytes_hash(b"abc\r")
+    assert orc.line_hash(b"\r") == py_bytes_hash(b"")
+    # the modulus value itself must canonicalise to 0
+    assert orc.bytes_hash(b"\xff" * 7 + b"\x1f") == py_bytes_hash(b"\xff" * 7 + b"\x1f")
+
+
+def test_line_splitting_and_counts():
+    for data, want in [(b"", 0), (b"a\n", 1), (b"a\nb", 2), (b"\n\n", 2), (b"\n", 1), (b"a", 1), (b"\r\n", 1)]:
+        arena, off, ln = orc.pack([data])
+        res = orc.scan(arena, off, ln, np.array([1], np.uint8), np.array([0], np.uint16), 1, line_hashes=True)
+        assert res["stats"]["n_lines"][0] == want == len(py_lines(data))
+        assert [int(h) for h in res["line_hash"]] == [py_bytes_hash(l[:-1] if l.endswith(b"\r") else l) for l in py_lines(data)]
+        assert int(res["stats"]["digest"][0]) == sum(int(h) for h in res["line_hash"]) & MASK
+
+
+def test_g4_statement_category_golden():
+    """Golden G4: every (statement, category) pair of the five Rev-A sheets of ML-Testing-v1.xlsx."""
+    rows = json.load(open(os.path.join(GOLD, "g4_statement_category.json")))
+    ledger = json.load(open(os.path.join(GOLD, "ledger.json")))["G4"]
+    known_misses = {(m["statement"], m["sheet_says"]) for m in ledger["misses"]}
+    hit = tot = 0
+    for r in rows:
+        st = r["statement"].encode("utf-8")
+        # S4: statements are already truncated and stripped
+        assert orc.statement(st) == st
+        got = orc.category_string(st)
+        tot += r["rows"]
+        if got == r["category"]:
+            hit += r["rows"]
+        else:
+            assert (r["statement"], r["category"]) in known_misses, (r, got)
+    assert [hit, tot] == ledger["category_rule_rows"] == [11954, 11981]
+
+
+def test_classify_rules():
+    name = orc.category_string
+    assert name(b"EXPECT_EQ") == "assertEqual" and name(b"ASSERT_NEAR") == "assertAlmostEqual"
+    assert name(b"EXPECT_STREQ") == "" and name(b"EXPECT_") == "" and name(b"else ASSERT_EQ") == "assertEqual"
+    assert name(b"EXPECT_THROW") == "assertRaises" and name(b"EXPECT_DOUBLE_EQ") == "assertDoubleEqual"
+    assert name(b"assert") == "assertTrue" and name(b"assert agent") == "assertTrue"
+    assert name(b"assert not agent.no_pull") == "assertNotEqual"
+    assert name(b'assert "Schedule not found" in str') == "assertFalse"
+    assert name(b'assert result == 0, "Repo did not pass Black formatting!"') == "assertEqual"
+    assert name(b"assert x is not None") == "assertFalse"
+    assert name(b"assert res.mapped == True") == "assertTrue"
+    assert name(b"assert a <= b") == "assertLessEqual" and name(b"assert a >= b") == "assertGreaterEqual"
+    assert name(b"assert a < b") == "assertLess" and name(b"assert a > b") == "assertGreater"
+    assert name(b"assert a != b") == "assertNotEqual"
+    assert name(b"self.assertEquals") == "assertEquals" and name(b"self.assert_") == "assertTrue"
+    assert name(b"self.assertWeirdCustomThing") == "assertWeirdCustomThing"
+    assert orc.classify(b"self.assertWeirdCustomThing")[0] == 127
+    assert name(b"x.assert_called_once_with") == "assert_called_once_with"
+    assert name(b"if") == "" and name(b"GPUAssert") == "" and name(b"") == "" and name(b'"""') == ""
+    assert name(b"assert\tx") == "" and name(b"assertx") == "assertx"
+    # every table name maps to its own id
+    for i in range(1, 127):
+        nm = orc.category_name(i)
+        if nm:
+            assert orc.classify(b"self." + nm.encode())[0] == i
+
+
+def test_statement_truncation():
+    assert orc.statement(b"   self.assertEqual(a, b)  ") == b"self.assertEqual"
+    assert orc.statement(b"\tassert sys.version_info >= (3, 6)\r") == b"assert sys.version_info >="
+    assert orc.statement(b"assert x") == b"assert x"
+    assert orc.statement(b"(assert)") == b""
+    assert orc.statement(b"   ") == b""
+
+
+def test_header_rules_and_method_strings():
+    hk, ms = orc.header_kind, orc.method_string
+    # PY (SPEC section 5)
+    assert hk(1, b"    def test_docker_agent_init(monkeypatch, runner_token):") == 1
+    assert ms(1, b"    def test_docker_agent_init(monkeypatch, runner_token):") == b"test_docker_agent_init(monkeypatch,runner_token)"
+    assert ms(1, b"def test_training_pipeline(config: Config, model_type: str, car_dir: str) \\") == \
+        b"test_training_pipeline(config:Config,model_type:str,car_dir:str)\\"
+    assert hk(1, b"parser.add_argument('-t', '--tested-skills', default=[])") == 1
+    assert ms(1, b"parser.add_argument('-t', '--tested-skills', default=[])") == b"parser.add_argument('-t','--tested-skills',ault=[])"
+    assert hk(1, b"class SkillTest(object):") == 1 and ms(1, b"class SkillTest(object):") == b"SkillTest(object)"
+    assert hk(1, b"classifier = 3") == 0 and hk(1, b"x = class Foo") == 0 and hk(1, b"class\tT:") == 1
+    assert ms(1, b"    async def test_x(self):") == b"asynctest_x(self)"
+    # C family
+    assert hk(2, b'      : sensor1_dst_("test"), sensor2_dst_("test"), fused_dst_("test") {') == 1
+    assert ms(2, b'      : sensor1_dst_("test"), sensor2_dst_("test"), fused_dst_("test") {') == b': sensor1_dst_("test"'
+    assert hk(2, b'    dst_manager->AddApp("test", fod_subsets, fod_subset_names);') == 0
+    assert hk(2, b"  ~DSTEvidenceTest() {}") == 1 and ms(2, b"  ~DSTEvidenceTest() {}") == b"~DSTEvidenceTest("
+    assert hk(2, b"TEST_F(DsmTest, Invalid) {") == 3 and ms(2, b"TEST_F(DsmTest, Invalid) {") == b"TEST_F(DsmTest, Invalid"
+    assert hk(2, b"  TEST_F(DsmTest, Invalid) {") == 3
+    assert ms(3, b"class NavigationLaneTest : public testing::Test {") == b"class NavigationLaneTest : public testing::Test"
+    assert hk(2, b"  void CreateTestMapNode(unsigned int m, unsigned int n,") == 1
+    assert hk(2, b'  EXPECT_EQ(latest_observed_msg_ptr->class_name(), "BlockerTest");') == 1
+    assert hk(2, b"for (int i = 0; i < n; ++i) {") == 0
+    assert hk(0, b"TEST_F(A, B) {") == 0
+    # Java
+    assert ms(4, b"    public void testFactory() throws Exception {") == b"testFactory()throwsException{"
+    assert ms(4, b"public class MapDecodeTest {") == b"MapDecodeTest{"
+    assert ms(4, b"  @Test public void testDoubleInitialize() throws Exception {") == b"@TesttestDoubleInitialize()throwsException{"
+
+
+def test_g3_reduce_golden():
+    """Golden G3: RQs/taxonomy_test2.csv -> tests_strategy_rq32.csv / tests_methods_v2.csv."""
+    d = np.load(os.path.join(GOLD, "g3_reduce.npz"))
+    out, cpr = orc.reduce(d["flags"], d["repo"], d["case_id"], len(d["repo_names"]), int(d["case_id"].max()) + 1)
+    assert np.array_equal(out, d["oracle_distinct"]) and np.array_equal(cpr, d["oracle_cases_per_repo"])
+    assert cpr.tolist() == [181, 164, 142, 160, 124, 100, 90, 216, 273] and cpr.sum() == 1450
+    ok = d["strategy_cell_reproduces"]
+    assert int(ok.sum()) == 162 and ok.size == 171
+    # re-derive the shipped cells (rounded twice: SPEC section 9) wherever the ledger says they reproduce
+    for j in range(ok.shape[0]):
+        for k in range(ok.shape[1]):
+            if ok[j, k]:
+                v = round(round(100.0 * out[j, k] / cpr[k], 4) / 1.1, 4)
+                s = ("%.4f" % v).rstrip("0").rstrip(".") or "0"
+                assert s == str(d["want_strategy_cells"][j][k])
+    ns = ok.shape[0]
+    tot = out[ns:].sum(axis=1)
+    rep = d["method_reproduces"].astype(bool)
+    assert np.array_equal(tot[rep], d["want_method_total_cases"][rep]) and int(rep.sum()) == 11
+
+
+def test_lcs_oracle_against_bruteforce():
+    rng = random.Random(7)
+
+    def brute(a, b):
+        dp = [[0] * (len(b) + 1) for _ in range(len(a) + 1)]
+        for i in range(len(a)):
+            for j in range(len(b)):
+                dp[i + 1][j + 1] = dp[i][j] + 1 if a[i] == b[j] else max(dp[i][j + 1], dp[i + 1][j])
+        return dp[-1][-1]
+    for _ in range(200):
+        a = [rng.randrange(6) for _ in range(rng.randrange(0, 30))]
+        b = [rng.randrange(6) for _ in range(rng.randrange(0, 30))]
+        assert orc.lcs(np.array(a, np.uint64), np.array(b, np.uint64)) == brute(a, b)
+
+
+def test_scan_on_edge_corpus_matches_python_restatement():
+    files, exts, grps = cu.edge_corpus()
+    arena, off, ln = orc.pack(files)
+    res = orc.scan(arena, off, ln, exts, grps, 3)
+    for i, f in enumerate(files):
+        lines = py_lines(f)
+        st = res["stats"][i]
+        assert st["n_lines"] == len(lines)
+        if exts[i]:
+            want = sum(1 for l in lines if b"assert" in l.lower() or b"EXPECT_" in l)
+            assert st["n_assert"] == want, (i, f[:40])
+        else:
+            assert st["n_assert"] == 0 and st["n_headers"] == 0
+    ev = res["assert_events"]
+    assert len(ev) == int(res["stats"]["n_assert"].sum()) == int(res["global_counts"].sum())
+    assert np.array_equal(res["group_counts"].sum(axis=0), res["global_counts"])
+    # events are in canonical order and their statement hash is the hash of the statement bytes
+    key = ev["file"].astype(np.int64) << 32 | ev["line_off"]
+    assert np.all(np.diff(key) > 0)
+    for e in ev[:200]:
+        f = files[e["file"]]
+        t = f[e["stmt_off"]:e["stmt_off"] + e["stmt_len"]]
+        assert int(e["stmt_hash"]) == py_bytes_hash(t)
+        assert orc.classify(t)[0] == e["cat"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference corpus not present (GPU box)")
+def test_c1_bundled_corpus_summary_is_stable():
+    """Config C1: the oracle over the bundled corpus reproduces the committed summary."""
+    import subprocess
+    import sys
+    want = json.load(open(os.path.join(GOLD, "c1_summary.json")))
+    assert want["n_files"] == 1779 and want["bytes"] == 10552416
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "make_golden.py"), "--check-c1"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]

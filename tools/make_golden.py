@@ -268,7 +268,7 @@ def golden_g3(ledger):
     print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok))
 
 
-def c1_summary(ledger):
+def c1_summary(ledger, write=True):
     """Config C1: the oracle over the bundled corpus (test files with a scannable extension)."""
     root = os.path.join(REF, "src")
     projects = sorted(os.listdir(root))
@@ -300,6 +300,8 @@ def c1_summary(ledger):
             "digest_xor": "%016x" % int(np.bitwise_xor.reduce(st["digest"])),
             "global_counts": {orc.category_name(i) or "''": int(c) for i, c in enumerate(res["global_counts"]) if c},
             "per_project_assert": {p: int(res["group_counts"][g].sum()) for g, p in enumerate(projects)}}
+    if not write:
+        return summ
     json.dump(summ, open(os.path.join(OUT, "c1_summary.json"), "w"), indent=1)
     ledger["C1"] = {"source": "src/** (test-path files with extension py/cc/cpp/java/c/h)",
                     "n_files": summ["n_files"], "bytes": summ["bytes"], "n_lines": summ["n_lines"],
@@ -310,6 +312,13 @@ def c1_summary(ledger):
 
 
 def main():
+    if "--check-c1" in sys.argv:   # recompute config C1 and compare with the committed summary
+        want = json.load(open(os.path.join(OUT, "c1_summary.json")))
+        got = json.loads(json.dumps(c1_summary({}, write=False)))
+        if got != want:
+            print("C1 summary differs", {k: (want.get(k), got.get(k)) for k in got if got.get(k) != want.get(k)})
+            sys.exit(1)
+        return
     os.makedirs(OUT, exist_ok=True)
     ledger = {"made_by": "tools/make_golden.py", "reference": "openjamoses/TOSEM-2021-Replication"}
     v1 = read_xlsx(os.path.join(REF, "Important-files/ML-Testing-v1.xlsx"), only=set(REV_A) | {"DeepSpeech"})

@@ -1,0 +1,413 @@
+// tsm_api.cu - the extern "C" boundary of libtosemscan.so (include/tosemscan.h): context, device
+// memory, H2D/D2H staging and kernel launches.  No torch types, no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "tsm_device.cuh"
+
+#include "tsm_scan_kernels.cuh"
+#include "tsm_reduce_kernels.cuh"
+#include "tsm_diff_kernels.cuh"
+
+using namespace tsm;
+
+static const char* const kNames[TSM_K] = TSM_CAT_NAMES_INIT;
+
+struct tsm_ctx {
+  int device = 0;
+  int sms = 0;
+  int64_t max_arena = 0;
+  int32_t max_files = 0, max_groups = 0;
+  int64_t max_events = 0;
+  // device buffers
+  uint8_t* d_arena = nullptr;
+  int32_t* d_off = nullptr;
+  int32_t* d_len = nullptr;
+  uint8_t* d_ext = nullptr;
+  uint16_t* d_grp = nullptr;
+  uint32_t* d_unit_file = nullptr;
+  uint32_t* d_unit_begin = nullptr;
+  uint32_t unit_cap = 0;
+  Ctrl* d_ctrl = nullptr;
+  tsm_file_stat* d_stats = nullptr;
+  unsigned long long* d_cand = nullptr;
+  tsm_header_event* d_hev = nullptr;
+  tsm_assert_event* d_aev = nullptr;
+  unsigned long long* d_counts = nullptr;   // [(max_groups + 1) * K + 4]
+  Ctrl* h_ctrl = nullptr;                   // pinned
+  // resident corpus
+  bool resident = false, scanned = false;
+  int32_t n_files = 0, n_groups = 1;
+  int64_t arena_bytes = 0;
+  uint32_t last_flags = 0;
+  int launches = 0;
+  // CUDA events around the 4 scan kernels: a ring of sets so that back-to-back scans can be timed
+  // per kernel without a host sync inside the timed region.
+  static constexpr int kRing = 32;
+  cudaEvent_t ev[kRing][5] = {};
+  bool ev_used[kRing] = {};
+  int ev_next = 0, ev_last = -1;
+  double ms_sum[4] = {0, 0, 0, 0};
+  long long ms_n = 0;
+};
+
+// Fold the elapsed times of event set `i` into the running sums (waits for it if still in flight).
+static void fold_events(tsm_ctx* c, int i) {
+  if (!c->ev_used[i]) return;
+  if (cudaEventSynchronize(c->ev[i][4]) == cudaSuccess) {
+    float ms;
+    bool ok = true;
+    float t[4];
+    for (int k = 0; k < 4; ++k) { ok &= cudaEventElapsedTime(&ms, c->ev[i][k], c->ev[i][k + 1]) == cudaSuccess; t[k] = ms; }
+    if (ok) { for (int k = 0; k < 4; ++k) c->ms_sum[k] += t[k]; c->ms_n++; }
+  }
+  c->ev_used[i] = false;
+}
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "tosemscan: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return TSM_E_CUDA; } } while (0)
+
+extern "C" int tsm_abi_version(void) { return TSM_ABI_VERSION; }
+
+extern "C" const char* tsm_strerror(int s) {
+  switch (s) {
+    case TSM_OK: return "ok";
+    case TSM_E_ARG: return "bad argument";
+    case TSM_E_LAYOUT: return "corpus violates the arena layout (docs/SPEC.md section 1)";
+    case TSM_E_CAPACITY: return "corpus or event list exceeds the context capacity";
+    case TSM_E_CUDA: return "CUDA error (no device, allocation or launch failure)";
+    case TSM_E_NOMEM: return "out of host memory";
+    case TSM_E_STATE: return "call out of order";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* tsm_category_name(int id) {
+  if (id == TSM_CAT_OTHER) return "<other>";
+  if (id < 0 || id >= TSM_CAT_NAMED) return "";
+  return kNames[id];
+}
+
+static void build_lut(uint32_t* lut) {
+  struct Pat { const char* s; int first; bool ci; };
+  static const Pat pats[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"test", 13, true}, {"def", 17, false},
+                             {"class", 20, false}, {"void", 25, false}, {"{", 29, false}};
+  memset(lut, 0, 256 * sizeof(uint32_t));
+  for (const Pat& p : pats)
+    for (int k = 0; p.s[k]; ++k) {
+      const unsigned char c = (unsigned char)p.s[k];
+      lut[c] |= 1u << (p.first + k);
+      if (p.ci && c >= 'a' && c <= 'z') lut[c - 32] |= 1u << (p.first + k);
+    }
+}
+
+extern "C" void tsm_destroy(tsm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_arena); cudaFree(c->d_off); cudaFree(c->d_len); cudaFree(c->d_ext); cudaFree(c->d_grp);
+  cudaFree(c->d_unit_file); cudaFree(c->d_unit_begin); cudaFree(c->d_ctrl); cudaFree(c->d_stats);
+  cudaFree(c->d_cand); cudaFree(c->d_hev); cudaFree(c->d_aev); cudaFree(c->d_counts);
+  if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
+  for (auto& set : c->ev) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
+  delete c;
+}
+
+extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, int32_t max_files,
+                          int32_t max_groups, int64_t max_events) {
+  if (!out || max_arena_bytes <= 0 || max_arena_bytes >= (1ll << 31) || max_files <= 0 || max_groups <= 0)
+    return TSM_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    fprintf(stderr, "tosemscan: no usable CUDA device %d (there is no CPU fallback)\n", device);
+    return TSM_E_CUDA;
+  }
+  CU(cudaSetDevice(device));
+  tsm_ctx* c = new (std::nothrow) tsm_ctx;
+  if (!c) return TSM_E_NOMEM;
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sms = prop.multiProcessorCount;
+  c->max_arena = (max_arena_bytes + 127) / 128 * 128;
+  c->max_files = max_files;
+  c->max_groups = max_groups;
+  c->max_events = max_events > 0 ? max_events : c->max_arena / 32 + max_files;
+  if (c->max_events > 0xFFFFFFF0ll) c->max_events = 0xFFFFFFF0ll;
+  c->unit_cap = (uint32_t)(c->max_arena / CH + max_files);
+  int rc = TSM_OK;
+  auto A = [&](void** p, size_t bytes) { if (rc == TSM_OK && cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) rc = TSM_E_CUDA; };
+  A((void**)&c->d_arena, (size_t)c->max_arena + 4096);   // slack: bulk copies round sizes up to 16 B
+  A((void**)&c->d_off, sizeof(int32_t) * ((size_t)max_files + 1));
+  A((void**)&c->d_len, sizeof(int32_t) * (size_t)max_files);
+  A((void**)&c->d_ext, (size_t)max_files);
+  A((void**)&c->d_grp, sizeof(uint16_t) * (size_t)max_files);
+  A((void**)&c->d_unit_file, sizeof(uint32_t) * (size_t)c->unit_cap);
+  A((void**)&c->d_unit_begin, sizeof(uint32_t) * (size_t)c->unit_cap);
+  A((void**)&c->d_ctrl, sizeof(Ctrl));
+  A((void**)&c->d_stats, sizeof(tsm_file_stat) * (size_t)max_files);
+  A((void**)&c->d_cand, sizeof(unsigned long long) * (size_t)c->max_events);
+  A((void**)&c->d_counts, sizeof(unsigned long long) * ((size_t)(max_groups + 1) * TSM_K + 4));
+  if (rc == TSM_OK && cudaHostAlloc((void**)&c->h_ctrl, sizeof(Ctrl) + 64, cudaHostAllocDefault) != cudaSuccess) rc = TSM_E_CUDA;
+  for (auto& set : c->ev) for (cudaEvent_t& e : set) if (rc == TSM_OK && cudaEventCreate(&e) != cudaSuccess) rc = TSM_E_CUDA;
+  if (rc == TSM_OK) {
+    uint32_t lut[256];
+    build_lut(lut);
+    static const uint8_t slot[TSM_CAT_SLOTS] = TSM_CAT_SLOT_INIT;
+    static const uint16_t offs[TSM_CAT_NAMED + 1] = TSM_CAT_OFF_INIT;
+    static const char blob[] = TSM_CAT_BLOB_INIT;
+    if (cudaMemcpyToSymbol(c_lut, lut, sizeof lut) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_cat_slot, slot, sizeof slot) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_cat_off, offs, sizeof offs) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_cat_blob, blob, TSM_CAT_BLOB_LEN + 1) != cudaSuccess ||
+        cudaMemset(c->d_arena, 0, (size_t)c->max_arena + 4096) != cudaSuccess ||
+        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) != cudaSuccess)
+      rc = TSM_E_CUDA;
+  }
+  if (rc != TSM_OK) {
+    fprintf(stderr, "tosemscan: tsm_create failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    tsm_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return TSM_OK;
+}
+
+static int check_corpus(const tsm_ctx* c, const tsm_corpus* k) {
+  if (!k || k->n_files < 0 || k->n_groups < 1 || (k->n_files > 0 && (!k->arena || !k->off || !k->len || !k->ext)))
+    return TSM_E_ARG;
+  if (k->n_files > c->max_files || k->n_groups > c->max_groups) return TSM_E_CAPACITY;
+  if (k->n_files == 0) return TSM_OK;
+  int64_t prev_end = 0;
+  for (int32_t i = 0; i < k->n_files; ++i) {
+    const int64_t o = k->off[i], l = k->len[i];
+    if (o < prev_end || (o & (TSM_ALIGN - 1)) || l < 0 || o + l > (int64_t)k->off[i + 1]) return TSM_E_LAYOUT;
+    if (k->grp && k->grp[i] >= k->n_groups) return TSM_E_LAYOUT;
+    if (k->ext[i] > TSM_EXT_H) return TSM_E_LAYOUT;
+    prev_end = o + l;
+  }
+  const int64_t total = k->off[k->n_files];
+  if (total & (TSM_ALIGN - 1)) return TSM_E_LAYOUT;
+  if (total > c->max_arena) return TSM_E_CAPACITY;
+  return TSM_OK;
+}
+
+extern "C" int tsm_upload(tsm_ctx* c, const tsm_corpus* k, void* stream) {
+  if (!c) return TSM_E_ARG;
+  int rc = check_corpus(c, k);
+  if (rc != TSM_OK) return rc;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t n = k->n_files;
+  c->n_files = n;
+  c->n_groups = k->n_groups;
+  c->arena_bytes = n ? k->off[n] : 0;
+  if (n) {
+    CU(cudaMemcpyAsync(c->d_arena, k->arena, (size_t)c->arena_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_off, k->off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_len, k->len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_ext, k->ext, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (k->grp) CU(cudaMemcpyAsync(c->d_grp, k->grp, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(c->d_grp, 0, sizeof(uint16_t) * (size_t)n, st));
+  }
+  c->resident = true;
+  c->scanned = false;
+  return TSM_OK;
+}
+
+static int ensure_event_buffers(tsm_ctx* c, uint32_t flags) {
+  if ((flags & TSM_SCAN_ASSERT_EVENTS) && !c->d_aev)
+    CU(cudaMalloc((void**)&c->d_aev, sizeof(tsm_assert_event) * (size_t)c->max_events));
+  if ((flags & TSM_SCAN_HEADER_EVENTS) && !c->d_hev)
+    CU(cudaMalloc((void**)&c->d_hev, sizeof(tsm_header_event) * (size_t)c->max_events));
+  return TSM_OK;
+}
+
+static ScanParams make_params(const tsm_ctx* c, uint32_t flags) {
+  ScanParams p;
+  p.arena = c->d_arena; p.off = c->d_off; p.len = c->d_len; p.ext = c->d_ext; p.grp = c->d_grp;
+  p.n_files = c->n_files; p.n_groups = c->n_groups;
+  p.unit_file = c->d_unit_file; p.unit_begin = c->d_unit_begin; p.unit_cap = c->unit_cap;
+  p.ctrl = c->d_ctrl; p.stats = c->d_stats;
+  p.cand = c->d_cand; p.cand_cap = (uint32_t)c->max_events;
+  p.hev = c->d_hev; p.hev_cap = (uint32_t)c->max_events;
+  p.aev = c->d_aev; p.aev_cap = (uint32_t)c->max_events;
+  p.counts = c->d_counts; p.flags = flags;
+  return p;
+}
+
+extern "C" int tsm_scan_resident(tsm_ctx* c, uint32_t flags, void* stream) {
+  if (!c) return TSM_E_ARG;
+  if (!c->resident) return TSM_E_STATE;
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_event_buffers(c, flags);
+  if (rc != TSM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ScanParams p = make_params(c, flags);
+  const int n = c->n_files;
+  c->launches = 0;
+  CU(cudaMemsetAsync(c->d_ctrl, 0, sizeof(Ctrl), st));
+  CU(cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned long long) * ((size_t)(c->n_groups + 1) * TSM_K + 4), st));
+  if (n) {
+    CU(cudaMemsetAsync(c->d_stats, 0, sizeof(tsm_file_stat) * (size_t)n, st));
+    const int es = c->ev_next;
+    c->ev_next = (es + 1) % tsm_ctx::kRing;
+    fold_events(c, es);                                  // only blocks when 32 scans are in flight
+    cudaEvent_t* ev = c->ev[es];
+    cudaEventRecord(ev[0], st);
+    k_plan<<<(n + 255) / 256, 256, 0, st>>>(p);
+    cudaEventRecord(ev[1], st);
+    k_scan<<<c->sms * 4, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
+    cudaEventRecord(ev[2], st);
+    const size_t hist = c->n_groups <= 16 ? sizeof(uint32_t) * (size_t)c->n_groups * TSM_K : 0;
+    k_classify<<<c->sms * 8, 256, hist, st>>>(p);
+    cudaEventRecord(ev[3], st);
+    k_totals<<<std::min((n + 255) / 256, c->sms * 4), 256, 0, st>>>(p);
+    cudaEventRecord(ev[4], st);
+    c->ev_used[es] = true;
+    c->ev_last = es;
+    c->launches = 4;
+    CU(cudaGetLastError());
+  }
+  c->last_flags = flags;
+  c->scanned = true;
+  return TSM_OK;
+}
+
+extern "C" int tsm_device_counts(tsm_ctx* c, void** dptr, int64_t* n_int64) {
+  if (!c || !dptr || !n_int64) return TSM_E_ARG;
+  if (!c->scanned) return TSM_E_STATE;
+  *dptr = c->d_counts;
+  *n_int64 = (int64_t)(c->n_groups + 1) * TSM_K + 4;
+  return TSM_OK;
+}
+
+extern "C" int tsm_last_launch_count(tsm_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int tsm_last_kernel_ms(tsm_ctx* c, float* ms4) {
+  if (!c || !ms4) return TSM_E_ARG;
+  if (!c->scanned || c->n_files == 0 || c->ev_last < 0) return TSM_E_STATE;
+  CU(cudaSetDevice(c->device));
+  cudaEvent_t* ev = c->ev[c->ev_last];
+  CU(cudaEventSynchronize(ev[4]));
+  for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms4[i], ev[i], ev[i + 1]));
+  return TSM_OK;
+}
+
+extern "C" int tsm_kernel_ms_stats(tsm_ctx* c, double* sum_ms4, int64_t* n_scans, int reset) {
+  if (!c) return TSM_E_ARG;
+  CU(cudaSetDevice(c->device));
+  for (int i = 0; i < tsm_ctx::kRing; ++i) fold_events(c, i);
+  if (sum_ms4) for (int k = 0; k < 4; ++k) sum_ms4[k] = c->ms_sum[k];
+  if (n_scans) *n_scans = c->ms_n;
+  if (reset) { for (double& v : c->ms_sum) v = 0; c->ms_n = 0; }
+  return TSM_OK;
+}
+
+extern "C" int tsm_download(tsm_ctx* c, tsm_result* r, void* stream) {
+  if (!c || !r) return TSM_E_ARG;
+  if (!c->scanned) return TSM_E_STATE;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = c->n_files, G = c->n_groups;
+  unsigned long long* h_tot = reinterpret_cast<unsigned long long*>(c->h_ctrl + 1);   // pinned tail
+  CU(cudaMemcpyAsync(c->h_ctrl, c->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_tot, c->d_counts + (size_t)(G + 1) * TSM_K, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (r->stats && n) CU(cudaMemcpyAsync(r->stats, c->d_stats, sizeof(tsm_file_stat) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (r->group_counts) CU(cudaMemcpyAsync(r->group_counts, c->d_counts, sizeof(int64_t) * (size_t)G * TSM_K, cudaMemcpyDeviceToHost, st));
+  if (r->global_counts) CU(cudaMemcpyAsync(r->global_counts, c->d_counts + (size_t)G * TSM_K, sizeof(int64_t) * TSM_K, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < 4; ++i) r->totals[i] = (int64_t)h_tot[i];
+  r->n_aev = 0; r->n_hev = 0;
+  if (c->h_ctrl->overflow) return TSM_E_CAPACITY;
+  if ((c->last_flags & TSM_SCAN_ASSERT_EVENTS) && r->aev) {
+    const int64_t m = c->h_ctrl->n_aev;
+    if (m > r->aev_cap) { r->n_aev = m; return TSM_E_CAPACITY; }
+    CU(cudaMemcpyAsync(r->aev, c->d_aev, sizeof(tsm_assert_event) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::sort(r->aev, r->aev + m, [](const tsm_assert_event& a, const tsm_assert_event& b) {
+      return a.file != b.file ? a.file < b.file : a.line_off < b.line_off; });
+    r->n_aev = m;
+  } else if (c->last_flags & TSM_SCAN_ASSERT_EVENTS) r->n_aev = c->h_ctrl->n_aev;
+  if ((c->last_flags & TSM_SCAN_HEADER_EVENTS) && r->hev) {
+    const int64_t m = c->h_ctrl->n_hev;
+    if (m > r->hev_cap) { r->n_hev = m; return TSM_E_CAPACITY; }
+    CU(cudaMemcpyAsync(r->hev, c->d_hev, sizeof(tsm_header_event) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::sort(r->hev, r->hev + m, [](const tsm_header_event& a, const tsm_header_event& b) {
+      return a.file != b.file ? a.file < b.file : a.line_off < b.line_off; });
+    r->n_hev = m;
+  } else if (c->last_flags & TSM_SCAN_HEADER_EVENTS) r->n_hev = c->h_ctrl->n_hev;
+  return TSM_OK;
+}
+
+extern "C" int tsm_scan(tsm_ctx* c, const tsm_corpus* k, tsm_result* r, uint32_t flags, void* stream) {
+  int rc = tsm_upload(c, k, stream);
+  if (rc != TSM_OK) return rc;
+  rc = tsm_scan_resident(c, flags, stream);
+  if (rc != TSM_OK) return rc;
+  return tsm_download(c, r, stream);
+}
+
+// ------------------------------------------------------------------------------------- S10 reduce
+extern "C" int tsm_reduce(tsm_ctx* c, const uint8_t* flags, const int32_t* repo, const int32_t* case_id,
+                          int32_t n_rows, int32_t n_flags, int32_t n_repos, int32_t n_cases,
+                          int64_t* out, int64_t* cases_per_repo, void* stream) {
+  if (!c || n_rows < 0 || n_flags < 0 || n_repos <= 0 || n_cases <= 0 || !out || (n_rows && (!flags || !repo || !case_id)))
+    return TSM_E_ARG;
+  for (int32_t i = 0; i < n_rows; ++i)
+    if (repo[i] < 0 || repo[i] >= n_repos || case_id[i] < 0 || case_id[i] >= n_cases) return TSM_E_ARG;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t words = ((size_t)n_cases + 31) / 32;
+  const size_t nbits = (size_t)(n_flags + 1) * n_repos * words;
+  uint8_t* d_flags = nullptr; int32_t *d_repo = nullptr, *d_case = nullptr; uint32_t* d_bits = nullptr;
+  unsigned long long* d_out = nullptr;
+  int rc = TSM_OK;
+  auto A = [&](void** p, size_t b) { if (rc == TSM_OK && cudaMalloc(p, b ? b : 16) != cudaSuccess) rc = TSM_E_CUDA; };
+  A((void**)&d_flags, (size_t)n_rows * n_flags); A((void**)&d_repo, sizeof(int32_t) * (size_t)n_rows);
+  A((void**)&d_case, sizeof(int32_t) * (size_t)n_rows); A((void**)&d_bits, sizeof(uint32_t) * nbits);
+  A((void**)&d_out, sizeof(unsigned long long) * (size_t)(n_flags + 1) * n_repos);
+  std::vector<unsigned long long> h((size_t)(n_flags + 1) * n_repos);
+  if (rc == TSM_OK) {
+    bool ok = true;
+    if (n_rows) {
+      ok &= cudaMemcpyAsync(d_flags, flags, (size_t)n_rows * n_flags, cudaMemcpyHostToDevice, st) == cudaSuccess;
+      ok &= cudaMemcpyAsync(d_repo, repo, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyHostToDevice, st) == cudaSuccess;
+      ok &= cudaMemcpyAsync(d_case, case_id, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
+    ok &= cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * nbits, st) == cudaSuccess;
+    ok &= cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * h.size(), st) == cudaSuccess;
+    if (ok) ok &= launch_reduce(d_flags, d_repo, d_case, n_rows, n_flags, n_repos, n_cases, d_bits, d_out, st) == 0;
+    ok &= cudaMemcpyAsync(h.data(), d_out, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaStreamSynchronize(st) == cudaSuccess;
+    if (!ok) rc = TSM_E_CUDA;
+  }
+  cudaFree(d_flags); cudaFree(d_repo); cudaFree(d_case); cudaFree(d_bits); cudaFree(d_out);
+  if (rc != TSM_OK) return rc;
+  // row 0 of the device table = "any row" (cases per repo), rows 1.. = the flags
+  for (int32_t r = 0; r < n_repos; ++r) if (cases_per_repo) cases_per_repo[r] = (int64_t)h[r];
+  for (int32_t f = 0; f < n_flags; ++f)
+    for (int32_t r = 0; r < n_repos; ++r) out[(size_t)f * n_repos + r] = (int64_t)h[(size_t)(f + 1) * n_repos + r];
+  c->launches = 2;
+  return TSM_OK;
+}
+
+// ------------------------------------------------------------------------------------- host helpers
+extern "C" void* tsm_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0) return nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void tsm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------- S8 diff
+extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
+                              int64_t* added, int64_t* removed, void* stream) {
+  (void)c; (void)olds; (void)news; (void)added; (void)removed; (void)stream;
+  return TSM_E_STATE;   // implemented in tsm_diff_kernels.cuh (next milestone)
+}

@@ -1,0 +1,636 @@
+// tsm_scan_kernels.cuh - hand-written sm_100a kernels of the corpus scan (docs/SPEC.md).
+//
+//   k_plan      files -> (file, 4 KiB chunk) work units                         [tiny]
+//   k_scan      THE hot kernel: every source byte is read from HBM exactly once.  One warp per
+//               work unit, chunk staged global->shared by a 1-D TMA bulk copy (cp.async.bulk +
+//               mbarrier, double buffered), pass 1 = SWAR newline table, pass 2 = lane-per-line
+//               Shift-And automaton + Mersenne-61 line hash, then per-file counters, digest and
+//               the candidate (assertion-line) list.
+//   k_classify  one thread per candidate: statement, last identifier, category (S5), events, and
+//               the cross-file aggregate into a shared-memory privatised [group][category] table.
+//
+// There is no reference kernel: the reference ships data only.  Rules cite
+// docs/SPEC.md, which cites the artefacts.
+#pragma once
+#include "tsm_device.cuh"
+
+namespace tsm {
+
+__constant__ uint32_t c_lut[256];                       // automaton byte classes
+__constant__ uint8_t c_cat_slot[TSM_CAT_SLOTS];         // perfect hash slot -> category id
+__constant__ uint16_t c_cat_off[TSM_CAT_NAMED + 1];
+__constant__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
+
+// ================================================================================= k_plan
+// One lane per file: units = ceil(len / CH); the warp reserves a contiguous range of the unit
+// table with one atomic.  Unit order is irrelevant for the results (all outputs are sums or sets).
+__global__ void k_plan(ScanParams p) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t nu = 0;
+  if (f < p.n_files) nu = ((uint32_t)p.len[f] + CH - 1) / CH;
+  uint32_t incl = nu;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t base = 0;
+  if (lane == 31 && total) base = atomicAdd(&p.ctrl->n_units, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t at = base + incl - nu;
+  for (uint32_t u = 0; u < nu; ++u, ++at) {
+    if (at < p.unit_cap) { p.unit_file[at] = (uint32_t)f; p.unit_begin[at] = u * CH; }
+    else p.ctrl->overflow = 1;
+  }
+}
+
+// ================================================================================= k_scan
+// SWAR: 16-bit mask of the bytes equal to '\n' in a 16-byte vector.
+__device__ __forceinline__ uint32_t nl_word(uint32_t w) {
+  const uint32_t y = w ^ 0x0A0A0A0Au;
+  const uint32_t t = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  const uint32_t z = ~(t | y | 0x7F7F7F7Fu);            // 0x80 in every byte that was '\n'
+  return ((z >> 7) * 0x00204081u) >> 21 & 0xFu;         // gather the four flag bits
+}
+__device__ __forceinline__ uint32_t nl16(const uint4& v) {
+  return nl_word(v.x) | (nl_word(v.y) << 4) | (nl_word(v.z) << 8) | (nl_word(v.w) << 12);
+}
+
+// Per-lane state of the line currently walked by this lane.
+struct LineState {
+  uint32_t s, e, eh;        // [s, e) = line, [s, eh) = hashed content (trailing CR dropped)
+  uint32_t pos;             // next 8-byte block to process
+  uint32_t D, A;            // automaton state / OR of all states
+  uint32_t r;               // rotation of the next block, 8 * (pos - s) mod 61
+  unsigned long long acc;   // Mersenne-61 accumulator
+};
+
+template <typename LoadByte>
+__device__ __forceinline__ void line_init(LineState& L, uint32_t s, uint32_t e, LoadByte lb) {
+  L.s = s; L.e = e; L.eh = e;
+  if (e > s && lb(e - 1) == 0x0D) L.eh = e - 1;
+  L.D = 0; L.A = 0; L.acc = 0;
+  if (s == e) { L.pos = e; L.r = 0; return; }
+  L.pos = s & ~7u;
+  const uint32_t lead = s - L.pos;                       // 0..7 bytes of the first block precede the line
+  L.r = lead ? 61u - 8u * lead : 0u;                     // 256^-lead mod (2^61-1)
+}
+
+// One 8-byte block: bytes outside [s, e) are zeroed (class 0 resets the automaton, weight 0 in the hash).
+__device__ __forceinline__ void line_block(LineState& L, unsigned long long w, const uint32_t* lut) {
+  const uint32_t pos = L.pos;
+  unsigned long long m = ~0ull;
+  if (pos < L.s) m <<= 8u * (L.s - pos);
+  unsigned long long mh = m;
+  if (pos + 8 > L.e) m &= ~0ull >> (8u * (pos + 8 - L.e));
+  if (pos + 8 > L.eh) mh = (pos >= L.eh) ? 0ull : (mh & (~0ull >> (8u * (pos + 8 - L.eh))));
+  const unsigned long long wa = w & m;
+  const uint32_t lo = (uint32_t)wa, hi = (uint32_t)(wa >> 32);
+  uint32_t D = L.D, A = L.A;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t c = __byte_perm(lo, 0, 0x4440 + k);
+    D = ((D << 1) | AUT_FIRST) & lut[c];
+    A |= D;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t c = __byte_perm(hi, 0, 0x4440 + k);
+    D = ((D << 1) | AUT_FIRST) & lut[c];
+    A |= D;
+  }
+  L.D = D; L.A = A;
+  const unsigned long long x = fold61(fold61(w & mh));
+  L.acc = fold61(L.acc + rotl61(x, L.r));
+  L.r += 3; if (L.r >= 61) L.r -= 61;                    // 2^64 = 2^3 mod (2^61-1)
+  L.pos = pos + 8;
+}
+
+// Does the stripped line start with `pat` (and, if need_ws, continue with blank or tab)?
+template <typename LoadByte>
+__device__ __forceinline__ bool starts_with(LoadByte lb, uint32_t s, uint32_t e, const char* pat, int n, bool need_ws) {
+  while (s < e && is_w(lb(s))) ++s;
+  if (s + n + (need_ws ? 1 : 0) > e) return false;
+  for (int k = 0; k < n; ++k)
+    if (lb(s + k) != (uint8_t)pat[k]) return false;
+  if (need_ws) { const uint32_t c = lb(s + n); return c == 0x20 || c == 0x09; }
+  return true;
+}
+
+// SPEC sections 4/5 on the automaton result of one line.  Returns the LF_* flag byte.
+template <typename LoadByte>
+__device__ __forceinline__ uint32_t line_flags(const LineState& L, int ext, LoadByte lb) {
+  if (ext == 0) return 0;
+  const uint32_t A = L.A;
+  uint32_t fl = (A & (F_ASSERT | F_EXPECT)) ? LF_CAND : 0;
+  bool hdr;
+  if (ext == TSM_EXT_PY) {
+    hdr = (A & F_DEF) != 0;
+    if (!hdr && (A & F_CLASS)) hdr = starts_with(lb, L.s, L.e, "class", 5, true);
+  } else {
+    hdr = (A & F_TEST) && (A & (F_BRACE | F_CLASS | F_VOID));
+  }
+  if (hdr) {
+    fl |= LF_HDR;
+    if (starts_with(lb, L.s, L.e, "TEST_F", 6, false)) fl |= LF_FIX;
+  }
+  return fl;
+}
+
+struct Accum { uint32_t lines, asserts, hdrs, fixes; unsigned long long digest; };
+
+struct SmemByte {                                        // byte source = the staged chunk
+  const uint8_t* b;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return b[i]; }
+};
+struct GmemByte {                                        // byte source = the file in HBM (slow path)
+  const uint8_t* b;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(b + i); }
+};
+
+// Append `n` list entries with one atomic; returns the base slot (broadcast from lane 0).
+__device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, uint32_t n, int lane) {
+  uint32_t base = 0;
+  if (lane == 0 && n) base = atomicAdd(counter, n);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// Pass 2 + compaction over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
+__device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, const uint8_t* buf,
+                                      const uint16_t* tab, uint8_t* lfl, uint32_t cnt, bool& skip_first,
+                                      uint32_t& next_start, uint32_t f, uint32_t cb, int ext, int lane,
+                                      Accum& ac) {
+  __syncwarp();
+  if (cnt == 0) return;
+  const uint32_t j0 = skip_first ? 1u : 0u;
+  const uint32_t ns = next_start;
+  const SmemByte lb{buf};
+  uint32_t next = j0;
+  bool active = false;
+  uint32_t myj = 0;
+  LineState L;
+  while (true) {
+    const uint32_t need = __ballot_sync(0xffffffffu, !active);
+    if (need) {
+      const uint32_t j = next + __popc(need & ((1u << lane) - 1u));
+      next += __popc(need);
+      if (!active && j < cnt) {
+        const uint32_t s = j ? (uint32_t)tab[j - 1] + 1u : ns;
+        line_init(L, s, tab[j], lb);
+        myj = j;
+        active = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) {
+      if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut);
+      if (L.pos >= L.e) {
+        ac.lines++;
+        ac.digest += mix_hash(canon61(L.acc), L.eh - L.s);
+        const uint32_t fl = line_flags(L, ext, lb);
+        ac.asserts += fl & LF_CAND;
+        ac.hdrs += (fl >> 1) & 1u;
+        ac.fixes += (fl >> 2) & 1u;
+        lfl[myj] = (uint8_t)fl;
+        active = false;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- compaction: candidates (always) and header events (on request) to their global lists
+  const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
+  uint32_t nc = 0, nh = 0;
+  for (uint32_t b = j0; b < cnt; b += 32) {
+    const uint32_t j = b + lane;
+    const uint32_t fb = j < cnt ? lfl[j] : 0u;
+    nc += __popc(__ballot_sync(0xffffffffu, fb & LF_CAND));
+    nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
+  }
+  if (!want_hev) nh = 0;
+  if (nc | nh) {
+    uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
+    uint32_t hbase = warp_reserve(&p.ctrl->n_hev, nh, lane);
+    for (uint32_t b = j0; b < cnt; b += 32) {
+      const uint32_t j = b + lane;
+      const uint32_t fb = j < cnt ? lfl[j] : 0u;
+      uint32_t s = 0, e = 0;
+      if (j < cnt) { s = j ? (uint32_t)tab[j - 1] + 1u : ns; e = tab[j]; }
+      const uint32_t line_off = cb + s - PRE;
+      const uint32_t mc = __ballot_sync(0xffffffffu, fb & LF_CAND);
+      if (fb & LF_CAND) {
+        const uint32_t slot = cbase + __popc(mc & ((1u << lane) - 1u));
+        if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | line_off;
+        else p.ctrl->overflow = 1;
+      }
+      cbase += __popc(mc);
+      if (want_hev) {
+        const uint32_t mh = __ballot_sync(0xffffffffu, fb & LF_HDR);
+        if (fb & LF_HDR) {
+          const uint32_t slot = hbase + __popc(mh & ((1u << lane) - 1u));
+          if (slot < p.hev_cap) p.hev[slot] = tsm_header_event{f, line_off, e - s, (fb >> 2) & 1u};
+          else p.ctrl->overflow = 1;
+        }
+        hbase += __popc(mh);
+      }
+    }
+  }
+  next_start = (uint32_t)tab[cnt - 1] + 1u;
+  skip_first = false;
+  __syncwarp();
+}
+
+// Slow path: a line that starts in this chunk but ends behind the staged bytes.  Walked by lane 0
+// straight from HBM (correct for any length; lines longer than 240 B past a chunk edge are rare).
+__device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut, uint32_t f, uint32_t fo,
+                                       uint32_t size, int ext, uint32_t s, Accum& ac) {
+  const uint8_t* g = p.arena + fo;
+  const GmemByte lb{g};
+  uint32_t e = s;
+  while (e < size && lb(e) != '\n') ++e;
+  LineState L;
+  line_init(L, s, e, lb);
+  while (L.pos < L.e) line_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), lut);
+  ac.lines++;
+  ac.digest += mix_hash(canon61(L.acc), L.eh - L.s);
+  const uint32_t fl = line_flags(L, ext, lb);
+  ac.asserts += fl & LF_CAND;
+  ac.hdrs += (fl >> 1) & 1u;
+  ac.fixes += (fl >> 2) & 1u;
+  if (fl & LF_CAND) {
+    const uint32_t slot = atomicAdd(&p.ctrl->n_cand, 1u);
+    if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | s;
+    else p.ctrl->overflow = 1;
+  }
+  if ((fl & LF_HDR) && (p.flags & TSM_SCAN_HEADER_EVENTS)) {
+    const uint32_t slot = atomicAdd(&p.ctrl->n_hev, 1u);
+    if (slot < p.hev_cap) p.hev[slot] = tsm_header_event{f, s, e - s, (fl >> 2) & 1u};
+    else p.ctrl->overflow = 1;
+  }
+}
+
+__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, const uint8_t* buf,
+                                              uint16_t* tab, uint8_t* lfl, uint32_t f, uint32_t cb, int lane) {
+  const uint32_t size = (uint32_t)p.len[f];
+  const uint32_t fo = (uint32_t)p.off[f];
+  const int ext = p.ext[f];
+  const uint32_t ce = min(cb + CH, size);
+  const uint32_t le = min(ce + EXT, size);
+  const uint32_t lim = PRE + (ce - cb);                  // buffer position just past the owned bytes
+  const uint32_t lim2 = PRE + (le - cb);                 // ... past the staged bytes
+  bool skip_first = (cb != 0) && (buf[PRE - 1] != '\n'); // chunk starts inside a foreign line
+  uint32_t next_start = PRE;
+  Accum ac{0, 0, 0, 0, 0};
+  uint32_t cnt = 0;
+  // ---- pass 1: newline table of the owned bytes, 512 B per step (16 B per lane, SWAR)
+  for (uint32_t tp = PRE; tp < lim; tp += 512) {
+    if (cnt + 512 > NL_CAP) {
+      drain(p, lut, buf, tab, lfl, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+      cnt = 0;
+    }
+    const uint32_t pos = tp + lane * 16;
+    uint32_t bits = 0;
+    if (pos < lim) {
+      bits = nl16(*reinterpret_cast<const uint4*>(buf + pos));
+      const uint32_t valid = lim - pos;
+      if (valid < 16) bits &= (1u << valid) - 1u;
+    }
+    const uint32_t c = __popc(bits);
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    uint32_t idx = cnt + incl - c;
+    while (bits) {
+      const uint32_t b = __ffs(bits) - 1;
+      tab[idx++] = (uint16_t)(pos + b);
+      bits &= bits - 1;
+    }
+    cnt += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  // ---- the last owned line: starts in the chunk, may end behind it
+  const uint32_t tail_start = cnt ? (uint32_t)tab[cnt - 1] + 1u : next_start;
+  const bool owned = !(skip_first && cnt == 0);
+  bool have_tail = false, tail_long = false;
+  uint32_t tail_end = 0;
+  if (owned && tail_start < lim) {
+    if (ce == size) { tail_end = lim; have_tail = true; }              // unterminated last line of the file
+    else {
+      const uint32_t pos = lim + lane * 16;
+      uint32_t bits = 0;
+      if (pos < lim2) {
+        bits = nl16(*reinterpret_cast<const uint4*>(buf + pos));
+        const uint32_t valid = lim2 - pos;
+        if (valid < 16) bits &= (1u << valid) - 1u;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, bits != 0);
+      if (m) {
+        const int src = __ffs(m) - 1;
+        const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
+        tail_end = lim + src * 16 + (__ffs(b) - 1);
+        have_tail = true;
+      } else if (le == size) { tail_end = lim2; have_tail = true; }    // file ends inside the staged bytes
+      else tail_long = true;
+    }
+  }
+  if (have_tail) {
+    if (cnt == NL_CAP) {
+      drain(p, lut, buf, tab, lfl, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+      cnt = 0;
+    }
+    if (lane == 0) tab[cnt] = (uint16_t)tail_end;
+    ++cnt;
+  }
+  drain(p, lut, buf, tab, lfl, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+  if (tail_long && lane == 0) long_line(p, lut, f, fo, size, ext, cb + tail_start - PRE, ac);
+  // ---- per-file counters: warp reduce, then one atomic per counter
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    ac.lines += __shfl_xor_sync(0xffffffffu, ac.lines, d);
+    ac.asserts += __shfl_xor_sync(0xffffffffu, ac.asserts, d);
+    ac.hdrs += __shfl_xor_sync(0xffffffffu, ac.hdrs, d);
+    ac.fixes += __shfl_xor_sync(0xffffffffu, ac.fixes, d);
+    ac.digest += __shfl_xor_sync(0xffffffffu, ac.digest, d);
+  }
+  if (lane == 0) {
+    tsm_file_stat* st = p.stats + f;
+    if (size <= CH) {                                    // sole owner of the record: plain store
+      *st = tsm_file_stat{ac.lines, ac.asserts, ac.hdrs, ac.fixes, ac.digest};
+    } else {
+      if (ac.lines) atomicAdd(&st->n_lines, ac.lines);
+      if (ac.asserts) atomicAdd(&st->n_assert, ac.asserts);
+      if (ac.hdrs) atomicAdd(&st->n_headers, ac.hdrs);
+      if (ac.fixes) atomicAdd(&st->n_fixture, ac.fixes);
+      if (ac.digest) atomicAdd(reinterpret_cast<unsigned long long*>(&st->digest), ac.digest);
+    }
+  }
+}
+
+// Stage the bytes [max(cb-16,0), min(cb+CH+EXT, size)) of file f so that file byte cb sits at buf+PRE.
+__device__ __forceinline__ void issue_load(const ScanParams& p, uint8_t* buf, uint64_t* bar, uint32_t f, uint32_t cb) {
+  const uint32_t size = (uint32_t)p.len[f];
+  const uint32_t lb = cb ? cb - PRE : 0u;
+  const uint32_t le = min(cb + CH + EXT, size);
+  const uint32_t bytes = (le - lb + 15u) & ~15u;          // the pad up to the 128-B file boundary is readable
+  mbar_expect_tx(bar, bytes);
+  bulk_load(buf + PRE - (cb - lb), p.arena + (size_t)(uint32_t)p.off[f] + lb, bytes, bar);
+}
+
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 4) k_scan(ScanParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t* lut = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_lut[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wb = smem + LUT_BYTES + warp * WARP_SMEM;
+  uint8_t* buf0 = wb;
+  uint8_t* buf1 = wb + BUF;
+  uint16_t* tab = reinterpret_cast<uint16_t*>(wb + 2 * BUF);
+  uint8_t* lfl = wb + 2 * BUF + TAB_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wb + 2 * BUF + TAB_BYTES + LFL_BYTES);
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  __syncwarp();
+  const uint32_t n_units = p.ctrl->n_units;
+  uint32_t phase0 = 0, phase1 = 0;
+  // claim + prefetch the first unit
+  uint32_t u = 0;
+  if (lane == 0) u = atomicAdd(&p.ctrl->work, 1u);
+  u = __shfl_sync(0xffffffffu, u, 0);
+  uint32_t f = 0, cb = 0;
+  if (u < n_units) {
+    f = p.unit_file[u]; cb = p.unit_begin[u];
+    if (lane == 0) issue_load(p, buf0, &bar[0], f, cb);
+  }
+  int cur = 0;
+  while (u < n_units) {
+    // claim the next unit and start its copy into the other buffer
+    uint32_t un = 0;
+    if (lane == 0) un = atomicAdd(&p.ctrl->work, 1u);
+    un = __shfl_sync(0xffffffffu, un, 0);
+    uint32_t fn = 0, cbn = 0;
+    if (un < n_units) {
+      fn = p.unit_file[un]; cbn = p.unit_begin[un];
+      if (lane == 0) issue_load(p, cur ? buf0 : buf1, &bar[cur ^ 1], fn, cbn);
+    }
+    // wait for the current buffer
+    if (cur == 0) { while (!mbar_try_wait(&bar[0], phase0)) {} phase0 ^= 1; }
+    else          { while (!mbar_try_wait(&bar[1], phase1)) {} phase1 ^= 1; }
+    process_chunk(p, lut, cur ? buf1 : buf0, tab, lfl, f, cb, lane);
+    __syncwarp();
+    u = un; f = fn; cb = cbn; cur ^= 1;
+  }
+}
+
+// ================================================================================= k_classify
+// One thread per candidate line.  Byte-serial state machine over the statement (it ends at the
+// first '('), exactly SPEC sections 4 and 6.
+struct ByteReader {                                      // 8-byte buffered reader over the file in HBM
+  const uint8_t* base; uint32_t cur_blk; unsigned long long w;
+  __device__ __forceinline__ ByteReader(const uint8_t* b) : base(b), cur_blk(0xFFFFFFFFu), w(0) {}
+  __device__ __forceinline__ uint32_t get(uint32_t i) {
+    const uint32_t blk = i >> 3;
+    if (blk != cur_blk) { w = __ldg(reinterpret_cast<const unsigned long long*>(base) + blk); cur_blk = blk; }
+    return (uint32_t)(w >> (8u * (i & 7u))) & 0xFFu;
+  }
+};
+
+__device__ __forceinline__ int stem_lookup(ByteReader& rd, uint32_t s, uint32_t n) {
+  // s = first byte after "EXPECT_" / "ASSERT_"; n = stem length
+  char t[10];
+  if (n == 0 || n > 9) return 0;
+  for (uint32_t k = 0; k < n; ++k) t[k] = (char)rd.get(s + k);
+#define STEM(str, id) if (n == sizeof(str) - 1) { bool ok = true; for (uint32_t k = 0; k < n; ++k) ok &= (t[k] == str[k]); if (ok) return id; }
+  STEM("EQ", 1) STEM("NE", 2) STEM("TRUE", 3) STEM("FALSE", 4) STEM("GT", 5) STEM("GE", 6)
+  STEM("LT", 7) STEM("LE", 8) STEM("NEAR", 9) STEM("FLOAT_EQ", 10) STEM("DOUBLE_EQ", 11) STEM("THROW", 12)
+#undef STEM
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) k_classify(ScanParams p) {
+  extern __shared__ uint32_t hist[];                     // [n_groups][K] when it fits, else unused
+  const bool use_smem = p.n_groups <= 16;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+  }
+  const uint32_t n = min(p.ctrl->n_cand, p.cand_cap);
+  const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long cd = p.cand[i];
+    const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
+    const uint32_t size = (uint32_t)p.len[f];
+    ByteReader rd(p.arena + (size_t)(uint32_t)p.off[f]);
+    // ---- statement T = stripped line cut before its first '(' and right-stripped (SPEC section 4)
+    uint32_t q = line_off;
+    while (q < size) { const uint32_t c = rd.get(q); if (c == '\n' || !is_w(c)) break; ++q; }
+    const uint32_t t0 = q;
+    uint32_t last = t0;                                  // one past the last non-blank byte
+    uint32_t run = t0; bool in_run = false, gap = false; // trailing identifier run (L)
+    unsigned long long win = 0;                          // last 8 bytes of e = T[7:], newest in the low byte
+    bool bare = false;
+    uint32_t feat = 0;                                   // bit0 " not ", 1 " in ", 2 " is not ", 3 True, 4 ==, 5 !=, 6 <=, 7 >=, 8 <, 9 >
+    unsigned long long hacc = 0; uint32_t hr = 0;        // Mersenne-61 of T (blanks inside T are part of it)
+    unsigned long long hacc_last = 0;                    // hash state at `last`
+    uint32_t k = 0;                                      // bytes of T seen so far (index inside T)
+    bool is_assert6 = true;
+    while (q < size) {
+      const uint32_t c = rd.get(q);
+      if (c == '\n' || c == '(') break;
+      // bare-assert detection on the first 7 bytes
+      if (k < 6) is_assert6 &= (c == (uint32_t)"assert"[k]);
+      else if (k == 6) bare = is_assert6 && (c == 0x20);
+      if (bare && k >= 7) {
+        win = (win << 8) | c;
+        const uint32_t ek = k - 7;                       // index inside e
+        const uint32_t w4 = (uint32_t)win; const uint32_t w2 = w4 & 0xFFFFu;
+        if (ek >= 4 && (win & 0xFFFFFFFFFFull) == 0x206E6F7420ull) feat |= 1;        // " not "
+        if (ek >= 3 && w4 == 0x20696E20u) feat |= 2;                                 // " in "
+        if (ek >= 7 && win == 0x206973206E6F7420ull) feat |= 4;                      // " is not "
+        if (ek >= 3 && w4 == 0x54727565u) feat |= 8;                                 // "True"
+        if (ek >= 1) {
+          if (w2 == 0x3D3Du) feat |= 16;                                             // "=="
+          if (w2 == 0x213Du) feat |= 32;                                             // "!="
+          if (w2 == 0x3C3Du) feat |= 64;                                             // "<="
+          if (w2 == 0x3E3Du) feat |= 128;                                            // ">="
+        }
+        if (c == '<') feat |= 256;
+        if (c == '>') feat |= 512;
+      }
+      hacc = fold61(hacc + rotl61((unsigned long long)c, hr));
+      hr += 8; if (hr >= 61) hr -= 61;
+      if (is_w(c)) gap = true;
+      else {
+        if (is_ident(c)) { if (!in_run || gap) run = q; in_run = true; } else in_run = false;
+        gap = false; last = q + 1; hacc_last = hacc;
+      }
+      ++q; ++k;
+    }
+    const uint32_t tlen = last - t0;
+    // features seen in trailing blanks do not belong to T: none of the patterns can end in the
+    // stripped tail except through a trailing blank (" not ", " in ", " is not ", "not ") - recheck
+    // those against tlen below.
+    const uint32_t Ls = in_run ? run : last;
+    const uint32_t Ln = last - Ls;
+    // ---- category (SPEC section 6)
+    int cat = 0;
+    bool done = false;
+    if (Ln >= 7) {
+      const uint32_t c0 = rd.get(Ls);
+      if (c0 == 'E' || c0 == 'A') {
+        const char* pre = c0 == 'E' ? "EXPECT_" : "ASSERT_";
+        bool ok = true;
+        for (int j = 1; j < 7; ++j) ok &= (rd.get(Ls + j) == (uint32_t)pre[j]);
+        if (ok) { cat = stem_lookup(rd, Ls + 7, Ln - 7); done = true; }
+      }
+    }
+    if (!done) {
+      const bool t_is_assert = (tlen == 6) && is_assert6;
+      if (t_is_assert || (bare && tlen >= 8)) {
+        done = true;
+        if (t_is_assert) { cat = 3; }                    // T == "assert": e is empty
+        else {
+          // patterns that end with a blank can only have matched inside T if they end before `last`
+          // (T is right-stripped): re-scan e = T[7:tlen) for them exactly.
+          const uint32_t e0 = t0 + 7, en = tlen - 7;
+          bool f_not = false, f_in = false, f_isnot = false, f_pre = false;
+          if (en >= 4) {
+            f_pre = rd.get(e0) == 'n' && rd.get(e0 + 1) == 'o' && rd.get(e0 + 2) == 't' && rd.get(e0 + 3) == ' ';
+          }
+          if (feat & (1 | 2 | 4)) {
+            for (uint32_t a = 0; a + 4 <= en; ++a) {
+              if (rd.get(e0 + a) != ' ') continue;
+              const uint32_t b1 = rd.get(e0 + a + 1), b2 = rd.get(e0 + a + 2), b3 = rd.get(e0 + a + 3);
+              if (b1 == 'i' && b2 == 'n' && b3 == ' ') f_in = true;
+              if (a + 5 <= en && b1 == 'n' && b2 == 'o' && b3 == 't' && rd.get(e0 + a + 4) == ' ') f_not = true;
+              if (a + 8 <= en && b1 == 'i' && b2 == 's' && b3 == ' ' && rd.get(e0 + a + 4) == 'n' &&
+                  rd.get(e0 + a + 5) == 'o' && rd.get(e0 + a + 6) == 't' && rd.get(e0 + a + 7) == ' ') f_isnot = true;
+            }
+          }
+          if (f_pre) cat = 2;
+          else if ((f_not && f_in) || f_isnot) cat = 4;
+          else if (feat & 8) cat = 3;
+          else if (feat & 16) cat = 1;
+          else if (feat & 32) cat = 2;
+          else if (feat & 64) cat = 8;
+          else if (feat & 128) cat = 6;
+          else if (feat & 256) cat = 7;
+          else if (feat & 512) cat = 5;
+          else cat = 3;
+        }
+      }
+    }
+    if (!done) {
+      bool pre = Ln >= 6;
+      if (pre) for (int j = 0; j < 6; ++j) pre &= (rd.get(Ls + j) == (uint32_t)"assert"[j]);
+      if (pre) {
+        if (Ln == 7 && rd.get(Ls + 6) == '_') cat = 3;
+        else {
+          cat = TSM_CAT_OTHER;
+          uint32_t h = 0x811C9DC5u;
+          for (uint32_t j = 0; j < Ln; ++j) h = (h ^ rd.get(Ls + j)) * 0x01000193u;
+          const int id = c_cat_slot[(h * TSM_CAT_HASH_MULT) >> 23];
+          if (id && (uint32_t)(c_cat_off[id + 1] - c_cat_off[id]) == Ln) {
+            bool ok = true;
+            for (uint32_t j = 0; j < Ln; ++j) ok &= (rd.get(Ls + j) == (uint32_t)(uint8_t)c_cat_blob[c_cat_off[id] + j]);
+            if (ok) cat = id;
+          }
+        }
+      }
+    }
+    // ---- aggregate + event
+    const uint32_t g = p.grp ? p.grp[f] : 0u;
+    if (use_smem) atomicAdd(&hist[g * TSM_K + cat], 1u);
+    else {
+      atomicAdd(&p.counts[(size_t)g * TSM_K + cat], 1ull);
+      atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + cat], 1ull);
+    }
+    if (want_ev) {
+      const uint32_t slot = atomicAdd(&p.ctrl->n_aev, 1u);
+      if (slot < p.aev_cap) {
+        tsm_assert_event ev;
+        ev.file = f; ev.line_off = line_off; ev.stmt_off = t0;
+        ev.stmt_len = (uint16_t)min(tlen, 65535u); ev.cat = (uint16_t)cat;
+        ev.ident_off = Ls; ev.ident_len = (uint16_t)min(Ln, 65535u); ev.pad = 0;
+        ev.stmt_hash = mix_hash(canon61(hacc_last), tlen);
+        p.aev[slot] = ev;
+      } else p.ctrl->overflow = 1;
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) {
+      const uint32_t v = hist[i];
+      if (v) {
+        atomicAdd(&p.counts[i], (unsigned long long)v);
+        atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + (i & (TSM_K - 1))], (unsigned long long)v);
+      }
+    }
+  }
+}
+
+// Totals of the per-file records (lines, assertion lines, headers, fixture headers).
+__global__ void k_totals(ScanParams p) {
+  unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_files; f += gridDim.x * blockDim.x) {
+    const tsm_file_stat s = p.stats[f];
+    t0 += s.n_lines; t1 += s.n_assert; t2 += s.n_headers; t3 += s.n_fixture;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    t0 += __shfl_xor_sync(0xffffffffu, t0, d); t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+    t2 += __shfl_xor_sync(0xffffffffu, t2, d); t3 += __shfl_xor_sync(0xffffffffu, t3, d);
+  }
+  if ((threadIdx.x & 31) == 0) {                         // the totals live behind the count table
+    unsigned long long* tot = p.counts + (size_t)(p.n_groups + 1) * TSM_K;
+    if (t0) atomicAdd(&tot[0], t0);
+    if (t1) atomicAdd(&tot[1], t1);
+    if (t2) atomicAdd(&tot[2], t2);
+    if (t3) atomicAdd(&tot[3], t3);
+  }
+}
+
+}  // namespace tsm
