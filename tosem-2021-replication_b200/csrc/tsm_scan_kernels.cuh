@@ -115,7 +115,13 @@ __device__ __forceinline__ bool starts_with(LoadByte lb, uint32_t s, uint32_t e,
   if (s + n + (need_ws ? 1 : 0) > e) return false;
   for (int k = 0; k < n; ++k)
     if (lb(s + k) != (uint8_t)pat[k]) return false;
-  if (need_ws) { const uint32_t c = lb(s + n); return c == 0x20 || c == 0x09; }
+  if (need_ws) {                                         // the blank must be inside the STRIPPED line:
+    const uint32_t c = lb(s + n);                        // some non-blank byte has to follow it
+    if (c != 0x20 && c != 0x09) return false;
+    for (uint32_t q = s + n + 1; q < e; ++q)
+      if (!is_w(lb(q))) return true;
+    return false;
+  }
   return true;
 }
 
