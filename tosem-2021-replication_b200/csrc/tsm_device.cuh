@@ -21,24 +21,29 @@ constexpr uint32_t PRE = 16;                  // bytes loaded in front (is the c
 constexpr uint32_t EXT = 240;                 // bytes loaded behind (terminator of the last owned line)
 constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128
 constexpr uint32_t NL_CAP = 1024;             // line-table entries per drain
+constexpr uint32_t WALK_BATCH = 256;          // lines walked (pass 2) before their balanced finalise (pass 3)
 constexpr uint32_t TAB_BYTES = (NL_CAP + 64) * 2;   // u16 newline positions
 constexpr uint32_t LFL_BYTES = NL_CAP + 64;         // u8 per-line flags
-constexpr uint32_t WARP_SMEM = ((2 * BUF + TAB_BYTES + LFL_BYTES + 32 + 127) / 128) * 128;
-constexpr uint32_t LUT_BYTES = 1024;
+constexpr uint32_t RAW_BYTES = WALK_BATCH * 12;     // per line: u64 Horner accumulator + u32 automaton OR
+constexpr uint32_t WARP_SMEM = ((BUF + TAB_BYTES + LFL_BYTES + RAW_BYTES + 16 + 127) / 128) * 128;
+constexpr uint32_t LUT_BYTES = 2048;          // two 256-entry automaton tables (PY, C family)
 constexpr int SCAN_WARPS = 4;                 // warps per CTA of k_scan (each warp is independent)
+constexpr int SCAN_CTAS_PER_SM = 5;
 constexpr uint32_t SCAN_SMEM = LUT_BYTES + SCAN_WARPS * WARP_SMEM;
 
-// ---- multi-pattern Shift-And automaton (SPEC sections 4, 5) ------------------------------------------
+// ---- multi-pattern Shift-And automata (SPEC sections 4, 5) -----------------------------------------
 // One state bit per pattern byte; D' = ((D << 1) | FIRST) & LUT[c]; a line's OR of all D tells
-// which patterns ended somewhere inside it.
-//   bits  0.. 5  assert  (ci)      bits  6..12  EXPECT_ (cs)     bits 13..16  test (ci)
-//   bits 17..19  def     (cs)      bits 20..24  class   (cs)     bits 25..28  void (cs)
-//   bit  29      {
-constexpr uint32_t AUT_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 17) | (1u << 20) | (1u << 25) | (1u << 29);
-constexpr uint32_t F_ASSERT = 1u << 5, F_EXPECT = 1u << 12, F_TEST = 1u << 16, F_DEF = 1u << 19,
-                   F_CLASS = 1u << 24, F_VOID = 1u << 28, F_BRACE = 1u << 29;
+// which patterns ended somewhere inside it.  One table per language family (the header rules differ):
+//   both  bits  0.. 5  assert (ci)   bits  6..12  EXPECT_ (cs)
+//   PY    bits 13..15  def           bits 16..20  class        bits 21..24  ST_F (gate of the TEST_F check)
+//   CJ    bits 13..16  test (ci)     bits 17..21  class        bits 22..25  void   bit 26  {   bits 27..30  ST_F
+constexpr uint32_t AF_ASSERT = 1u << 5, AF_EXPECT = 1u << 12;
+constexpr uint32_t PY_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 16) | (1u << 21);
+constexpr uint32_t PY_DEF = 1u << 15, PY_CLASS = 1u << 20, PY_STF = 1u << 24;
+constexpr uint32_t CJ_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 17) | (1u << 22) | (1u << 26) | (1u << 27);
+constexpr uint32_t CJ_TEST = 1u << 16, CJ_CLASS = 1u << 21, CJ_VOID = 1u << 25, CJ_BRACE = 1u << 26, CJ_STF = 1u << 30;
 
-// per-line flag byte written by k_scan's pass 2
+// per-line flag byte written by k_scan's pass 3
 constexpr uint8_t LF_CAND = 1, LF_HDR = 2, LF_FIX = 4;
 
 struct Ctrl {                     // device control block, zeroed before every scan

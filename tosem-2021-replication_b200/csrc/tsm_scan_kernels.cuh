@@ -16,7 +16,7 @@
 
 namespace tsm {
 
-__constant__ uint32_t c_lut[256];                       // automaton byte classes
+__constant__ uint32_t c_lut[512];                       // automaton byte classes: [0,256) PY, [256,512) C/C++/Java
 __constant__ uint8_t c_cat_slot[TSM_CAT_SLOTS];         // perfect hash slot -> category id
 __constant__ uint16_t c_cat_off[TSM_CAT_NAMED + 1];
 __constant__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
@@ -47,6 +47,13 @@ __global__ void k_plan(ScanParams p) {
 }
 
 // ================================================================================= k_scan
+// Work unit = (file, 4 KiB chunk).  Per warp, per unit:
+//   stage   one 1-D TMA bulk copy (cp.async.bulk + mbarrier) of [chunk-16, chunk+4096+240) into shared
+//   pass 1  SWAR newline table (16 B per lane per step, perfectly balanced)
+//   pass 2  lane-per-line walk, 2 x 8 B per iteration, lanes refill dynamically: Shift-And
+//           automaton (one LDS per byte) + Mersenne-61 Horner; raw (A, B) per line into shared
+//   pass 3  balanced finalise, one lane per line: hash finalisation, header / assertion flags
+//   pass 4  ballot compaction of candidate (and header-event) lines into the global lists
 // SWAR: 16-bit mask of the bytes equal to '\n' in a 16-byte vector.
 __device__ __forceinline__ uint32_t nl_word(uint32_t w) {
   const uint32_t y = w ^ 0x0A0A0A0Au;
@@ -60,55 +67,49 @@ __device__ __forceinline__ uint32_t nl16(const uint4& v) {
 
 // Per-lane state of the line currently walked by this lane.
 struct LineState {
-  uint32_t s, e, eh;        // [s, e) = line, [s, eh) = hashed content (trailing CR dropped)
+  uint32_t s, e;            // [s, e) = line
   uint32_t pos;             // next 8-byte block to process
   uint32_t D, A;            // automaton state / OR of all states
-  uint32_t r;               // rotation of the next block, 8 * (pos - s) mod 61
-  unsigned long long acc;   // Mersenne-61 accumulator
+  unsigned long long B;     // Horner accumulator: B_k = B_{k-1} * 2^-64 + X_k  (mod 2^61-1)
 };
 
-template <typename LoadByte>
-__device__ __forceinline__ void line_init(LineState& L, uint32_t s, uint32_t e, LoadByte lb) {
-  L.s = s; L.e = e; L.eh = e;
-  if (e > s && lb(e - 1) == 0x0D) L.eh = e - 1;
-  L.D = 0; L.A = 0; L.acc = 0;
-  if (s == e) { L.pos = e; L.r = 0; return; }
-  L.pos = s & ~7u;
-  const uint32_t lead = s - L.pos;                       // 0..7 bytes of the first block precede the line
-  L.r = lead ? 61u - 8u * lead : 0u;                     // 256^-lead mod (2^61-1)
+__device__ __forceinline__ void line_init(LineState& L, uint32_t s, uint32_t e) {
+  L.s = s; L.e = e; L.D = 0; L.A = 0; L.B = 0;
+  L.pos = (s == e) ? e : (s & ~7u);
 }
 
-// One 8-byte block: bytes outside [s, e) are zeroed (class 0 resets the automaton, weight 0 in the hash).
-__device__ __forceinline__ void line_block(LineState& L, unsigned long long w, const uint32_t* lut) {
+// One 8-byte block.  kAut = false for files without a scannable extension (hash only).
+template <bool kAut>
+__device__ __forceinline__ void line_block(LineState& L, unsigned long long w, const uint32_t* lut, uint32_t first) {
   const uint32_t pos = L.pos;
-  unsigned long long m = ~0ull;
-  if (pos < L.s) m <<= 8u * (L.s - pos);
-  unsigned long long mh = m;
-  if (pos + 8 > L.e) m &= ~0ull >> (8u * (pos + 8 - L.e));
-  if (pos + 8 > L.eh) mh = (pos >= L.eh) ? 0ull : (mh & (~0ull >> (8u * (pos + 8 - L.eh))));
-  const unsigned long long wa = w & m;
-  const uint32_t lo = (uint32_t)wa, hi = (uint32_t)(wa >> 32);
-  uint32_t D = L.D, A = L.A;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t c = __byte_perm(lo, 0, 0x4440 + k);
-    D = ((D << 1) | AUT_FIRST) & lut[c];
-    A |= D;
+  if (pos < L.s || pos + 8 > L.e) {                      // first / last block: zero the bytes outside the line
+    unsigned long long m = ~0ull;
+    if (pos < L.s) m <<= 8u * (L.s - pos);
+    if (pos + 8 > L.e) m &= ~0ull >> (8u * (pos + 8 - L.e));
+    w &= m;
   }
+  if (kAut) {
+    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+    uint32_t D = L.D, A = L.A;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t c = __byte_perm(hi, 0, 0x4440 + k);
-    D = ((D << 1) | AUT_FIRST) & lut[c];
-    A |= D;
+    for (int k = 0; k < 4; ++k) {
+      D = ((D + D) | first) & lut[__byte_perm(lo, 0, 0x4440 + k)];
+      A |= D;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      D = ((D + D) | first) & lut[__byte_perm(hi, 0, 0x4440 + k)];
+      A |= D;
+    }
+    L.D = D; L.A = A;
   }
-  L.D = D; L.A = A;
-  const unsigned long long x = fold61(fold61(w & mh));
-  L.acc = fold61(L.acc + rotl61(x, L.r));
-  L.r += 3; if (L.r >= 61) L.r -= 61;                    // 2^64 = 2^3 mod (2^61-1)
+  // B = B * 2^-64 + w  (2^-64 = 2^-3 = 2^58 mod 2^61-1: a rotation by 3 to the right)
+  const unsigned long long b = L.B;
+  const unsigned long long rot = (b >> 3) | ((b & 7ull) << 58);
+  L.B = fold61(fold61(rot + fold61(w)));
   L.pos = pos + 8;
 }
 
-// Does the stripped line start with `pat` (and, if need_ws, continue with blank or tab)?
 template <typename LoadByte>
 __device__ __forceinline__ bool starts_with(LoadByte lb, uint32_t s, uint32_t e, const char* pat, int n, bool need_ws) {
   while (s < e && is_w(lb(s))) ++s;
@@ -125,26 +126,6 @@ __device__ __forceinline__ bool starts_with(LoadByte lb, uint32_t s, uint32_t e,
   return true;
 }
 
-// SPEC sections 4/5 on the automaton result of one line.  Returns the LF_* flag byte.
-template <typename LoadByte>
-__device__ __forceinline__ uint32_t line_flags(const LineState& L, int ext, LoadByte lb) {
-  if (ext == 0) return 0;
-  const uint32_t A = L.A;
-  uint32_t fl = (A & (F_ASSERT | F_EXPECT)) ? LF_CAND : 0;
-  bool hdr;
-  if (ext == TSM_EXT_PY) {
-    hdr = (A & F_DEF) != 0;
-    if (!hdr && (A & F_CLASS)) hdr = starts_with(lb, L.s, L.e, "class", 5, true);
-  } else {
-    hdr = (A & F_TEST) && (A & (F_BRACE | F_CLASS | F_VOID));
-  }
-  if (hdr) {
-    fl |= LF_HDR;
-    if (starts_with(lb, L.s, L.e, "TEST_F", 6, false)) fl |= LF_FIX;
-  }
-  return fl;
-}
-
 struct Accum { uint32_t lines, asserts, hdrs, fixes; unsigned long long digest; };
 
 struct SmemByte {                                        // byte source = the staged chunk
@@ -156,6 +137,43 @@ struct GmemByte {                                        // byte source = the fi
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(b + i); }
 };
 
+// Finish one line from its raw (A, B): SPEC section 3 hash (trailing CR dropped) and SPEC sections 4/5 flags.
+template <typename LoadByte>
+__device__ __forceinline__ uint32_t line_finish(uint32_t s, uint32_t e, uint32_t A, unsigned long long B, int ext,
+                                                LoadByte lb, Accum& ac) {
+  uint32_t len = e - s;
+  unsigned long long h = 0;
+  if (len) {
+    // N * 2^(8*lead) = B * 2^(64*(m-1)), m = number of 8-byte blocks the line touches
+    const uint32_t lead = s & 7u, m = ((e - 1) >> 3) - (s >> 3) + 1;
+    uint32_t R = (3u * (m - 1) + 61u * 8u - 8u * lead) % 61u;
+    h = rotl61(canon61(B), R);
+    if (lb(e - 1) == 0x0D) {                             // drop one trailing CR: subtract 0x0D * 256^(len-1)
+      --len;
+      const unsigned long long cr = rotl61(0x0Dull, (8u * len) % 61u);
+      h = h >= cr ? h - cr : h + M61 - cr;
+    }
+    h = canon61(h);
+  }
+  ac.lines++;
+  ac.digest += mix_hash(h, len);
+  if (ext == 0) return 0;
+  uint32_t fl = (A & (AF_ASSERT | AF_EXPECT)) ? LF_CAND : 0;
+  bool hdr;
+  if (ext == TSM_EXT_PY) {
+    hdr = (A & PY_DEF) != 0;
+    if (!hdr && (A & PY_CLASS)) hdr = starts_with(lb, s, e, "class", 5, true);
+    if (hdr) { fl |= LF_HDR; if ((A & PY_STF) && starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }
+  } else {
+    hdr = (A & CJ_TEST) && (A & (CJ_BRACE | CJ_CLASS | CJ_VOID));
+    if (hdr) { fl |= LF_HDR; if ((A & CJ_STF) && starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }
+  }
+  ac.asserts += fl & LF_CAND;
+  ac.hdrs += (fl >> 1) & 1u;
+  ac.fixes += (fl >> 2) & 1u;
+  return fl;
+}
+
 // Append `n` list entries with one atomic; returns the base slot (broadcast from lane 0).
 __device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, uint32_t n, int lane) {
   uint32_t base = 0;
@@ -163,56 +181,70 @@ __device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, uint32_t n, 
   return __shfl_sync(0xffffffffu, base, 0);
 }
 
-// Pass 2 + compaction over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
-__device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, const uint8_t* buf,
-                                      const uint16_t* tab, uint8_t* lfl, uint32_t cnt, bool& skip_first,
-                                      uint32_t& next_start, uint32_t f, uint32_t cb, int ext, int lane,
-                                      Accum& ac) {
+struct WarpSmem {                                        // per-warp carve-up of the dynamic shared memory
+  uint8_t* buf; uint16_t* tab; uint8_t* lfl; uint32_t* rawA; unsigned long long* rawB; uint64_t* bar;
+};
+
+// Passes 2-4 over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
+template <bool kAut>
+__device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, uint32_t first, const WarpSmem& ws,
+                                      uint32_t cnt, bool& skip_first, uint32_t& next_start, uint32_t f,
+                                      uint32_t cb, int ext, int lane, Accum& ac) {
   __syncwarp();
   if (cnt == 0) return;
+  const uint8_t* buf = ws.buf;
+  const uint16_t* tab = ws.tab;
   const uint32_t j0 = skip_first ? 1u : 0u;
   const uint32_t ns = next_start;
   const SmemByte lb{buf};
-  uint32_t next = j0;
-  bool active = false;
-  uint32_t myj = 0;
-  LineState L;
-  while (true) {
-    const uint32_t need = __ballot_sync(0xffffffffu, !active);
-    if (need) {
-      const uint32_t j = next + __popc(need & ((1u << lane) - 1u));
-      next += __popc(need);
-      if (!active && j < cnt) {
-        const uint32_t s = j ? (uint32_t)tab[j - 1] + 1u : ns;
-        line_init(L, s, tab[j], lb);
-        myj = j;
-        active = true;
+  for (uint32_t lo = j0; lo < cnt; lo += WALK_BATCH) {
+    const uint32_t hi = min(cnt, lo + WALK_BATCH);
+    // ---- pass 2: walk
+    uint32_t next = lo;
+    bool active = false;
+    uint32_t myj = 0;
+    LineState L;
+    while (true) {
+      const uint32_t need = __ballot_sync(0xffffffffu, !active);
+      if (need) {
+        const uint32_t j = next + __popc(need & ((1u << lane) - 1u));
+        next += __popc(need);
+        if (!active && j < hi) {
+          line_init(L, j ? (uint32_t)tab[j - 1] + 1u : ns, tab[j]);
+          myj = j;
+          active = true;
+        }
+      }
+      if (!__any_sync(0xffffffffu, active)) break;
+      if (active) {
+        if (L.pos < L.e) line_block<kAut>(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
+        if (L.pos < L.e) line_block<kAut>(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
+        if (L.pos >= L.e) {
+          ws.rawA[myj - lo] = L.A;
+          ws.rawB[myj - lo] = L.B;
+          active = false;
+        }
       }
     }
-    if (!__any_sync(0xffffffffu, active)) break;
-    if (active) {
-      if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut);
-      if (L.pos >= L.e) {
-        ac.lines++;
-        ac.digest += mix_hash(canon61(L.acc), L.eh - L.s);
-        const uint32_t fl = line_flags(L, ext, lb);
-        ac.asserts += fl & LF_CAND;
-        ac.hdrs += (fl >> 1) & 1u;
-        ac.fixes += (fl >> 2) & 1u;
-        lfl[myj] = (uint8_t)fl;
-        active = false;
-      }
+    __syncwarp();
+    // ---- pass 3: balanced finalise
+    for (uint32_t j = lo + lane; j < hi; j += 32) {
+      const uint32_t s = j ? (uint32_t)tab[j - 1] + 1u : ns;
+      ws.lfl[j] = (uint8_t)line_finish(s, tab[j], ws.rawA[j - lo], ws.rawB[j - lo], ext, lb, ac);
     }
+    __syncwarp();
   }
-  __syncwarp();
-  // ---- compaction: candidates (always) and header events (on request) to their global lists
+  // ---- pass 4: candidates (always) and header events (on request) to their global lists
+  const uint8_t* lfl = ws.lfl;
   const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
   uint32_t nc = 0, nh = 0;
-  for (uint32_t b = j0; b < cnt; b += 32) {
-    const uint32_t j = b + lane;
-    const uint32_t fb = j < cnt ? lfl[j] : 0u;
-    nc += __popc(__ballot_sync(0xffffffffu, fb & LF_CAND));
-    nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
+  if (ext != 0) {
+    for (uint32_t b = j0; b < cnt; b += 32) {
+      const uint32_t j = b + lane;
+      const uint32_t fb = j < cnt ? lfl[j] : 0u;
+      nc += __popc(__ballot_sync(0xffffffffu, fb & LF_CAND));
+      nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
+    }
   }
   if (!want_hev) nh = 0;
   if (nc | nh) {
@@ -249,21 +281,19 @@ __device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, 
 
 // Slow path: a line that starts in this chunk but ends behind the staged bytes.  Walked by lane 0
 // straight from HBM (correct for any length; lines longer than 240 B past a chunk edge are rare).
-__device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut, uint32_t f, uint32_t fo,
-                                       uint32_t size, int ext, uint32_t s, Accum& ac) {
+__device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut, uint32_t first, uint32_t f,
+                                       uint32_t fo, uint32_t size, int ext, uint32_t s, Accum& ac) {
   const uint8_t* g = p.arena + fo;
   const GmemByte lb{g};
   uint32_t e = s;
   while (e < size && lb(e) != '\n') ++e;
   LineState L;
-  line_init(L, s, e, lb);
-  while (L.pos < L.e) line_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), lut);
-  ac.lines++;
-  ac.digest += mix_hash(canon61(L.acc), L.eh - L.s);
-  const uint32_t fl = line_flags(L, ext, lb);
-  ac.asserts += fl & LF_CAND;
-  ac.hdrs += (fl >> 1) & 1u;
-  ac.fixes += (fl >> 2) & 1u;
+  line_init(L, s, e);
+  while (L.pos < L.e) {
+    const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos));
+    if (ext) line_block<true>(L, w, lut, first); else line_block<false>(L, w, lut, first);
+  }
+  const uint32_t fl = line_finish(s, e, L.A, L.B, ext, lb, ac);
   if (fl & LF_CAND) {
     const uint32_t slot = atomicAdd(&p.ctrl->n_cand, 1u);
     if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | s;
@@ -276,11 +306,12 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
   }
 }
 
-__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, const uint8_t* buf,
-                                              uint16_t* tab, uint8_t* lfl, uint32_t f, uint32_t cb, int lane) {
+template <bool kAut>
+__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, uint32_t first,
+                                              const WarpSmem& ws, uint32_t f, uint32_t cb, int ext, int lane) {
+  const uint8_t* buf = ws.buf;
+  uint16_t* tab = ws.tab;
   const uint32_t size = (uint32_t)p.len[f];
-  const uint32_t fo = (uint32_t)p.off[f];
-  const int ext = p.ext[f];
   const uint32_t ce = min(cb + CH, size);
   const uint32_t le = min(ce + EXT, size);
   const uint32_t lim = PRE + (ce - cb);                  // buffer position just past the owned bytes
@@ -292,7 +323,7 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   // ---- pass 1: newline table of the owned bytes, 512 B per step (16 B per lane, SWAR)
   for (uint32_t tp = PRE; tp < lim; tp += 512) {
     if (cnt + 512 > NL_CAP) {
-      drain(p, lut, buf, tab, lfl, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+      drain<kAut>(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
       cnt = 0;
     }
     const uint32_t pos = tp + lane * 16;
@@ -345,15 +376,15 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   }
   if (have_tail) {
     if (cnt == NL_CAP) {
-      drain(p, lut, buf, tab, lfl, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+      drain<kAut>(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
       cnt = 0;
     }
     if (lane == 0) tab[cnt] = (uint16_t)tail_end;
     ++cnt;
   }
-  drain(p, lut, buf, tab, lfl, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-  if (tail_long && lane == 0) long_line(p, lut, f, fo, size, ext, cb + tail_start - PRE, ac);
-  // ---- per-file counters: warp reduce, then one atomic per counter
+  drain<kAut>(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+  if (tail_long && lane == 0) long_line(p, lut, first, f, (uint32_t)p.off[f], size, ext, cb + tail_start - PRE, ac);
+  // ---- per-file counters: warp reduce, then one store (single-chunk file) or one atomic per counter
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     ac.lines += __shfl_xor_sync(0xffffffffu, ac.lines, d);
@@ -386,48 +417,39 @@ __device__ __forceinline__ void issue_load(const ScanParams& p, uint8_t* buf, ui
   bulk_load(buf + PRE - (cb - lb), p.arena + (size_t)(uint32_t)p.off[f] + lb, bytes, bar);
 }
 
-__global__ void __launch_bounds__(SCAN_WARPS * 32, 4) k_scan(ScanParams p) {
+__global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t* lut = reinterpret_cast<uint32_t*>(smem);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_lut[i];
+  uint32_t* lut_py = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* lut_cj = lut_py + 256;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) lut_py[i] = c_lut[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wb = smem + LUT_BYTES + warp * WARP_SMEM;
-  uint8_t* buf0 = wb;
-  uint8_t* buf1 = wb + BUF;
-  uint16_t* tab = reinterpret_cast<uint16_t*>(wb + 2 * BUF);
-  uint8_t* lfl = wb + 2 * BUF + TAB_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wb + 2 * BUF + TAB_BYTES + LFL_BYTES);
-  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  WarpSmem ws;
+  ws.buf = wb;
+  ws.tab = reinterpret_cast<uint16_t*>(wb + BUF);
+  ws.lfl = wb + BUF + TAB_BYTES;
+  ws.rawB = reinterpret_cast<unsigned long long*>(wb + BUF + TAB_BYTES + LFL_BYTES);
+  ws.rawA = reinterpret_cast<uint32_t*>(wb + BUF + TAB_BYTES + LFL_BYTES + 8 * WALK_BATCH);
+  ws.bar = reinterpret_cast<uint64_t*>(wb + BUF + TAB_BYTES + LFL_BYTES + 12 * WALK_BATCH);
+  if (lane == 0) { mbar_init(ws.bar, 1); fence_mbar_init(); }
   __syncwarp();
   const uint32_t n_units = p.ctrl->n_units;
-  uint32_t phase0 = 0, phase1 = 0;
-  // claim + prefetch the first unit
-  uint32_t u = 0;
-  if (lane == 0) u = atomicAdd(&p.ctrl->work, 1u);
-  u = __shfl_sync(0xffffffffu, u, 0);
-  uint32_t f = 0, cb = 0;
-  if (u < n_units) {
-    f = p.unit_file[u]; cb = p.unit_begin[u];
-    if (lane == 0) issue_load(p, buf0, &bar[0], f, cb);
-  }
-  int cur = 0;
-  while (u < n_units) {
-    // claim the next unit and start its copy into the other buffer
-    uint32_t un = 0;
-    if (lane == 0) un = atomicAdd(&p.ctrl->work, 1u);
-    un = __shfl_sync(0xffffffffu, un, 0);
-    uint32_t fn = 0, cbn = 0;
-    if (un < n_units) {
-      fn = p.unit_file[un]; cbn = p.unit_begin[un];
-      if (lane == 0) issue_load(p, cur ? buf0 : buf1, &bar[cur ^ 1], fn, cbn);
-    }
-    // wait for the current buffer
-    if (cur == 0) { while (!mbar_try_wait(&bar[0], phase0)) {} phase0 ^= 1; }
-    else          { while (!mbar_try_wait(&bar[1], phase1)) {} phase1 ^= 1; }
-    process_chunk(p, lut, cur ? buf1 : buf0, tab, lfl, f, cb, lane);
+  uint32_t phase = 0;
+  while (true) {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(&p.ctrl->work, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= n_units) break;
+    const uint32_t f = p.unit_file[u], cb = p.unit_begin[u];
+    if (lane == 0) issue_load(p, ws.buf, ws.bar, f, cb);
+    const int ext = p.ext[f];
+    while (!mbar_try_wait(ws.bar, phase)) {}
+    phase ^= 1;
+    if (ext == 0) process_chunk<false>(p, lut_py, 0u, ws, f, cb, 0, lane);
+    else if (ext == TSM_EXT_PY) process_chunk<true>(p, lut_py, PY_FIRST, ws, f, cb, ext, lane);
+    else process_chunk<true>(p, lut_cj, CJ_FIRST, ws, f, cb, ext, lane);
     __syncwarp();
-    u = un; f = fn; cb = cbn; cur ^= 1;
   }
 }
 
