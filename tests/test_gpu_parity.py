@@ -180,3 +180,49 @@ def test_errors_are_reported_not_swallowed(scanner):
         small.scan(ts.pack([b"x" * 9000], [1]))
     assert e.value.status == -3
     small.close()
+
+
+def _pairs(seed, n, size_cap, lam=6.0):
+    """BASELINE config C5 shape: old ~ C4 law capped, new = old with Poisson(lam) line edits."""
+    base = ts.gen_corpus(0x7053454D0005 + seed, n, size_law=1, pinned=False)
+    olds = [base.file_bytes(i)[:size_cap] for i in range(n)]
+    news = [ts.gen_edit(1000 + seed * 7919 + i, o, lam) for i, o in enumerate(olds)]
+    return olds, news
+
+
+def check_diff(scanner, olds, news):
+    a = ts.pack(olds, [1] * len(olds))
+    b = ts.pack(news, [1] * len(news))
+    add, rem = scanner.diff_pairs(a, b)
+    wadd, wrem = orc.diff_pairs((a.arena, a.off, a.len), (b.arena, b.off, b.len))
+    bad = np.nonzero((add != wadd) | (rem != wrem))[0]
+    assert bad.size == 0, (bad[:5], add[bad[:5]], wadd[bad[:5]], rem[bad[:5]], wrem[bad[:5]])
+    return add, rem
+
+
+def test_diff_edge_cases(scanner):
+    olds = [b"", b"a\n", b"a\nb\nc\n", b"a\nb\nc", b"x\n" * 100, b"same\n" * 50, b"a\nb\n", b"q\r\nr\n", b"1\n2\n3\n4\n5\n",
+            b"\n\n\n", b"only old\n", b""]
+    news = [b"", b"a\n", b"a\nc\n", b"a\nb\nc\n", b"y\n" * 70, b"same\n" * 50, b"b\na\n", b"q\nr\r\n", b"5\n4\n3\n2\n1\n",
+            b"\n", b"", b"only new\nsecond\n"]
+    add, rem = check_diff(scanner, olds, news)
+    assert (add[0], rem[0]) == (0, 0) and (add[2], rem[2]) == (0, 1) and (add[4], rem[4]) == (70, 100)
+    assert (add[7], rem[7]) == (0, 0)          # a trailing CR is not part of the line content (SPEC section 3)
+    assert (add[3], rem[3]) == (0, 0)          # "c" with and without a final newline is the same line
+
+
+def test_diff_c5_shape(scanner):
+    olds, news = _pairs(1, 400, 65536)
+    add, rem = check_diff(scanner, olds, news)
+    assert add.sum() > 0 and rem.sum() > 0
+    # cloc = added + removed (ML-Testing-v1.xlsx!projects:R1) and the identity pair has none
+    same_add, same_rem = scanner.diff_pairs(ts.pack(olds[:50], [1] * 50), ts.pack(olds[:50], [1] * 50))
+    assert same_add.sum() == 0 and same_rem.sum() == 0
+
+
+def test_diff_heavy_edits_and_unrelated_files(scanner):
+    olds, news = _pairs(2, 60, 20000, lam=80.0)
+    check_diff(scanner, olds, news)
+    olds2, _ = _pairs(3, 40, 12000)
+    _, news2 = _pairs(4, 40, 12000)
+    check_diff(scanner, olds2, news2)          # unrelated files: D close to n + m

@@ -412,8 +412,85 @@ extern "C" void* tsm_host_alloc(int64_t bytes) {
 extern "C" void tsm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------- S8 diff
+namespace {
+struct DevBuf {                                           // cudaMalloc'd scratch, freed on scope exit
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct HostSide {                                         // device image of one side of the pairs
+  DevBuf arena, off, len, n_lines, line_base, line_end, line_hash;
+  std::vector<unsigned long long> base;                   // host copy of line_base
+  DiffSide d{};
+};
+
+int side_lines(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
+  const int32_t n = k->n_files;
+  const size_t ab = (size_t)k->off[n];
+  if (!h.arena.alloc(ab + 4096) || !h.off.alloc(sizeof(int32_t) * ((size_t)n + 1)) || !h.len.alloc(sizeof(int32_t) * (size_t)n) ||
+      !h.n_lines.alloc(sizeof(uint32_t) * (size_t)n) || !h.line_base.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
+    return TSM_E_CUDA;
+  CU(cudaMemsetAsync(h.arena.as<uint8_t>() + ab, 0, 4096, st));
+  CU(cudaMemcpyAsync(h.arena.p, k->arena, ab, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h.off.p, k->off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h.len.p, k->len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  h.d.arena = h.arena.as<uint8_t>(); h.d.off = h.off.as<int32_t>(); h.d.len = h.len.as<int32_t>();
+  h.d.n_lines = h.n_lines.as<uint32_t>();
+  k_count_lines<<<(n * 32 + 255) / 256, 256, 0, st>>>(h.d, n);
+  std::vector<uint32_t> nl((size_t)n);
+  CU(cudaMemcpyAsync(nl.data(), h.n_lines.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  h.base.assign((size_t)n + 1, 0);
+  for (int32_t i = 0; i < n; ++i) h.base[(size_t)i + 1] = h.base[(size_t)i] + nl[(size_t)i];
+  const unsigned long long total = h.base[(size_t)n];
+  if (!h.line_end.alloc(sizeof(uint32_t) * (size_t)total) || !h.line_hash.alloc(sizeof(unsigned long long) * (size_t)total))
+    return TSM_E_CUDA;
+  CU(cudaMemcpyAsync(h.line_base.p, h.base.data(), sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  h.d.line_base = h.line_base.as<unsigned long long>();
+  h.d.line_end = h.line_end.as<uint32_t>();
+  h.d.line_hash = h.line_hash.as<unsigned long long>();
+  k_mark_lines<<<(n * 32 + 255) / 256, 256, 0, st>>>(h.d, n);
+  if (total) k_hash_lines<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h.d, n, total);
+  CU(cudaGetLastError());
+  return TSM_OK;
+}
+}  // namespace
+
 extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
                               int64_t* added, int64_t* removed, void* stream) {
-  (void)c; (void)olds; (void)news; (void)added; (void)removed; (void)stream;
-  return TSM_E_STATE;   // implemented in tsm_diff_kernels.cuh (next milestone)
+  if (!c || !olds || !news || !added || !removed || olds->n_files != news->n_files) return TSM_E_ARG;
+  const int32_t n = olds->n_files;
+  if (n == 0) return TSM_OK;
+  for (const tsm_corpus* k : {olds, news}) {              // same layout rules as the scan (SPEC section 1)
+    if (!k->arena || !k->off || !k->len) return TSM_E_ARG;
+    for (int32_t i = 0; i < n; ++i)
+      if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1])
+        return TSM_E_LAYOUT;
+  }
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  HostSide A, B;
+  int rc = side_lines(olds, A, st);
+  if (rc == TSM_OK) rc = side_lines(news, B, st);
+  if (rc != TSM_OK) return rc;
+  std::vector<unsigned long long> vbase((size_t)n + 1, 0);
+  for (int32_t i = 0; i < n; ++i)
+    vbase[(size_t)i + 1] = vbase[(size_t)i] + 2 * ((A.base[(size_t)i + 1] - A.base[(size_t)i]) + (B.base[(size_t)i + 1] - B.base[(size_t)i])) + 3;
+  DevBuf d_vbase, d_v, d_add, d_rem;
+  if (!d_vbase.alloc(sizeof(unsigned long long) * ((size_t)n + 1)) || !d_v.alloc(sizeof(int32_t) * (size_t)vbase[(size_t)n]) ||
+      !d_add.alloc(sizeof(long long) * (size_t)n) || !d_rem.alloc(sizeof(long long) * (size_t)n))
+    return TSM_E_CUDA;
+  CU(cudaMemcpyAsync(d_vbase.p, vbase.data(), sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  k_myers<<<(n * 32 + 127) / 128, 128, 0, st>>>(A.d.line_hash, A.d.line_base, B.d.line_hash, B.d.line_base, n,
+                                               d_v.as<int32_t>(), d_vbase.as<unsigned long long>(),
+                                               d_add.as<long long>(), d_rem.as<long long>());
+  CU(cudaGetLastError());
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  CU(cudaMemcpyAsync(added, d_add.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(removed, d_rem.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  c->launches = 7;
+  return TSM_OK;
 }

@@ -1,3 +1,145 @@
-// tsm_diff_kernels.cuh - S8 revision-pair churn (docs/SPEC.md section 8).  Placeholder: filled in below.
+// tsm_diff_kernels.cuh - S8 revision-pair churn (docs/SPEC.md section 8): per (old, new) pair the number of
+// added / removed lines = |new| - LCS, |old| - LCS over the SPEC section 3 line-hash sequences.
+// Pins: Important-files/ML-Testing-v1.xlsx!projects:R1 (`cloc = added + removed`); no revision
+// history ships, so parity is against the oracle's O(n*m) DP (a different algorithm: here Myers O(ND)).
+//
+//   k_count_lines   warp per file: SWAR newline count                     -> n_lines[file]
+//   k_mark_lines    warp per file: ordered newline positions (ballot compaction) -> line_end[]
+//   k_hash_lines    thread per line: Mersenne-61 line hash from HBM       -> line_hash[]
+//   k_myers         warp per pair: common prefix/suffix trim, then the greedy furthest-reaching
+//                   D-path search with the diagonals of one D spread over the lanes
 #pragma once
-#include "tsm_device.cuh"
+#include "tsm_scan_kernels.cuh"
+
+namespace tsm {
+
+struct DiffSide {                   // one corpus (old or new) on the device
+  const uint8_t* arena; const int32_t* off; const int32_t* len;
+  uint32_t* n_lines;                // [n]
+  const unsigned long long* line_base;   // [n+1] exclusive prefix of n_lines
+  uint32_t* line_end;               // [total lines] file-relative end of each line (position of its LF or EOF)
+  unsigned long long* line_hash;    // [total lines]
+};
+
+__device__ __forceinline__ uint32_t nl16_at(const uint8_t* g, uint32_t pos, uint32_t size) {
+  // 16 bytes at file offset pos (16-B aligned; the arena is padded so the load is in bounds)
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + pos));
+  uint32_t bits = nl16(v);
+  const uint32_t valid = size - pos;
+  if (valid < 16) bits &= (1u << valid) - 1u;
+  return bits;
+}
+
+__global__ void k_count_lines(DiffSide d, int32_t n) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (f >= n) return;
+  const uint8_t* g = d.arena + (uint32_t)d.off[f];
+  const uint32_t size = (uint32_t)d.len[f];
+  uint32_t c = 0;
+  for (uint32_t pos = lane * 16; pos < size; pos += 512) c += __popc(nl16_at(g, pos, size));
+#pragma unroll
+  for (int k = 16; k; k >>= 1) c += __shfl_xor_sync(0xffffffffu, c, k);
+  if (lane == 0) d.n_lines[f] = c + ((size && __ldg(g + size - 1) != '\n') ? 1u : 0u);   // unterminated last line
+}
+
+__global__ void k_mark_lines(DiffSide d, int32_t n) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (f >= n) return;
+  const uint8_t* g = d.arena + (uint32_t)d.off[f];
+  const uint32_t size = (uint32_t)d.len[f];
+  unsigned long long at = d.line_base[f];
+  for (uint32_t tp = 0; tp < size; tp += 512) {
+    const uint32_t pos = tp + lane * 16;
+    uint32_t bits = pos < size ? nl16_at(g, pos, size) : 0u;
+    const uint32_t c = __popc(bits);
+    uint32_t incl = c;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, k);
+      if (lane >= k) incl += t;
+    }
+    unsigned long long idx = at + incl - c;
+    while (bits) { d.line_end[idx++] = pos + (__ffs(bits) - 1); bits &= bits - 1; }
+    at += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0 && size && __ldg(g + size - 1) != '\n') d.line_end[at] = size;
+}
+
+__global__ void k_hash_lines(DiffSide d, int32_t n, unsigned long long total) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // file of line i: binary search in line_base
+  int lo = 0, hi = n;                                   // line_base[lo] <= i < line_base[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (d.line_base[mid] <= i) lo = mid; else hi = mid; }
+  const int f = lo;
+  const uint8_t* g = d.arena + (uint32_t)d.off[f];
+  const uint32_t e = d.line_end[i];
+  const uint32_t s = (i == d.line_base[f]) ? 0u : d.line_end[i - 1] + 1u;
+  LineState L;
+  line_init(L, s, e);
+  while (L.pos < L.e) line_block<false>(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), nullptr, 0u);
+  Accum ac{0, 0, 0, 0, 0};
+  line_finish(s, e, 0u, L.B, 0, GmemByte{g}, ac);       // ext 0: hash only; digest of one line = its hash
+  d.line_hash[i] = ac.digest;
+}
+
+// Edit distance D (insertions + deletions) of hash sequences a[0..n) and b[0..m); one warp per pair.
+// V (furthest x per diagonal) lives in global scratch of 2*(n+m)+3 ints per pair.
+__global__ void k_myers(const unsigned long long* ha, const unsigned long long* la, const unsigned long long* hb,
+                        const unsigned long long* lb, int32_t n_pairs, int32_t* vbuf, const unsigned long long* vbase,
+                        long long* added, long long* removed) {
+  const int pr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pr >= n_pairs) return;
+  const unsigned long long* a = ha + la[pr];
+  const unsigned long long* b = hb + lb[pr];
+  int n = (int)(la[pr + 1] - la[pr]), m = (int)(lb[pr + 1] - lb[pr]);
+  const int n0 = n, m0 = m;
+  // common prefix
+  int pre = 0;
+  while (true) {
+    const int i = pre + lane;
+    const bool ne = !(i < n && i < m && a[i] == b[i]);
+    const uint32_t mk = __ballot_sync(0xffffffffu, ne);
+    if (mk) { pre += __ffs(mk) - 1; break; }
+    pre += 32;
+  }
+  a += pre; b += pre; n -= pre; m -= pre;
+  int suf = 0;
+  while (true) {
+    const int i = suf + lane;
+    const bool ne = !(i < n && i < m && a[n - 1 - i] == b[m - 1 - i]);
+    const uint32_t mk = __ballot_sync(0xffffffffu, ne);
+    if (mk) { suf += __ffs(mk) - 1; break; }
+    suf += 32;
+  }
+  n -= suf; m -= suf;
+  int D = 0;
+  if (n == 0 || m == 0) D = n + m;
+  else {
+    int32_t* V = vbuf + vbase[pr] + (n + m + 1);          // V[k], k in [-(n+m)-1, n+m+1]
+    if (lane == 0) V[1] = 0;
+    __syncwarp();
+    bool done = false;
+    for (D = 0; D <= n + m && !done; ++D) {
+      bool hit = false;
+      for (int k = -D + 2 * lane; k <= D; k += 64) {
+        int x;
+        if (k == -D || (k != D && V[k - 1] < V[k + 1])) x = V[k + 1]; else x = V[k - 1] + 1;
+        int y = x - k;
+        while (x < n && y < m && a[x] == b[y]) { ++x; ++y; }
+        V[k] = x;
+        if (x >= n && y >= m) hit = true;
+      }
+      __syncwarp();
+      done = __any_sync(0xffffffffu, hit);
+    }
+    --D;                                                  // the loop increments once more after the hit
+  }
+  if (lane == 0) {
+    const long long lcs = ((long long)(n + m) - D) / 2 + pre + suf;
+    removed[pr] = n0 - lcs;
+    added[pr] = m0 - lcs;
+  }
+}
+
+}  // namespace tsm
