@@ -1,0 +1,185 @@
+"""The C++ host driver `tosem-scan`: CSV schemas of the reference's shipped tables, rows built by the
+product (GPU events + host method strings) against rows built from the oracle's line functions."""
+import collections
+import csv
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import corpus_util as cu
+import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "tosem-2021-replication_b200", "tosemscan", "tosem-scan")
+EXT = {"py": 1, "cc": 2, "cpp": 3, "java": 4, "c": 5, "h": 6}
+
+
+def test_cli_builds_and_prints_usage():
+    assert os.path.exists(CLI), "run __graft_entry__.build()"
+    out = subprocess.run([CLI, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "tosem-scan scan" in out.stderr
+
+
+def make_tree(root):
+    files = {
+        "tests/test_agent.py": cu.PY_SAMPLE,
+        "modules/perception/fusion/common/dst_evidence_test.cc": cu.CC_SAMPLE,
+        "integration/java/MapDecodeTest.java": cu.JAVA_SAMPLE,
+        "external/lib/test_api.py": b"def test_fastCopyAndTranspose():\n    assert_equal(b, a.T)\n    assert_equal(b, a.T)\n",
+        "third_party/protobuf-3.5/smoke/unit_test.cpp": b"TEST_F(Fix, A) {\n  EXPECT_EQ(1, 2);\n  EXPECT_EQ(1,\n 2);\n}\nvoid g() { ASSERT_TRUE(x); }\n",
+        "regression/weird,name\"test.c": b"int testmain(void) {\n  assert(x == \"a,b\");\n  assert(x == \"a,b\");\n}\n",
+        "src/main.py": b"assert False\n",                      # no `test` in the path: not selected
+        "tests/data.json": b'{"assert": 1}\n',                  # no scannable extension: no rows
+        "tests/empty_test.py": b"",
+    }
+    for rel, data in files.items():
+        p = os.path.join(root, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        open(p, "wb").write(data)
+    return files
+
+
+def tag(rel, fixture):
+    if rel.startswith("external/"):
+        t = "external"
+    elif "integration" in rel:
+        t = "integration"
+    elif "regression" in rel:
+        t = "regression"
+    elif "swarming" in rel:
+        t = "swarming"
+    else:
+        t = "unit_test"
+    comps = rel.split("/")[:-1]
+    if any(c.startswith("protobuf-") for c in comps):
+        t += ", Protocol Buffers"
+    if "smoke" in comps:
+        t += ", smoke"
+    return t + (", Fixture" if fixture else "")
+
+
+def expected(files):
+    """Rows and per-file summaries from the oracle's line-level functions (docs/SPEC.md sections 2-7)."""
+    rows, summ = [], []
+    sel = sorted((r for r in files if "test" in r.lower() and r.rsplit(".", 1)[-1] in EXT), key=lambda r: r.split("/"))
+    for i, rel in enumerate(sel, start=1):
+        data, ext = files[rel], EXT[rel.rsplit(".", 1)[-1]]
+        cur = (-1, False, b"xxxx")
+        keyed = collections.OrderedDict()
+        hist = collections.OrderedDict()
+        pos = 0
+        while pos < len(data):
+            e = data.find(b"\n", pos)
+            e = len(data) if e < 0 else e
+            line = data[pos:e]
+            hk = orc.header_kind(ext, line)
+            if hk:
+                cur = (pos, bool(hk & 2), orc.method_string(ext, line))
+            if orc.is_assert_line(line):
+                st = orc.statement(line)
+                cat = orc.category_string(st)
+                k = (cur[0], st)
+                if k not in keyed:
+                    keyed[k] = [cur, st, cat, 0]
+                keyed[k][3] += 1
+                hist[cat] = hist.get(cat, 0) + 1
+            pos = e + 1
+        for cur_, st, cat, n in keyed.values():
+            rows.append([rel, rel.rsplit(".", 1)[-1], tag(rel, cur_[1]), cur_[2].decode("latin-1"), st.decode("latin-1"), str(n), cat])
+        order = sorted(hist, key=lambda c: -hist[c])
+        summ.append([str(i), rel, str(sum(hist.values())), ", ".join("%d:%s" % (hist[c], c) for c in order)])
+    return rows, summ
+
+
+def read_csv(path):
+    raw = open(path, "rb").read()
+    assert b"\n" not in raw.replace(b"\r\n", b""), "CRLF line ends only"
+    return list(csv.reader(io.StringIO(raw.decode("latin-1"), newline="")))
+
+
+@pytest.mark.gpu
+def test_scan_rows_and_summary(tmp_path):
+    files = make_tree(str(tmp_path / "proj"))
+    rows_p, sum_p = str(tmp_path / "rows.csv"), str(tmp_path / "summary.csv")
+    out = subprocess.run([CLI, "scan", str(tmp_path / "proj"), "--rows", rows_p, "--summary", sum_p], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    want_rows, want_sum = expected(files)
+    got = read_csv(rows_p)
+    assert got[0] == ["fileName", "extension", "test_name", "method", "statement", "counts", "category"]
+    assert got[1:] == want_rows
+    gs = read_csv(sum_p)
+    assert gs[0] == ["Id", "FileName", "total assert", "assertion"] and gs[1:] == want_sum
+    # spot checks against the reference's own example cells (ML-Testing-v1.xlsx!apollo_tests:R8-R10, !prefect_tests:R2)
+    flat = {(r[0], r[3], r[4]): r for r in got[1:]}
+    r = flat[("modules/perception/fusion/common/dst_evidence_test.cc", ': sensor1_dst_("test"', "EXPECT_NEAR")]
+    assert r[2] == "unit_test" and r[5] == "1" and r[6] == "assertAlmostEqual"
+    r = flat[("tests/test_agent.py", "test_docker_agent_init(monkeypatch,runner_token)", "assert agent.labels == []")]
+    assert r[6] == "assertEqual"
+    assert flat[("third_party/protobuf-3.5/smoke/unit_test.cpp", "TEST_F(Fix, A", "EXPECT_EQ")][2] == "unit_test, Protocol Buffers, smoke, Fixture"
+    assert flat[("external/lib/test_api.py", "test_fastCopyAndTranspose()", "assert_equal")][5] == "2"
+    # the aggregate table on stdout sums to the number of assertion lines
+    agg = [l.split(",") for l in out.stdout.replace("\r\n", "\n").strip().split("\n")[1:]]
+    assert sum(int(a[-1]) for a in agg) == sum(int(s[2]) for s in want_sum)
+
+
+@pytest.mark.gpu
+def test_reduce_tables(tmp_path):
+    rng = np.random.default_rng(5)
+    repos = ["autokeras", "auto_sklearn", "tpot", "Ray", "DeepSpeech2", "google_automl", "nni", "Apollo", "Nupic"]
+    cols = ["Index", "Labels", "Cases", "Repo", "status_test", "Error_Type", "negative_test", "logical_statement",
+            "logical_expression", "null_pointer", "value_range", "Approximation_Type", "checks_type", "regression",
+            "Integration", "mock_test", "API"]
+    lines, recs = [cols], []
+    for i in range(600):
+        repo = repos[int(rng.integers(0, 9))]
+        rec = {"Index": str(i), "Labels": 'a "quoted", label\nwith a newline' if i % 50 == 0 else "x", "Cases": str(int(rng.integers(0, 120))) + repo[:2],
+               "Repo": repo, "status_test": str(int(rng.random() < 0.3)), "Error_Type": ["", "ValueError", "RuntimeError"][int(rng.integers(0, 3))],
+               "negative_test": str(int(rng.random() < 0.2)), "logical_statement": "0", "logical_expression": str(int(rng.random() < 0.1)),
+               "null_pointer": "0", "value_range": str(int(rng.random() < 0.4)), "Approximation_Type": ["", "rounding_tolence"][int(rng.integers(0, 2))],
+               "checks_type": ["", "instance_check"][int(rng.integers(0, 2))], "regression": "0", "Integration": str(int(rng.random() < 0.05)),
+               "mock_test": str(int(rng.random() < 0.1)), "API": ""}
+        recs.append(rec)
+        lines.append([rec[c] for c in cols])
+    tax = tmp_path / "taxonomy.csv"
+    with open(tax, "w", newline="", encoding="utf-8") as f:
+        csv.writer(f, lineterminator="\r\n").writerows(lines)
+    sp, mp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    s = read_csv(sp)
+    assert s[0][:10] == ["Tests"] + repos
+    cases = {r: {x["Cases"] for x in recs if x["Repo"] == r} for r in repos}
+    row = {x[0]: x for x in s[1:]}
+    for name, pred in [("status_analysis", lambda x: x["status_test"] == "1"), ("value_error", lambda x: x["Error_Type"] == "ValueError"),
+                       ("logical_condition", lambda x: x["logical_statement"] == "1" or x["logical_expression"] == "1"),
+                       ("rounding_tolence", lambda x: x["Approximation_Type"] == "rounding_tolence")]:
+        for k, r in enumerate(repos):
+            d = len({x["Cases"] for x in recs if x["Repo"] == r and pred(x)})
+            v = round(round(100.0 * d / len(cases[r]), 4) / 1.1, 4)
+            assert row[name][1 + k] == (("%.4f" % v).rstrip("0").rstrip(".") or "0"), (name, r)
+    m = {x[0]: x for x in read_csv(mp)[1:]}
+    tot = sum(len(c) for c in cases.values())
+    d = len({(x["Repo"], x["Cases"]) for x in recs if x["mock_test"] not in ("", "0")})
+    assert m["mock_test"][1] == str(d) and m["mock_test"][2] == (("%.4f" % round(100.0 * d / tot, 4)).rstrip("0").rstrip(".") or "0")
+
+
+@pytest.mark.gpu
+def test_diff_trees(tmp_path):
+    old, new = tmp_path / "old", tmp_path / "new"
+    os.makedirs(old / "a")
+    os.makedirs(new / "a")
+    (old / "a" / "x.py").write_bytes(b"1\n2\n3\n4\n")
+    (new / "a" / "x.py").write_bytes(b"1\n3\n4\n5\n6\n")
+    (old / "gone.c").write_bytes(b"a\nb\n")
+    (new / "fresh.c").write_bytes(b"c\n")
+    (old / "same.h").write_bytes(b"s\n")
+    (new / "same.h").write_bytes(b"s\n")
+    outp = str(tmp_path / "churn.csv")
+    out = subprocess.run([CLI, "diff", str(old), str(new), "--out", outp], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.replace("\r\n", "\n").strip().split("\n") == ["cloc,added,removed", "6,3,3"]
+    got = {r[0]: r[1:] for r in read_csv(outp)[1:]}
+    assert got == {"a/x.py": ["3", "2", "1"], "gone.c": ["2", "0", "2"], "fresh.c": ["1", "1", "0"]}

@@ -1,0 +1,547 @@
+// tosem_scan_cli.cpp - `tosem-scan`, the C++ host driver of the corpus-scan loop.
+//
+// The reference package ships no entry point to stay compatible with; what it
+// ships are the loop's OUTPUT SCHEMAS, and this driver writes exactly those:
+//   raw rows      fileName,extension,test_name,method,statement,counts,category
+//                 (Important-files/ML-Testing-v1.xlsx!apollo_tests:R1)
+//   per-file      Id,FileName,total assert,assertion   ("32:assertEqual, 15:assertIn, ...")
+//                 (selection/completed-labels/Release-Meta-tpot.csv:1-2)
+//   RQ tables     RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/tests_methods_v2.csv from
+//                 RQs/taxonomy_test2.csv
+//   churn         cloc,added,removed  (Important-files/ML-Testing-v1.xlsx!projects:R1)
+// All CSVs are CRLF, UTF-8, RFC-4180 quoted, like every CSV the package ships.
+//
+// Host work only: tree walk + test-file selection (S0), extension / test_name tags (S1, S2), packing
+// into the pinned byte arena, method strings (S3, host side of SPEC section 5), CSV.  Every byte of the scan
+// itself goes through libtosemscan.so (sm_100a kernels); there is no CPU fallback.
+//
+//   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files]
+//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]
+//   tosem-scan diff   <old-root> <new-root> [--out F]
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "../../include/tosemscan.h"
+
+namespace fs = std::filesystem;
+
+static bool die(const std::string& m) { fprintf(stderr, "tosem-scan: %s\n", m.c_str()); exit(2); return false; }
+static void ck(int rc, const char* what) { if (rc != TSM_OK) die(std::string(what) + ": " + tsm_strerror(rc)); }
+
+static std::string lower(std::string s) { for (char& c : s) if (c >= 'A' && c <= 'Z') c = (char)(c + 32); return s; }
+static bool is_w(unsigned char c) { return c == 0x20 || c == 0x09 || c == 0x0D || c == 0x0B || c == 0x0C; }
+
+// ---------------------------------------------------------------------------------- CSV (RFC 4180, CRLF)
+static std::string csv_cell(const std::string& s) {
+  if (s.find_first_of(",\"\r\n") == std::string::npos) return s;
+  std::string o = "\"";
+  for (char c : s) { if (c == '"') o += '"'; o += c; }
+  return o + "\"";
+}
+static void csv_row(std::ostream& os, const std::vector<std::string>& cells) {
+  for (size_t i = 0; i < cells.size(); ++i) { if (i) os << ','; os << csv_cell(cells[i]); }
+  os << "\r\n";
+}
+static std::vector<std::vector<std::string>> csv_read(const std::string& path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) die("cannot open " + path);
+  std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  if (data.compare(0, 3, "\xEF\xBB\xBF") == 0) data.erase(0, 3);
+  std::vector<std::vector<std::string>> rows;
+  std::vector<std::string> row;
+  std::string cell;
+  bool q = false, any = false;
+  for (size_t i = 0; i < data.size(); ++i) {
+    const char c = data[i];
+    if (q) {
+      if (c == '"') { if (i + 1 < data.size() && data[i + 1] == '"') { cell += '"'; ++i; } else q = false; }
+      else cell += c;
+    } else if (c == '"') { q = true; any = true; }
+    else if (c == ',') { row.push_back(cell); cell.clear(); any = true; }
+    else if (c == '\n' || c == '\r') {
+      if (c == '\r' && i + 1 < data.size() && data[i + 1] == '\n') ++i;
+      if (any || !cell.empty()) { row.push_back(cell); rows.push_back(row); }
+      row.clear(); cell.clear(); any = false;
+    } else { cell += c; any = true; }
+  }
+  if (any || !cell.empty()) { row.push_back(cell); rows.push_back(row); }
+  return rows;
+}
+
+// ---------------------------------------------------------------------------------- S0-S2: walk and tag
+struct FileEntry { std::string rel, abs; int ext; int grp; int64_t size; };
+
+static int ext_tag(const std::string& rel) {               // S1
+  const size_t d = rel.rfind('.');
+  if (d == std::string::npos || rel.find('/', d) != std::string::npos) return TSM_EXT_OTHER;
+  const std::string e = rel.substr(d + 1);
+  if (e == "py") return TSM_EXT_PY;
+  if (e == "cc") return TSM_EXT_CC;
+  if (e == "cpp") return TSM_EXT_CPP;
+  if (e == "java") return TSM_EXT_JAVA;
+  if (e == "c") return TSM_EXT_C;
+  if (e == "h") return TSM_EXT_H;
+  return TSM_EXT_OTHER;
+}
+static const char* ext_name(int t) { static const char* n[] = {"", "py", "cc", "cpp", "java", "c", "h"}; return n[t]; }
+
+static std::string test_name_tag(const std::string& rel, bool fixture) {   // S2 (mock / Module: parity unpinned, omitted)
+  std::string t;
+  if (rel.rfind("external/", 0) == 0) t = "external";
+  else if (rel.find("integration") != std::string::npos) t = "integration";
+  else if (rel.find("regression") != std::string::npos) t = "regression";
+  else if (rel.find("swarming") != std::string::npos) t = "swarming";
+  else t = "unit_test";
+  bool proto = false, smoke = false;
+  size_t p = 0;
+  while (p < rel.size()) {
+    size_t q = rel.find('/', p);
+    if (q == std::string::npos) break;                     // last component is the file name
+    const std::string comp = rel.substr(p, q - p);
+    if (comp.rfind("protobuf-", 0) == 0) proto = true;
+    if (comp == "smoke") smoke = true;
+    p = q + 1;
+  }
+  if (proto) t += ", Protocol Buffers";
+  if (smoke) t += ", smoke";
+  if (fixture) t += ", Fixture";
+  return t;
+}
+
+static void walk(const std::string& root, int grp, bool all_files, std::vector<FileEntry>& out) {
+  std::vector<fs::path> paths;
+  for (auto it = fs::recursive_directory_iterator(root, fs::directory_options::skip_permission_denied);
+       it != fs::recursive_directory_iterator(); ++it)
+    if (it->is_regular_file() && !it->is_symlink()) paths.push_back(it->path());
+  std::sort(paths.begin(), paths.end());
+  for (const fs::path& p : paths) {
+    const std::string rel = fs::relative(p, root).generic_string();
+    const int ext = ext_tag(rel);
+    if (!all_files) {
+      if (lower(rel).find("test") == std::string::npos) continue;          // S0: path contains `test`
+      if (ext == TSM_EXT_OTHER) continue;                                   // S1: no rows for other extensions
+    }
+    out.push_back({rel, p.string(), ext, grp, (int64_t)fs::file_size(p)});
+  }
+}
+
+// ---------------------------------------------------------------------------------- S3: method strings
+static std::string method_string(int ext, const uint8_t* line, uint32_t len) {   // docs/SPEC.md section 5
+  uint32_t b = 0, e = len;
+  while (b < e && is_w(line[b])) ++b;
+  while (e > b && is_w(line[e - 1])) --e;
+  auto sw = [&](uint32_t i, const char* pat) { const size_t m = strlen(pat); return i + m <= e && memcmp(line + i, pat, m) == 0; };
+  std::string o;
+  if (ext == TSM_EXT_PY) {
+    uint32_t i = b;
+    if (sw(i, "class")) i += 5;
+    while (i < e) {
+      if (sw(i, "def")) { i += 3; continue; }
+      if (!is_w(line[i])) o += (char)line[i];
+      ++i;
+    }
+    if (!o.empty() && o.back() == ':') o.pop_back();
+  } else if (ext == TSM_EXT_JAVA) {
+    static const char* const words[] = {"public", "private", "protected", "static", "void", "class"};
+    uint32_t i = b;
+    while (i < e) {
+      bool hit = false;
+      for (const char* w : words) if (sw(i, w)) { i += (uint32_t)strlen(w); hit = true; break; }
+      if (hit) continue;
+      if (!is_w(line[i])) o += (char)line[i];
+      ++i;
+    }
+  } else {
+    uint32_t t = b;
+    while (t < e && line[t] != ')') ++t;
+    uint32_t s = b, u = t;
+    while (s < t && (is_w(line[s]) || line[s] == '{')) ++s;
+    while (u > s && (is_w(line[u - 1]) || line[u - 1] == '{')) --u;
+    for (uint32_t i = s; i < u; ++i) if (line[i] != '{') o += (char)line[i];
+  }
+  return o;
+}
+
+// ---------------------------------------------------------------------------------- scan
+struct Batch {                                             // one packed arena (<= ~1 GiB) of consecutive files
+  size_t first = 0, count = 0;
+  Batch() = default;
+  Batch(size_t f, size_t c) : first(f), count(c) {}
+  std::vector<int32_t> off, len;
+  std::vector<uint8_t> ext;
+  std::vector<uint16_t> grp;
+  uint8_t* arena = nullptr;
+  int64_t bytes = 0;
+};
+
+static void load_batch(const std::vector<FileEntry>& files, Batch& b) {
+  b.len.resize(b.count); b.off.resize(b.count + 1); b.ext.resize(b.count); b.grp.resize(b.count);
+  for (size_t i = 0; i < b.count; ++i) {
+    const FileEntry& f = files[b.first + i];
+    b.len[i] = (int32_t)f.size; b.ext[i] = (uint8_t)f.ext; b.grp[i] = (uint16_t)f.grp;
+  }
+  b.bytes = tsm_layout(b.len.data(), (int32_t)b.count, b.off.data());
+  if (b.bytes < 0) die("batch does not fit an int32-indexed arena");
+  b.arena = (uint8_t*)tsm_host_alloc(std::max<int64_t>(b.bytes, 128));
+  if (!b.arena) die("pinned arena allocation failed (no CUDA device? there is no CPU fallback)");
+  memset(b.arena, 0, (size_t)std::max<int64_t>(b.bytes, 128));
+  for (size_t i = 0; i < b.count; ++i) {
+    std::ifstream in(files[b.first + i].abs, std::ios::binary);
+    in.read((char*)b.arena + b.off[i], b.len[i]);
+    if (in.gcount() != b.len[i]) die("short read: " + files[b.first + i].abs);
+  }
+}
+
+struct ScanOut {
+  std::vector<tsm_file_stat> stats;
+  std::vector<tsm_assert_event> aev;
+  std::vector<tsm_header_event> hev;
+  std::vector<int64_t> group_counts;
+};
+
+static int cmd_scan(const std::vector<std::string>& roots, const std::string& rows_path, const std::string& summary_path,
+                    int gpus, bool all_files) {
+  std::vector<FileEntry> files;
+  for (size_t g = 0; g < roots.size(); ++g) walk(roots[g], (int)g, all_files, files);
+  const int n_groups = (int)std::max<size_t>(roots.size(), 1);
+  fprintf(stderr, "tosem-scan: %zu files selected under %zu root(s)\n", files.size(), roots.size());
+  // batches of consecutive files, each at most ~1 GiB of arena and 1M files
+  std::vector<Batch> batches;
+  {
+    int64_t cur = 0; size_t first = 0;
+    for (size_t i = 0; i < files.size(); ++i) {
+      if (files[i].size >= (1ll << 30)) die("file larger than 1 GiB: " + files[i].abs);
+      const int64_t padded = (files[i].size + 127) / 128 * 128;
+      if (i > first && (cur + padded > (1ll << 30) || i - first >= (1u << 20))) {
+        batches.emplace_back(first, i - first); first = i; cur = 0;
+      }
+      cur += padded;
+    }
+    if (files.size() > first) batches.emplace_back(first, files.size() - first);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device (there is no CPU fallback)");
+  gpus = std::max(1, std::min(gpus, ndev));
+  std::vector<ScanOut> outs(batches.size());
+  // one host thread per GPU; batch b goes to GPU b % gpus; one ncclAllReduce of the count table at the end
+  std::vector<ncclComm_t> comms(gpus);
+  std::vector<int> devs(gpus);
+  for (int i = 0; i < gpus; ++i) devs[i] = i;
+  if (gpus > 1 && ncclCommInitAll(comms.data(), gpus, devs.data()) != ncclSuccess) die("ncclCommInitAll failed");
+  const size_t table = (size_t)(n_groups + 1) * TSM_NUM_CATEGORIES + 4;
+  std::vector<std::vector<int64_t>> totals(gpus, std::vector<int64_t>(table, 0));
+  auto worker = [&](int g) {
+    cudaSetDevice(g);
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    int64_t max_arena = 1 << 20; int32_t max_files = 16;
+    for (size_t b = g; b < batches.size(); b += gpus) {
+      int64_t bytes = 0;
+      for (size_t i = 0; i < batches[b].count; ++i) bytes += (files[batches[b].first + i].size + 127) / 128 * 128;
+      max_arena = std::max(max_arena, bytes + 4096);
+      max_files = std::max<int32_t>(max_files, (int32_t)batches[b].count);
+    }
+    tsm_ctx* ctx = nullptr;
+    ck(tsm_create(&ctx, g, max_arena, max_files, std::max(n_groups, 1), 0), "tsm_create");
+    int64_t* d_acc = nullptr;                               // running sum of the count tables of this GPU's batches
+    cudaMalloc((void**)&d_acc, table * sizeof(int64_t));
+    cudaMemsetAsync(d_acc, 0, table * sizeof(int64_t), st);
+    for (size_t b = g; b < batches.size(); b += gpus) {
+      Batch& B = batches[b];
+      load_batch(files, B);
+      tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, n_groups};
+      ScanOut& o = outs[b];
+      o.stats.resize(B.count);
+      o.group_counts.assign((size_t)n_groups * TSM_NUM_CATEGORIES, 0);
+      const int64_t cap = std::max<int64_t>(B.bytes / 8 + 1024, 1024);
+      o.aev.resize((size_t)cap); o.hev.resize((size_t)cap);
+      tsm_result r{};
+      r.stats = o.stats.data(); r.group_counts = o.group_counts.data();
+      r.aev = o.aev.data(); r.aev_cap = cap; r.hev = o.hev.data(); r.hev_cap = cap;
+      ck(tsm_scan(ctx, &c, &r, TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS, st), "tsm_scan");
+      o.aev.resize((size_t)r.n_aev); o.hev.resize((size_t)r.n_hev);
+      void* dptr = nullptr; int64_t n64 = 0;
+      ck(tsm_device_counts(ctx, &dptr, &n64), "tsm_device_counts");
+      // accumulate on the device: acc += counts (tiny; a cudaMemcpy + host add would also do)
+      std::vector<int64_t> h((size_t)n64);
+      cudaMemcpyAsync(h.data(), dptr, (size_t)n64 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      for (size_t i = 0; i < (size_t)n64 && i < table; ++i) totals[g][i] += h[i];
+    }
+    cudaMemcpyAsync(d_acc, totals[g].data(), table * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (gpus > 1) {                                         // the single collective of the path
+      ncclAllReduce(d_acc, d_acc, table, ncclInt64, ncclSum, comms[g], st);
+    }
+    cudaMemcpyAsync(totals[g].data(), d_acc, table * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(d_acc);
+    tsm_destroy(ctx);
+    cudaStreamDestroy(st);
+  };
+  if (gpus == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; ++g) th.emplace_back(worker, g);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < gpus; ++g) ncclCommDestroy(comms[g]);
+  }
+  // ---- rows + summary
+  std::ofstream rows_os, sum_os;
+  if (!rows_path.empty()) { rows_os.open(rows_path, std::ios::binary); csv_row(rows_os, {"fileName", "extension", "test_name", "method", "statement", "counts", "category"}); }
+  if (!summary_path.empty()) { sum_os.open(summary_path, std::ios::binary); csv_row(sum_os, {"Id", "FileName", "total assert", "assertion"}); }
+  int64_t id = 0;
+  for (size_t b = 0; b < batches.size(); ++b) {
+    const Batch& B = batches[b];
+    const ScanOut& o = outs[b];
+    size_t ai = 0, hi = 0;
+    for (size_t i = 0; i < B.count; ++i) {
+      const FileEntry& f = files[B.first + i];
+      const uint8_t* base = B.arena + B.off[i];
+      ++id;
+      struct Row { int64_t hdr; std::string stmt; int cat; std::string catname; int64_t count; bool fixture; std::string method; };
+      std::vector<Row> rows;
+      std::map<std::pair<int64_t, std::string>, size_t> index;
+      std::map<std::string, int64_t> hist; std::vector<std::string> hist_order;
+      int64_t cur_hdr = -1; bool cur_fix = false; std::string cur_method = "xxxx";
+      while (ai < o.aev.size() && o.aev[ai].file == i) {
+        const tsm_assert_event& ev = o.aev[ai++];
+        while (hi < o.hev.size() && o.hev[hi].file == i && o.hev[hi].line_off <= ev.line_off) {   // governing header
+          const tsm_header_event& h = o.hev[hi++];
+          cur_hdr = h.line_off; cur_fix = (h.kind & 1u) != 0;
+          cur_method = method_string(f.ext, base + h.line_off, h.line_len);
+        }
+        // the statement may be longer than the 16-bit event field: re-derive its end on the host if saturated
+        uint32_t sl = ev.stmt_len;
+        if (sl == 65535) { const uint8_t* p = base + ev.stmt_off; uint32_t e = 0, last = 0; while (ev.stmt_off + e < (uint32_t)B.len[i] && p[e] != '\n' && p[e] != '(') { if (!is_w(p[e])) last = e + 1; ++e; } sl = last; }
+        std::string stmt((const char*)base + ev.stmt_off, sl);
+        std::string cat = ev.cat == 127 ? std::string((const char*)base + ev.ident_off, ev.ident_len) : std::string(tsm_category_name(ev.cat));
+        auto key = std::make_pair(cur_hdr, stmt);
+        auto it = index.find(key);
+        if (it == index.end()) { index[key] = rows.size(); rows.push_back({cur_hdr, stmt, ev.cat, cat, 1, cur_fix, cur_method}); }
+        else rows[it->second].count++;
+        if (!hist.count(cat)) hist_order.push_back(cat);
+        hist[cat]++;
+      }
+      while (hi < o.hev.size() && o.hev[hi].file == i) ++hi;
+      if (rows_os.is_open())
+        for (const Row& r : rows)
+          csv_row(rows_os, {f.rel, ext_name(f.ext), test_name_tag(f.rel, r.fixture), r.method, r.stmt, std::to_string(r.count), r.catname});
+      if (sum_os.is_open()) {
+        std::stable_sort(hist_order.begin(), hist_order.end(), [&](const std::string& x, const std::string& y) { return hist[x] > hist[y]; });
+        std::string a;
+        for (const std::string& c : hist_order) { if (!a.empty()) a += ", "; a += std::to_string(hist[c]) + ":" + c; }
+        csv_row(sum_os, {std::to_string(id), f.rel, std::to_string(o.stats[i].n_assert), a});
+      }
+    }
+  }
+  // ---- the aggregate table (global counts after the allreduce) to stdout
+  const std::vector<int64_t>& T = totals[0];
+  printf("category,count\r\n");
+  for (int k = 0; k < TSM_NUM_CATEGORIES; ++k) {
+    const int64_t v = T[(size_t)n_groups * TSM_NUM_CATEGORIES + k];
+    if (v) printf("%s,%lld\r\n", k == 0 ? "" : tsm_category_name(k), (long long)v);
+  }
+  const size_t tot = (size_t)(n_groups + 1) * TSM_NUM_CATEGORIES;
+  fprintf(stderr, "tosem-scan: lines=%lld assertion_lines=%lld headers=%lld fixture_headers=%lld on %d GPU(s)\n",
+          (long long)T[tot], (long long)T[tot + 1], (long long)T[tot + 2], (long long)T[tot + 3], gpus);
+  for (Batch& B : batches) tsm_host_free(B.arena);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- reduce (S10)
+struct FlagDef { const char* name; const char* col; const char* val; const char* col2; };
+// the naive column mapping of tools/make_golden.py (162 / 171 cells of tests_strategy_rq32.csv reproduce)
+static const FlagDef kStrategy[] = {
+    {"status_analysis", "status_test", "1", nullptr}, {"value_error", "Error_Type", "ValueError", nullptr},
+    {"runtime_error", "Error_Type", "RuntimeError", nullptr}, {"memory_error", "Error_Type", "MemoryError", nullptr},
+    {"type_error", "Error_Type", "TypeError", nullptr}, {"import_error", "Error_Type", "ImportError", nullptr},
+    {"key_error", "Error_Type", "KeyError", nullptr}, {"AssertionError", "Error_Type", "AssertionError", nullptr},
+    {"FileError", "Error_Type", "FileError", nullptr}, {"NotImplementedError", "Error_Type", "NotImplementedError", nullptr},
+    {"negative_test", "negative_test", "1", nullptr}, {"logical_condition", "logical_statement", "1", "logical_expression"},
+    {"Null_pointer", "null_pointer", "1", nullptr}, {"value_range", "value_range", "1", nullptr},
+    {"absolute_relative_tolerence", "Approximation_Type", "absolute_relative_tolerence", nullptr},
+    {"error_bounding", "Approximation_Type", "error_bounding", nullptr},
+    {"rounding_tolence", "Approximation_Type", "rounding_tolence", nullptr},
+    {"instance_check", "checks_type", "instance_check", nullptr}, {"sub_set_checks", "checks_type", "sub_set_checks", nullptr}};
+static const FlagDef kMethods[] = {
+    {"regression", "regression", nullptr, nullptr}, {"integration", "Integration", nullptr, nullptr},
+    {"end_to_end", "end_to_end", nullptr, nullptr}, {"sanity", "sanity", nullptr, nullptr},
+    {"mock_test", "mock_test", nullptr, nullptr}, {"periodic_validation", "periodic_validation", nullptr, nullptr},
+    {"example_test", "example_test", nullptr, nullptr}, {"static_inspection", "static_inspection_test", nullptr, nullptr},
+    {"robustness_test", "roboustness", nullptr, nullptr}, {"experimental", "Experimental_benchmark_test", nullptr, nullptr},
+    {"api_test", "API", nullptr, nullptr}, {"threat", "ThreadTest", nullptr, nullptr}, {"blob", "blob_performance", nullptr, nullptr}};
+
+static std::string trim(const std::string& s) {
+  size_t a = 0, b = s.size();
+  while (a < b && (s[a] == ' ' || s[a] == '\t')) ++a;
+  while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t')) --b;
+  return s.substr(a, b - a);
+}
+static std::string fmt_num(double v, int dec) {            // shipped cells drop trailing zeros ("0", "43.771")
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.*f", dec, v);
+  std::string s = buf;
+  if (s.find('.') != std::string::npos) { while (!s.empty() && s.back() == '0') s.pop_back(); if (!s.empty() && s.back() == '.') s.pop_back(); }
+  return s.empty() ? "0" : s;
+}
+static double round_to(double v, int dec) { const double p = std::pow(10.0, dec); return std::round(v * p) / p; }
+
+static int cmd_reduce(const std::string& path, const std::string& strategy_path, const std::string& methods_path) {
+  auto rows = csv_read(path);
+  if (rows.size() < 2) die("empty taxonomy");
+  std::map<std::string, int> col;
+  for (size_t i = 0; i < rows[0].size(); ++i) col[rows[0][i]] = (int)i;
+  for (const char* need : {"Cases", "Repo"}) if (!col.count(need)) die(std::string("taxonomy lacks column ") + need);
+  // repo ids in the column order of tests_strategy_rq32.csv:1 when all nine are present, else first-seen order
+  std::vector<std::string> repos = {"autokeras", "auto_sklearn", "tpot", "Ray", "DeepSpeech2", "google_automl", "nni", "Apollo", "Nupic"};
+  std::map<std::string, int> rid, cid;
+  for (size_t r = 1; r < rows.size(); ++r) if ((int)rows[r].size() > col["Repo"] && !std::count(repos.begin(), repos.end(), rows[r][col["Repo"]])) repos.push_back(rows[r][col["Repo"]]);
+  for (size_t i = 0; i < repos.size(); ++i) rid[repos[i]] = (int)i;
+  const int nS = sizeof(kStrategy) / sizeof(kStrategy[0]), nM = sizeof(kMethods) / sizeof(kMethods[0]), nF = nS + nM;
+  std::vector<uint8_t> flags; std::vector<int32_t> repo, cas;
+  auto cell = [&](const std::vector<std::string>& r, const char* c) -> std::string {
+    auto it = col.find(c); return (it == col.end() || it->second >= (int)r.size()) ? std::string() : trim(r[it->second]); };
+  for (size_t r = 1; r < rows.size(); ++r) {
+    const auto& R = rows[r];
+    if ((int)R.size() <= std::max(col["Cases"], col["Repo"])) continue;
+    const std::string cs = R[col["Cases"]];
+    if (!cid.count(cs)) { const int k = (int)cid.size(); cid[cs] = k; }
+    repo.push_back(rid[R[col["Repo"]]]); cas.push_back(cid[cs]);
+    for (int j = 0; j < nS; ++j) {
+      bool v = cell(R, kStrategy[j].col) == kStrategy[j].val;
+      if (kStrategy[j].col2) v = v || cell(R, kStrategy[j].col2) == "1";
+      flags.push_back(v);
+    }
+    for (int j = 0; j < nM; ++j) { const std::string v = cell(R, kMethods[j].col); flags.push_back(!(v.empty() || v == "0")); }
+  }
+  const int n_rows = (int)repo.size(), n_repos = (int)repos.size(), n_cases = (int)cid.size();
+  tsm_ctx* ctx = nullptr;
+  ck(tsm_create(&ctx, 0, 1 << 20, 16, 1, 0), "tsm_create");
+  std::vector<int64_t> out((size_t)nF * n_repos), cpr((size_t)n_repos);
+  ck(tsm_reduce(ctx, flags.data(), repo.data(), cas.data(), n_rows, nF, n_repos, n_cases, out.data(), cpr.data(), nullptr), "tsm_reduce");
+  tsm_destroy(ctx);
+  int64_t all_cases = 0; for (int64_t c : cpr) all_cases += c;
+  if (!strategy_path.empty()) {                             // layout of RQs/RQ3/tests_strategy_rq32.csv
+    std::ofstream os(strategy_path, std::ios::binary);
+    std::vector<std::string> h = {"Tests"};
+    for (auto& r : repos) h.push_back(r);
+    h.push_back("");
+    for (auto& r : repos) h.push_back(r);
+    csv_row(os, h);
+    std::vector<std::vector<double>> v(nS, std::vector<double>(n_repos));
+    std::vector<double> colsum(n_repos, 0.0);
+    for (int j = 0; j < nS; ++j) for (int r = 0; r < n_repos; ++r) {
+      // rounded twice, like the shipped cells (docs/SPEC.md section 9): 26/142 -> 18.3099 -> /1.1 -> 16.6454
+      v[j][r] = cpr[r] ? round_to(round_to(100.0 * out[(size_t)j * n_repos + r] / cpr[r], 4) / 1.1, 4) : 0.0;
+      colsum[r] += v[j][r];
+    }
+    for (int j = 0; j < nS; ++j) {
+      std::vector<std::string> row = {kStrategy[j].name};
+      for (int r = 0; r < n_repos; ++r) row.push_back(fmt_num(v[j][r], 4));
+      row.push_back("");
+      for (int r = 0; r < n_repos; ++r) row.push_back(fmt_num(colsum[r] > 0 ? round_to(v[j][r] / colsum[r] * 100.0, 2) : 0.0, 2));
+      csv_row(os, row);
+    }
+    std::vector<std::string> last = {""};
+    for (int r = 0; r < n_repos; ++r) last.push_back(fmt_num(colsum[r], 4));
+    last.push_back("");
+    for (int r = 0; r < n_repos; ++r) last.push_back("100");
+    csv_row(os, last);
+  }
+  if (!methods_path.empty()) {                              // first three columns of RQs/RQ4/tests_methods_v2.csv
+    std::ofstream os(methods_path, std::ios::binary);
+    csv_row(os, {"Test_methods", "total_cases", "percentage"});
+    for (int j = 0; j < nM; ++j) {
+      int64_t t = 0;
+      for (int r = 0; r < n_repos; ++r) t += out[(size_t)(nS + j) * n_repos + r];
+      csv_row(os, {kMethods[j].name, std::to_string(t), fmt_num(all_cases ? round_to(100.0 * t / all_cases, 4) : 0.0, 4)});
+    }
+  }
+  fprintf(stderr, "tosem-scan: reduce %d rows, %d cases, %d repos\n", n_rows, n_cases, n_repos);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- diff (S8)
+static int cmd_diff(const std::string& old_root, const std::string& new_root, const std::string& out_path) {
+  std::vector<FileEntry> a, b;
+  walk(old_root, 0, true, a);
+  walk(new_root, 0, true, b);
+  std::map<std::string, const FileEntry*> bm;
+  for (const FileEntry& f : b) bm[f.rel] = &f;
+  // pairs by relative path; a file present on one side only is paired with the empty file
+  struct Pair { std::string rel; const FileEntry* o; const FileEntry* n; };
+  std::vector<Pair> pairs;
+  std::map<std::string, bool> seen;
+  for (const FileEntry& f : a) { auto it = bm.find(f.rel); pairs.push_back({f.rel, &f, it == bm.end() ? nullptr : it->second}); seen[f.rel] = true; }
+  for (const FileEntry& f : b) if (!seen.count(f.rel)) pairs.push_back({f.rel, nullptr, &f});
+  auto pack = [&](bool old_side, Batch& B, std::vector<FileEntry>& tmp) {
+    for (const Pair& p : pairs) { const FileEntry* f = old_side ? p.o : p.n; tmp.push_back(f ? *f : FileEntry{p.rel, "", 0, 0, 0}); }
+    B.first = 0; B.count = tmp.size();
+    B.len.resize(B.count); B.off.resize(B.count + 1); B.ext.assign(B.count, 0); B.grp.assign(B.count, 0);
+    for (size_t i = 0; i < B.count; ++i) B.len[i] = (int32_t)tmp[i].size;
+    B.bytes = tsm_layout(B.len.data(), (int32_t)B.count, B.off.data());
+    if (B.bytes < 0) die("tree does not fit one int32-indexed arena; diff it per sub-directory");
+    B.arena = (uint8_t*)tsm_host_alloc(std::max<int64_t>(B.bytes, 128));
+    if (!B.arena) die("pinned arena allocation failed");
+    memset(B.arena, 0, (size_t)std::max<int64_t>(B.bytes, 128));
+    for (size_t i = 0; i < B.count; ++i) if (!tmp[i].abs.empty()) { std::ifstream in(tmp[i].abs, std::ios::binary); in.read((char*)B.arena + B.off[i], B.len[i]); }
+  };
+  Batch A, N; std::vector<FileEntry> ta, tn;
+  pack(true, A, ta); pack(false, N, tn);
+  tsm_ctx* ctx = nullptr;
+  ck(tsm_create(&ctx, 0, 1 << 20, 16, 1, 0), "tsm_create");
+  tsm_corpus ca{A.arena, A.off.data(), A.len.data(), A.ext.data(), A.grp.data(), (int32_t)A.count, 1};
+  tsm_corpus cn{N.arena, N.off.data(), N.len.data(), N.ext.data(), N.grp.data(), (int32_t)N.count, 1};
+  std::vector<int64_t> added(pairs.size()), removed(pairs.size());
+  ck(tsm_diff_pairs(ctx, &ca, &cn, added.data(), removed.data(), nullptr), "tsm_diff_pairs");
+  tsm_destroy(ctx);
+  std::ofstream os;
+  if (!out_path.empty()) { os.open(out_path, std::ios::binary); csv_row(os, {"fileName", "cloc", "added", "removed"}); }
+  int64_t ta_ = 0, tr_ = 0;
+  for (size_t i = 0; i < pairs.size(); ++i) {
+    ta_ += added[i]; tr_ += removed[i];
+    if (os.is_open() && (added[i] || removed[i])) csv_row(os, {pairs[i].rel, std::to_string(added[i] + removed[i]), std::to_string(added[i]), std::to_string(removed[i])});
+  }
+  printf("cloc,added,removed\r\n%lld,%lld,%lld\r\n", (long long)(ta_ + tr_), (long long)ta_, (long long)tr_);
+  tsm_host_free(A.arena); tsm_host_free(N.arena);
+  return 0;
+}
+
+static void usage() {
+  fprintf(stderr,
+          "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files]\n"
+          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]\n"
+          "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
+          "Scans run on the GPU through libtosemscan.so (sm_100a); there is no CPU fallback.\n");
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage(); return argc < 2 ? 2 : 0; }
+  const std::string cmd = argv[1];
+  std::vector<std::string> pos;
+  std::map<std::string, std::string> opt;
+  bool all_files = false;
+  for (int i = 2; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--all-files") all_files = true;
+    else if (a.rfind("--", 0) == 0) { if (i + 1 >= argc) die("missing value for " + a); opt[a] = argv[++i]; }
+    else pos.push_back(a);
+  }
+  if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files); }
+  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"]); }
+  if (cmd == "diff") { if (pos.size() != 2) die("diff needs <old-root> <new-root>"); return cmd_diff(pos[0], pos[1], opt["--out"]); }
+  usage();
+  return 2;
+}
