@@ -268,7 +268,7 @@ extern "C" int tsm_scan_resident(tsm_ctx* c, uint32_t flags, void* stream) {
     cudaEventRecord(ev[1], st);
     k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
     cudaEventRecord(ev[2], st);
-    const size_t hist = c->n_groups <= 16 ? sizeof(uint32_t) * (size_t)c->n_groups * TSM_K : 0;
+    const size_t hist = sizeof(uint32_t) * (256 + (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0));
     k_classify<<<c->sms * 8, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
     k_totals<<<std::min((n + 255) / 256, c->sms * 4), 256, 0, st>>>(p);

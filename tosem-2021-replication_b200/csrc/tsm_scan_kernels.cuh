@@ -454,153 +454,152 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(Scan
 }
 
 // ================================================================================= k_classify
-// One thread per candidate line.  Byte-serial state machine over the statement (it ends at the
-// first '('), exactly SPEC sections 4 and 6.
-struct ByteReader {                                      // 8-byte buffered reader over the file in HBM
-  const uint8_t* base; uint32_t cur_blk; unsigned long long w;
-  __device__ __forceinline__ ByteReader(const uint8_t* b) : base(b), cur_blk(0xFFFFFFFFu), w(0) {}
+// One thread per candidate line, exactly SPEC sections 4 and 6.  The statement T ends at the first '(';
+// one pass over its bytes (8-byte loads, one shared-memory class lookup per byte) finds the
+// stripped start, the right-stripped end and the last identifier L; everything else (gtest stem,
+// bare-assert operators, table lookup of L, statement hash) touches only the few bytes it needs.
+constexpr uint32_t CC_W = 1, CC_IDENT = 2, CC_STOP = 4;  // byte classes: blank, [A-Za-z0-9_], '(' or LF
+
+struct FileBytes {                                       // 8-byte buffered reader over one file in HBM
+  const unsigned long long* base; uint32_t cur_blk; unsigned long long w;
+  __device__ __forceinline__ explicit FileBytes(const uint8_t* b)
+      : base(reinterpret_cast<const unsigned long long*>(b)), cur_blk(0xFFFFFFFFu), w(0) {}
   __device__ __forceinline__ uint32_t get(uint32_t i) {
     const uint32_t blk = i >> 3;
-    if (blk != cur_blk) { w = __ldg(reinterpret_cast<const unsigned long long*>(base) + blk); cur_blk = blk; }
+    if (blk != cur_blk) { w = __ldg(base + blk); cur_blk = blk; }
     return (uint32_t)(w >> (8u * (i & 7u))) & 0xFFu;
+  }
+  // the 8 bytes at file offset i (unaligned), little-endian; bytes past the word pair are garbage-free
+  __device__ __forceinline__ unsigned long long get8(uint32_t i) {
+    const uint32_t blk = i >> 3, sh = 8u * (i & 7u);
+    const unsigned long long lo = __ldg(base + blk);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (__ldg(base + blk + 1) << (64u - sh));
   }
 };
 
-__device__ __forceinline__ int stem_lookup(ByteReader& rd, uint32_t s, uint32_t n) {
-  // s = first byte after "EXPECT_" / "ASSERT_"; n = stem length
-  char t[10];
-  if (n == 0 || n > 9) return 0;
-  for (uint32_t k = 0; k < n; ++k) t[k] = (char)rd.get(s + k);
-#define STEM(str, id) if (n == sizeof(str) - 1) { bool ok = true; for (uint32_t k = 0; k < n; ++k) ok &= (t[k] == str[k]); if (ok) return id; }
-  STEM("EQ", 1) STEM("NE", 2) STEM("TRUE", 3) STEM("FALSE", 4) STEM("GT", 5) STEM("GE", 6)
-  STEM("LT", 7) STEM("LE", 8) STEM("NEAR", 9) STEM("FLOAT_EQ", 10) STEM("DOUBLE_EQ", 11) STEM("THROW", 12)
-#undef STEM
-  return 0;
+__device__ __forceinline__ unsigned long long low_bytes(unsigned long long v, uint32_t n) {   // keep n <= 8 bytes
+  return n >= 8 ? v : (v & ((1ull << (8u * n)) - 1ull));
+}
+
+// gtest stem table (SPEC section 6 rule 1): stem = bytes after "EXPECT_" / "ASSERT_", n = its length
+__device__ __forceinline__ int stem_lookup(FileBytes& rd, uint32_t s, uint32_t n) {
+  if (n < 2 || n > 9) return 0;
+  const unsigned long long v = low_bytes(rd.get8(s), n);
+  const uint32_t c9 = n == 9 ? rd.get(s + 8) : 0u;
+  switch (n) {
+    case 2:
+      if (v == 0x5145ull) return 1;            // EQ
+      if (v == 0x454Eull) return 2;            // NE
+      if (v == 0x5447ull) return 5;            // GT
+      if (v == 0x4547ull) return 6;            // GE
+      if (v == 0x544Cull) return 7;            // LT
+      if (v == 0x454Cull) return 8;            // LE
+      return 0;
+    case 4:
+      if (v == 0x45555254ull) return 3;        // TRUE
+      if (v == 0x5241454Eull) return 9;        // NEAR
+      return 0;
+    case 5:
+      if (v == 0x45534C4146ull) return 4;      // FALSE
+      if (v == 0x574F524854ull) return 12;     // THROW
+      return 0;
+    case 8: return v == 0x51455F54414F4C46ull ? 10 : 0;                 // FLOAT_EQ
+    case 9: return (v == 0x455F454C42554F44ull && c9 == 'Q') ? 11 : 0;   // DOUBLE_EQ
+    default: return 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
-  extern __shared__ uint32_t hist[];                     // [n_groups][K] when it fits, else unused
+  extern __shared__ uint32_t csm[];                      // [256] byte classes, then [n_groups][K] histogram
+  uint32_t* cls = csm;
+  uint32_t* hist = csm + 256;
   const bool use_smem = p.n_groups <= 16;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint32_t c = (uint32_t)i;
+    cls[i] = (is_w(c) ? CC_W : 0u) | (is_ident(c) ? CC_IDENT : 0u) | ((c == '(' || c == '\n') ? CC_STOP : 0u);
   }
+  if (use_smem) for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
   const uint32_t n = min(p.ctrl->n_cand, p.cand_cap);
   const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long cd = p.cand[i];
     const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
     const uint32_t size = (uint32_t)p.len[f];
-    ByteReader rd(p.arena + (size_t)(uint32_t)p.off[f]);
-    // ---- statement T = stripped line cut before its first '(' and right-stripped (SPEC section 4)
+    FileBytes rd(p.arena + (size_t)(uint32_t)p.off[f]);
+    // ---- one pass: T = [t0, last), L = trailing identifier run [run, last) if in_run
     uint32_t q = line_off;
-    while (q < size) { const uint32_t c = rd.get(q); if (c == '\n' || !is_w(c)) break; ++q; }
+    while (q < size && (cls[rd.get(q)] & CC_W)) ++q;     // LF is not blank: stops at the line end too
     const uint32_t t0 = q;
-    uint32_t last = t0;                                  // one past the last non-blank byte
-    uint32_t run = t0; bool in_run = false, gap = false; // trailing identifier run (L)
-    unsigned long long win = 0;                          // last 8 bytes of e = T[7:], newest in the low byte
-    bool bare = false;
-    uint32_t feat = 0;                                   // bit0 " not ", 1 " in ", 2 " is not ", 3 True, 4 ==, 5 !=, 6 <=, 7 >=, 8 <, 9 >
-    unsigned long long hacc = 0; uint32_t hr = 0;        // Mersenne-61 of T (blanks inside T are part of it)
-    unsigned long long hacc_last = 0;                    // hash state at `last`
-    uint32_t k = 0;                                      // bytes of T seen so far (index inside T)
-    bool is_assert6 = true;
+    uint32_t last = t0, run = t0;
+    bool in_run = false, gap = false;
     while (q < size) {
-      const uint32_t c = rd.get(q);
-      if (c == '\n' || c == '(') break;
-      // bare-assert detection on the first 7 bytes
-      if (k < 6) is_assert6 &= (c == (uint32_t)"assert"[k]);
-      else if (k == 6) bare = is_assert6 && (c == 0x20);
-      if (bare && k >= 7) {
-        win = (win << 8) | c;
-        const uint32_t ek = k - 7;                       // index inside e
-        const uint32_t w4 = (uint32_t)win; const uint32_t w2 = w4 & 0xFFFFu;
-        if (ek >= 4 && (win & 0xFFFFFFFFFFull) == 0x206E6F7420ull) feat |= 1;        // " not "
-        if (ek >= 3 && w4 == 0x20696E20u) feat |= 2;                                 // " in "
-        if (ek >= 7 && win == 0x206973206E6F7420ull) feat |= 4;                      // " is not "
-        if (ek >= 3 && w4 == 0x54727565u) feat |= 8;                                 // "True"
-        if (ek >= 1) {
-          if (w2 == 0x3D3Du) feat |= 16;                                             // "=="
-          if (w2 == 0x213Du) feat |= 32;                                             // "!="
-          if (w2 == 0x3C3Du) feat |= 64;                                             // "<="
-          if (w2 == 0x3E3Du) feat |= 128;                                            // ">="
-        }
-        if (c == '<') feat |= 256;
-        if (c == '>') feat |= 512;
-      }
-      hacc = fold61(hacc + rotl61((unsigned long long)c, hr));
-      hr += 8; if (hr >= 61) hr -= 61;
-      if (is_w(c)) gap = true;
+      const uint32_t k = cls[rd.get(q)];
+      if (k & CC_STOP) break;
+      if (k & CC_W) gap = true;
       else {
-        if (is_ident(c)) { if (!in_run || gap) run = q; in_run = true; } else in_run = false;
-        gap = false; last = q + 1; hacc_last = hacc;
+        if (k & CC_IDENT) { if (!in_run || gap) run = q; in_run = true; } else in_run = false;
+        gap = false; last = q + 1;
       }
-      ++q; ++k;
+      ++q;
     }
     const uint32_t tlen = last - t0;
-    // features seen in trailing blanks do not belong to T: none of the patterns can end in the
-    // stripped tail except through a trailing blank (" not ", " in ", " is not ", "not ") - recheck
-    // those against tlen below.
-    const uint32_t Ls = in_run ? run : last;
-    const uint32_t Ln = last - Ls;
-    // ---- category (SPEC section 6)
+    const uint32_t Ls = in_run ? run : last, Ln = last - Ls;
+    // ---- category (SPEC section 6), first match wins
     int cat = 0;
     bool done = false;
-    if (Ln >= 7) {
-      const uint32_t c0 = rd.get(Ls);
-      if (c0 == 'E' || c0 == 'A') {
-        const char* pre = c0 == 'E' ? "EXPECT_" : "ASSERT_";
-        bool ok = true;
-        for (int j = 1; j < 7; ++j) ok &= (rd.get(Ls + j) == (uint32_t)pre[j]);
-        if (ok) { cat = stem_lookup(rd, Ls + 7, Ln - 7); done = true; }
-      }
+    if (Ln >= 7) {                                       // rule 1: EXPECT_x / ASSERT_x
+      const unsigned long long h7 = low_bytes(rd.get8(Ls), 7);
+      if (h7 == 0x5F544345505845ull || h7 == 0x5F545245535341ull) { cat = stem_lookup(rd, Ls + 7, Ln - 7); done = true; }
     }
-    if (!done) {
-      const bool t_is_assert = (tlen == 6) && is_assert6;
-      if (t_is_assert || (bare && tlen >= 8)) {
+    if (!done && tlen >= 6) {                            // rule 2: T == "assert" or T starts with "assert "
+      const unsigned long long h = rd.get8(t0);
+      const bool a6 = low_bytes(h, 6) == 0x747265737361ull;
+      if (a6 && tlen == 6) { cat = 3; done = true; }
+      else if (a6 && tlen >= 8 && ((h >> 48) & 0xFF) == 0x20) {
         done = true;
-        if (t_is_assert) { cat = 3; }                    // T == "assert": e is empty
-        else {
-          // patterns that end with a blank can only have matched inside T if they end before `last`
-          // (T is right-stripped): re-scan e = T[7:tlen) for them exactly.
-          const uint32_t e0 = t0 + 7, en = tlen - 7;
-          bool f_not = false, f_in = false, f_isnot = false, f_pre = false;
-          if (en >= 4) {
-            f_pre = rd.get(e0) == 'n' && rd.get(e0 + 1) == 'o' && rd.get(e0 + 2) == 't' && rd.get(e0 + 3) == ' ';
-          }
-          if (feat & (1 | 2 | 4)) {
-            for (uint32_t a = 0; a + 4 <= en; ++a) {
-              if (rd.get(e0 + a) != ' ') continue;
-              const uint32_t b1 = rd.get(e0 + a + 1), b2 = rd.get(e0 + a + 2), b3 = rd.get(e0 + a + 3);
-              if (b1 == 'i' && b2 == 'n' && b3 == ' ') f_in = true;
-              if (a + 5 <= en && b1 == 'n' && b2 == 'o' && b3 == 't' && rd.get(e0 + a + 4) == ' ') f_not = true;
-              if (a + 8 <= en && b1 == 'i' && b2 == 's' && b3 == ' ' && rd.get(e0 + a + 4) == 'n' &&
-                  rd.get(e0 + a + 5) == 'o' && rd.get(e0 + a + 6) == 't' && rd.get(e0 + a + 7) == ' ') f_isnot = true;
-            }
-          }
-          if (f_pre) cat = 2;
-          else if ((f_not && f_in) || f_isnot) cat = 4;
-          else if (feat & 8) cat = 3;
-          else if (feat & 16) cat = 1;
-          else if (feat & 32) cat = 2;
-          else if (feat & 64) cat = 8;
-          else if (feat & 128) cat = 6;
-          else if (feat & 256) cat = 7;
-          else if (feat & 512) cat = 5;
-          else cat = 3;
+        const uint32_t e0 = t0 + 7, en = tlen - 7;       // e = T[7:]
+        bool f_not = false, f_in = false, f_isnot = false, f_true = false;
+        bool eq = false, ne = false, le = false, ge = false, lt = false, gt = false;
+        const bool f_pre = en >= 4 && (uint32_t)rd.get8(e0) == 0x20746F6Eu;          // "not "
+        unsigned long long win = 0;                      // last 8 bytes of e, newest in the low byte
+        for (uint32_t a = 0; a < en; ++a) {
+          const uint32_t c = rd.get(e0 + a);
+          win = (win << 8) | c;
+          const uint32_t w4 = (uint32_t)win, w2 = w4 & 0xFFFFu;
+          if ((win & 0xFFFFFFFFFFull) == 0x206E6F7420ull) f_not = true;              // " not "
+          if (w4 == 0x20696E20u) f_in = true;                                        // " in "
+          if (win == 0x206973206E6F7420ull) f_isnot = true;                          // " is not "
+          if (w4 == 0x54727565u) f_true = true;                                      // "True"
+          if (w2 == 0x3D3Du) eq = true;
+          if (w2 == 0x213Du) ne = true;
+          if (w2 == 0x3C3Du) le = true;
+          if (w2 == 0x3E3Du) ge = true;
+          if (c == '<') lt = true;
+          if (c == '>') gt = true;
         }
+        if (f_pre) cat = 2;
+        else if ((f_not && f_in) || f_isnot) cat = 4;
+        else if (f_true) cat = 3;
+        else if (eq) cat = 1;
+        else if (ne) cat = 2;
+        else if (le) cat = 8;
+        else if (ge) cat = 6;
+        else if (lt) cat = 7;
+        else if (gt) cat = 5;
+        else cat = 3;
       }
     }
-    if (!done) {
-      bool pre = Ln >= 6;
-      if (pre) for (int j = 0; j < 6; ++j) pre &= (rd.get(Ls + j) == (uint32_t)"assert"[j]);
-      if (pre) {
-        if (Ln == 7 && rd.get(Ls + 6) == '_') cat = 3;
+    if (!done && Ln >= 6) {                              // rules 3-5 on L
+      const unsigned long long h = rd.get8(Ls);
+      if (low_bytes(h, 6) == 0x747265737361ull) {
+        if (Ln == 7 && ((h >> 48) & 0xFF) == '_') cat = 3;
         else {
           cat = TSM_CAT_OTHER;
-          uint32_t h = 0x811C9DC5u;
-          for (uint32_t j = 0; j < Ln; ++j) h = (h ^ rd.get(Ls + j)) * 0x01000193u;
-          const int id = c_cat_slot[(h * TSM_CAT_HASH_MULT) >> 23];
+          uint32_t hh = 0x811C9DC5u;
+          for (uint32_t j = 0; j < Ln; ++j) hh = (hh ^ rd.get(Ls + j)) * 0x01000193u;
+          const int id = c_cat_slot[(hh * TSM_CAT_HASH_MULT) >> 23];
           if (id && (uint32_t)(c_cat_off[id + 1] - c_cat_off[id]) == Ln) {
             bool ok = true;
             for (uint32_t j = 0; j < Ln; ++j) ok &= (rd.get(Ls + j) == (uint32_t)(uint8_t)c_cat_blob[c_cat_off[id] + j]);
@@ -617,13 +616,18 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
       atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + cat], 1ull);
     }
     if (want_ev) {
+      unsigned long long hacc = 0; uint32_t hr = 0;     // Mersenne-61 of T (SPEC section 3)
+      for (uint32_t j = 0; j < tlen; ++j) {
+        hacc = fold61(hacc + rotl61((unsigned long long)rd.get(t0 + j), hr));
+        hr += 8; if (hr >= 61) hr -= 61;
+      }
       const uint32_t slot = atomicAdd(&p.ctrl->n_aev, 1u);
       if (slot < p.aev_cap) {
         tsm_assert_event ev;
         ev.file = f; ev.line_off = line_off; ev.stmt_off = t0;
         ev.stmt_len = (uint16_t)min(tlen, 65535u); ev.cat = (uint16_t)cat;
         ev.ident_off = Ls; ev.ident_len = (uint16_t)min(Ln, 65535u); ev.pad = 0;
-        ev.stmt_hash = mix_hash(canon61(hacc_last), tlen);
+        ev.stmt_hash = mix_hash(canon61(hacc), tlen);
         p.aev[slot] = ev;
       } else p.ctrl->overflow = 1;
     }
