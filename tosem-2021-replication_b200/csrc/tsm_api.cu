@@ -32,6 +32,11 @@ struct tsm_ctx {
   uint32_t* d_unit_begin = nullptr;
   uint32_t unit_cap = 0;
   Ctrl* d_ctrl = nullptr;
+  SlabCtl* d_slab = nullptr;                // [kMaxSlabs]
+  cudaStream_t copy_stream = nullptr;       // H2D of arena slabs, overlapped with the scan of earlier slabs
+  cudaEvent_t slab_ev[64] = {};
+  cudaEvent_t ready_ev = nullptr;
+  static constexpr int kMaxSlabs = 64;
   tsm_file_stat* d_stats = nullptr;
   unsigned long long* d_cand = nullptr;
   tsm_header_event* d_hev = nullptr;
@@ -115,6 +120,10 @@ extern "C" void tsm_destroy(tsm_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_arena); cudaFree(c->d_off); cudaFree(c->d_len); cudaFree(c->d_ext); cudaFree(c->d_grp);
   cudaFree(c->d_unit_file); cudaFree(c->d_unit_begin); cudaFree(c->d_ctrl); cudaFree(c->d_stats);
+  cudaFree(c->d_slab);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (cudaEvent_t e : c->slab_ev) if (e) cudaEventDestroy(e);
+  if (c->ready_ev) cudaEventDestroy(c->ready_ev);
   cudaFree(c->d_cand); cudaFree(c->d_hev); cudaFree(c->d_aev); cudaFree(c->d_counts);
   if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
   for (auto& set : c->ev) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
@@ -154,6 +163,10 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   A((void**)&c->d_unit_file, sizeof(uint32_t) * (size_t)c->unit_cap);
   A((void**)&c->d_unit_begin, sizeof(uint32_t) * (size_t)c->unit_cap);
   A((void**)&c->d_ctrl, sizeof(Ctrl));
+  A((void**)&c->d_slab, sizeof(SlabCtl) * tsm_ctx::kMaxSlabs);
+  if (rc == TSM_OK && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = TSM_E_CUDA;
+  for (cudaEvent_t& e : c->slab_ev) if (rc == TSM_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = TSM_E_CUDA;
+  if (rc == TSM_OK && cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming) != cudaSuccess) rc = TSM_E_CUDA;
   A((void**)&c->d_stats, sizeof(tsm_file_stat) * (size_t)max_files);
   A((void**)&c->d_cand, sizeof(unsigned long long) * (size_t)c->max_events);
   A((void**)&c->d_counts, sizeof(unsigned long long) * ((size_t)(max_groups + 1) * TSM_K + 4));
@@ -245,42 +258,76 @@ static ScanParams make_params(const tsm_ctx* c, uint32_t flags) {
   return p;
 }
 
-extern "C" int tsm_scan_resident(tsm_ctx* c, uint32_t flags, void* stream) {
-  if (!c) return TSM_E_ARG;
-  if (!c->resident) return TSM_E_STATE;
-  CU(cudaSetDevice(c->device));
+// One scan = [memsets] + per slab (k_plan, k_scan) + k_classify + k_totals on `st`.  With host != NULL
+// the arena slabs are copied on the ctx's copy stream and each slab's kernels wait for its copy only,
+// so the H2D of slab s+1 overlaps the scan of slab s (the e2e path); with host == NULL the arena is
+// already resident and there is a single slab.
+static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_corpus* host) {
   int rc = ensure_event_buffers(c, flags);
   if (rc != TSM_OK) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const ScanParams p = make_params(c, flags);
+  ScanParams p = make_params(c, flags);
   const int n = c->n_files;
   c->launches = 0;
   CU(cudaMemsetAsync(c->d_ctrl, 0, sizeof(Ctrl), st));
+  CU(cudaMemsetAsync(c->d_slab, 0, sizeof(SlabCtl) * tsm_ctx::kMaxSlabs, st));
   CU(cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned long long) * ((size_t)(c->n_groups + 1) * TSM_K + 4), st));
   if (n) {
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(tsm_file_stat) * (size_t)n, st));
+    // slab boundaries (file indices): one slab when resident, ~32 MiB of arena each when streaming
+    std::vector<int32_t> cut{0};
+    if (host) {
+      int64_t slab_bytes = 32ll << 20;
+      while (c->arena_bytes / slab_bytes + 1 > tsm_ctx::kMaxSlabs) slab_bytes *= 2;
+      int64_t next = slab_bytes;
+      for (int32_t i = 1; i < n; ++i)
+        if ((int64_t)host->off[i] >= next) { cut.push_back(i); next = (int64_t)host->off[i] + slab_bytes; }
+      CU(cudaEventRecord(c->ready_ev, st));               // the arena may still be read by earlier work on st
+      CU(cudaStreamWaitEvent(c->copy_stream, c->ready_ev, 0));
+    }
+    cut.push_back(n);
     const int es = c->ev_next;
     c->ev_next = (es + 1) % tsm_ctx::kRing;
     fold_events(c, es);                                  // only blocks when 32 scans are in flight
     cudaEvent_t* ev = c->ev[es];
     cudaEventRecord(ev[0], st);
-    k_plan<<<(n + 255) / 256, 256, 0, st>>>(p);
-    cudaEventRecord(ev[1], st);
-    k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
+    const int n_slabs = (int)cut.size() - 1;
+    for (int s = 0; s < n_slabs; ++s) {
+      const int32_t f0 = cut[(size_t)s], f1 = cut[(size_t)s + 1];
+      if (host) {
+        const size_t b0 = (size_t)host->off[f0], b1 = (size_t)host->off[f1];
+        CU(cudaMemcpyAsync(c->d_arena + b0, host->arena + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->slab_ev[s], c->copy_stream));
+        CU(cudaStreamWaitEvent(st, c->slab_ev[s], 0));
+      }
+      p.slab = c->d_slab + s; p.f_begin = f0; p.f_end = f1;
+      // units of earlier slabs are bounded by (arena bytes before f0) / CH + f0
+      p.unit_base = (uint32_t)((host ? (int64_t)host->off[f0] : 0) / CH + f0);
+      k_plan<<<(f1 - f0 + 255) / 256, 256, 0, st>>>(p);
+      if (s == 0 && n_slabs == 1) cudaEventRecord(ev[1], st);
+      k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
+    }
+    if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);
     const size_t hist = sizeof(uint32_t) * (256 + (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0));
     k_classify<<<c->sms * 8, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
     k_totals<<<std::min((n + 255) / 256, c->sms * 4), 256, 0, st>>>(p);
     cudaEventRecord(ev[4], st);
-    c->ev_used[es] = true;
+    c->ev_used[es] = (n_slabs == 1);
     c->ev_last = es;
-    c->launches = 4;
+    c->launches = 2 * n_slabs + 2;
     CU(cudaGetLastError());
   }
   c->last_flags = flags;
   c->scanned = true;
   return TSM_OK;
+}
+
+extern "C" int tsm_scan_resident(tsm_ctx* c, uint32_t flags, void* stream) {
+  if (!c) return TSM_E_ARG;
+  if (!c->resident) return TSM_E_STATE;
+  CU(cudaSetDevice(c->device));
+  return launch_scan(c, flags, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int tsm_device_counts(tsm_ctx* c, void** dptr, int64_t* n_int64) {
@@ -351,9 +398,24 @@ extern "C" int tsm_download(tsm_ctx* c, tsm_result* r, void* stream) {
 }
 
 extern "C" int tsm_scan(tsm_ctx* c, const tsm_corpus* k, tsm_result* r, uint32_t flags, void* stream) {
-  int rc = tsm_upload(c, k, stream);
+  if (!c || !r) return TSM_E_ARG;
+  int rc = check_corpus(c, k);
   if (rc != TSM_OK) return rc;
-  rc = tsm_scan_resident(c, flags, stream);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t n = k->n_files;
+  c->n_files = n;
+  c->n_groups = k->n_groups;
+  c->arena_bytes = n ? k->off[n] : 0;
+  if (n) {                                                // the index first (small), the arena slab by slab
+    CU(cudaMemcpyAsync(c->d_off, k->off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_len, k->len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_ext, k->ext, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (k->grp) CU(cudaMemcpyAsync(c->d_grp, k->grp, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(c->d_grp, 0, sizeof(uint16_t) * (size_t)n, st));
+  }
+  c->resident = true;
+  rc = launch_scan(c, flags, st, k);
   if (rc != TSM_OK) return rc;
   return tsm_download(c, r, stream);
 }

@@ -47,14 +47,13 @@ constexpr uint32_t CJ_TEST = 1u << 16, CJ_CLASS = 1u << 21, CJ_VOID = 1u << 25, 
 constexpr uint8_t LF_CAND = 1, LF_HDR = 2, LF_FIX = 4;
 
 struct Ctrl {                     // device control block, zeroed before every scan
-  uint32_t n_units;               // written by k_plan
-  uint32_t work;                  // k_scan work-stealing cursor
   uint32_t n_cand;                // candidates appended by k_scan
   uint32_t n_hev;
   uint32_t n_aev;
   uint32_t overflow;              // some list hit its capacity
-  uint32_t pad[2];
 };
+
+struct SlabCtl { uint32_t n_units, work; };   // per-slab unit count (k_plan) and work cursor (k_scan)
 
 struct ScanParams {
   const uint8_t* arena;
@@ -67,6 +66,9 @@ struct ScanParams {
   uint32_t* unit_file;
   uint32_t* unit_begin;
   uint32_t unit_cap;
+  SlabCtl* slab;                  // this launch's slab
+  int32_t f_begin, f_end;         // files of this slab
+  uint32_t unit_base;             // first slot of this slab in the unit table
   Ctrl* ctrl;
   tsm_file_stat* stats;
   unsigned long long* cand;

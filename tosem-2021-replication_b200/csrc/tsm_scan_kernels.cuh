@@ -25,10 +25,10 @@ __constant__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
 // One lane per file: units = ceil(len / CH); the warp reserves a contiguous range of the unit
 // table with one atomic.  Unit order is irrelevant for the results (all outputs are sums or sets).
 __global__ void k_plan(ScanParams p) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = p.f_begin + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t nu = 0;
-  if (f < p.n_files) nu = ((uint32_t)p.len[f] + CH - 1) / CH;
+  if (f < p.f_end) nu = ((uint32_t)p.len[f] + CH - 1) / CH;
   uint32_t incl = nu;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -37,9 +37,9 @@ __global__ void k_plan(ScanParams p) {
   }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   uint32_t base = 0;
-  if (lane == 31 && total) base = atomicAdd(&p.ctrl->n_units, total);
+  if (lane == 31 && total) base = atomicAdd(&p.slab->n_units, total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  uint32_t at = base + incl - nu;
+  uint32_t at = p.unit_base + base + incl - nu;
   for (uint32_t u = 0; u < nu; ++u, ++at) {
     if (at < p.unit_cap) { p.unit_file[at] = (uint32_t)f; p.unit_begin[at] = u * CH; }
     else p.ctrl->overflow = 1;
@@ -434,14 +434,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(Scan
   ws.bar = reinterpret_cast<uint64_t*>(wb + BUF + TAB_BYTES + LFL_BYTES + 12 * WALK_BATCH);
   if (lane == 0) { mbar_init(ws.bar, 1); fence_mbar_init(); }
   __syncwarp();
-  const uint32_t n_units = p.ctrl->n_units;
+  const uint32_t n_units = p.slab->n_units;
   uint32_t phase = 0;
   while (true) {
     uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(&p.ctrl->work, 1u);
+    if (lane == 0) u = atomicAdd(&p.slab->work, 1u);
     u = __shfl_sync(0xffffffffu, u, 0);
     if (u >= n_units) break;
-    const uint32_t f = p.unit_file[u], cb = p.unit_begin[u];
+    const uint32_t f = p.unit_file[p.unit_base + u], cb = p.unit_begin[p.unit_base + u];
     if (lane == 0) issue_load(p, ws.buf, ws.bar, f, cb);
     const int ext = p.ext[f];
     while (!mbar_try_wait(ws.bar, phase)) {}
