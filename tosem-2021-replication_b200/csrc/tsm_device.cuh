@@ -20,15 +20,28 @@ constexpr uint32_t CH = 4096;                 // bytes of a file owned by one wo
 constexpr uint32_t PRE = 16;                  // bytes loaded in front (is the chunk start a line start?)
 constexpr uint32_t EXT = 240;                 // bytes loaded behind (terminator of the last owned line)
 constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128
-constexpr uint32_t NL_CAP = 1024;             // line-table entries per drain
-constexpr uint32_t WALK_BATCH = 256;          // lines walked (pass 2) before their balanced finalise (pass 3)
-constexpr uint32_t TAB_BYTES = (NL_CAP + 64) * 2;   // u16 newline positions
-constexpr uint32_t LFL_BYTES = NL_CAP + 64;         // u8 per-line flags
+#ifndef TSM_NL_CAP
+#define TSM_NL_CAP 1024
+#endif
+#ifndef TSM_WALK_BATCH
+#define TSM_WALK_BATCH 256
+#endif
+#ifndef TSM_SCAN_WARPS
+#define TSM_SCAN_WARPS 4
+#endif
+#ifndef TSM_SCAN_CTAS
+#define TSM_SCAN_CTAS 5
+#endif
+constexpr uint32_t NL_CAP = TSM_NL_CAP;       // line-table entries per drain (>= 512 + 1)
+constexpr uint32_t WALK_BATCH = TSM_WALK_BATCH;   // lines walked (pass 2) before their balanced finalise (pass 3)
+constexpr uint32_t TAB_BYTES = (NL_CAP + 64) * 2;   // u16 per line: newline position (13 bits) | LF_* flags << 13
+constexpr uint32_t TAB_POS = 0x1FFFu;                // BUF < 8192
 constexpr uint32_t RAW_BYTES = WALK_BATCH * 12;     // per line: u64 Horner accumulator + u32 automaton OR
-constexpr uint32_t WARP_SMEM = ((BUF + TAB_BYTES + LFL_BYTES + RAW_BYTES + 16 + 127) / 128) * 128;
-constexpr uint32_t LUT_BYTES = 2048;          // two 256-entry automaton tables (PY, C family)
-constexpr int SCAN_WARPS = 4;                 // warps per CTA of k_scan (each warp is independent)
-constexpr int SCAN_CTAS_PER_SM = 5;
+constexpr uint32_t WARP_SMEM = ((BUF + TAB_BYTES + RAW_BYTES + 16 + 127) / 128) * 128;
+static_assert(BUF <= TAB_POS + 1, "line-table positions must fit 13 bits");
+constexpr uint32_t LUT_BYTES = 3072;          // three 256-entry automaton tables (PY, C family, all-zero)
+constexpr int SCAN_WARPS = TSM_SCAN_WARPS;    // warps per CTA of k_scan (each warp is independent)
+constexpr int SCAN_CTAS_PER_SM = TSM_SCAN_CTAS;
 constexpr uint32_t SCAN_SMEM = LUT_BYTES + SCAN_WARPS * WARP_SMEM;
 
 // ---- multi-pattern Shift-And automata (SPEC sections 4, 5) -----------------------------------------

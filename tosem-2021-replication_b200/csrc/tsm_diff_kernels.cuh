@@ -77,7 +77,7 @@ __global__ void k_hash_lines(DiffSide d, int32_t n, unsigned long long total) {
   const uint32_t s = (i == d.line_base[f]) ? 0u : d.line_end[i - 1] + 1u;
   LineState L;
   line_init(L, s, e);
-  while (L.pos < L.e) line_block<false>(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), nullptr, 0u);
+  while (L.pos < L.e) hash_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)));
   Accum ac{0, 0, 0, 0, 0};
   line_finish(s, e, 0u, L.B, 0, GmemByte{g}, ac);       // ext 0: hash only; digest of one line = its hash
   d.line_hash[i] = ac.digest;

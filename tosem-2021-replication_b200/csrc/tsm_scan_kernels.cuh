@@ -78,8 +78,8 @@ __device__ __forceinline__ void line_init(LineState& L, uint32_t s, uint32_t e) 
   L.pos = (s == e) ? e : (s & ~7u);
 }
 
-// One 8-byte block.  kAut = false for files without a scannable extension (hash only).
-template <bool kAut>
+// One 8-byte block.  Files without a scannable extension run the same code on an all-zero table
+// (nothing ever matches): one instantiation keeps the kernel small enough for the instruction cache.
 __device__ __forceinline__ void line_block(LineState& L, unsigned long long w, const uint32_t* lut, uint32_t first) {
   const uint32_t pos = L.pos;
   if (pos < L.s || pos + 8 > L.e) {                      // first / last block: zero the bytes outside the line
@@ -88,7 +88,7 @@ __device__ __forceinline__ void line_block(LineState& L, unsigned long long w, c
     if (pos + 8 > L.e) m &= ~0ull >> (8u * (pos + 8 - L.e));
     w &= m;
   }
-  if (kAut) {
+  {
     const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
     uint32_t D = L.D, A = L.A;
 #pragma unroll
@@ -104,6 +104,21 @@ __device__ __forceinline__ void line_block(LineState& L, unsigned long long w, c
     L.D = D; L.A = A;
   }
   // B = B * 2^-64 + w  (2^-64 = 2^-3 = 2^58 mod 2^61-1: a rotation by 3 to the right)
+  const unsigned long long b = L.B;
+  const unsigned long long rot = (b >> 3) | ((b & 7ull) << 58);
+  L.B = fold61(fold61(rot + fold61(w)));
+  L.pos = pos + 8;
+}
+
+// Hash-only variant (S8 line hashes): same masking and Horner step, no automaton.
+__device__ __forceinline__ void hash_block(LineState& L, unsigned long long w) {
+  const uint32_t pos = L.pos;
+  if (pos < L.s || pos + 8 > L.e) {
+    unsigned long long m = ~0ull;
+    if (pos < L.s) m <<= 8u * (L.s - pos);
+    if (pos + 8 > L.e) m &= ~0ull >> (8u * (pos + 8 - L.e));
+    w &= m;
+  }
   const unsigned long long b = L.B;
   const unsigned long long rot = (b >> 3) | ((b & 7ull) << 58);
   L.B = fold61(fold61(rot + fold61(w)));
@@ -182,66 +197,81 @@ __device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, uint32_t n, 
 }
 
 struct WarpSmem {                                        // per-warp carve-up of the dynamic shared memory
-  uint8_t* buf; uint16_t* tab; uint8_t* lfl; uint32_t* rawA; unsigned long long* rawB; uint64_t* bar;
+  uint8_t* buf; uint16_t* tab; uint32_t* rawA; unsigned long long* rawB; uint64_t* bar;
 };
 
+// Pass 2: lanes walk the lines [lo, hi) of the table, refilling dynamically; raw (A, B) per line to shared.
+// Not inlined on purpose: the hot loop gets its own register allocation (the chunk-level state of
+// the caller is saved once per call instead of competing with the loop for registers).
+__device__ __noinline__ void walk_lines(const WarpSmem& ws, const uint32_t* lut, uint32_t first, uint32_t lo,
+                                        uint32_t hi, uint32_t ns, int lane) {
+  const uint8_t* buf = ws.buf;
+  const uint16_t* tab = ws.tab;
+  uint32_t next = lo;
+  bool active = false;
+  uint32_t myj = 0;
+  LineState L;
+  while (true) {
+    const uint32_t need = __ballot_sync(0xffffffffu, !active);
+    if (need) {
+      const uint32_t j = next + __popc(need & ((1u << lane) - 1u));
+      next += __popc(need);
+      if (!active && j < hi) {
+        line_init(L, j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns, (uint32_t)tab[j] & TAB_POS);
+        myj = j;
+        active = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) {
+      if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
+      if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
+      if (L.pos >= L.e) {
+        ws.rawA[myj - lo] = L.A;
+        ws.rawB[myj - lo] = L.B;
+        active = false;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Pass 3: balanced finalise, one lane per line.
+__device__ __noinline__ void finish_lines(const WarpSmem& ws, uint32_t lo, uint32_t hi, uint32_t ns, int ext,
+                                          int lane, Accum& ac) {
+  const SmemByte lb{ws.buf};
+  Accum a = ac;
+  for (uint32_t j = lo + lane; j < hi; j += 32) {
+    const uint32_t s = j ? ((uint32_t)ws.tab[j - 1] & TAB_POS) + 1u : ns;
+    const uint32_t e = (uint32_t)ws.tab[j] & TAB_POS;
+    const uint32_t fl = line_finish(s, e, ws.rawA[j - lo], ws.rawB[j - lo], ext, lb, a);
+    ws.tab[j] = (uint16_t)(e | (fl << 13));              // flags ride in the 3 spare bits of the entry
+  }
+  ac = a;
+  __syncwarp();
+}
+
 // Passes 2-4 over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
-template <bool kAut>
 __device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, uint32_t first, const WarpSmem& ws,
                                       uint32_t cnt, bool& skip_first, uint32_t& next_start, uint32_t f,
                                       uint32_t cb, int ext, int lane, Accum& ac) {
   __syncwarp();
   if (cnt == 0) return;
-  const uint8_t* buf = ws.buf;
   const uint16_t* tab = ws.tab;
   const uint32_t j0 = skip_first ? 1u : 0u;
   const uint32_t ns = next_start;
-  const SmemByte lb{buf};
   for (uint32_t lo = j0; lo < cnt; lo += WALK_BATCH) {
     const uint32_t hi = min(cnt, lo + WALK_BATCH);
-    // ---- pass 2: walk
-    uint32_t next = lo;
-    bool active = false;
-    uint32_t myj = 0;
-    LineState L;
-    while (true) {
-      const uint32_t need = __ballot_sync(0xffffffffu, !active);
-      if (need) {
-        const uint32_t j = next + __popc(need & ((1u << lane) - 1u));
-        next += __popc(need);
-        if (!active && j < hi) {
-          line_init(L, j ? (uint32_t)tab[j - 1] + 1u : ns, tab[j]);
-          myj = j;
-          active = true;
-        }
-      }
-      if (!__any_sync(0xffffffffu, active)) break;
-      if (active) {
-        if (L.pos < L.e) line_block<kAut>(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
-        if (L.pos < L.e) line_block<kAut>(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
-        if (L.pos >= L.e) {
-          ws.rawA[myj - lo] = L.A;
-          ws.rawB[myj - lo] = L.B;
-          active = false;
-        }
-      }
-    }
-    __syncwarp();
-    // ---- pass 3: balanced finalise
-    for (uint32_t j = lo + lane; j < hi; j += 32) {
-      const uint32_t s = j ? (uint32_t)tab[j - 1] + 1u : ns;
-      ws.lfl[j] = (uint8_t)line_finish(s, tab[j], ws.rawA[j - lo], ws.rawB[j - lo], ext, lb, ac);
-    }
-    __syncwarp();
+    walk_lines(ws, lut, first, lo, hi, ns, lane);          // pass 2
+    finish_lines(ws, lo, hi, ns, ext, lane, ac);                 // pass 3
   }
   // ---- pass 4: candidates (always) and header events (on request) to their global lists
-  const uint8_t* lfl = ws.lfl;
   const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
   uint32_t nc = 0, nh = 0;
   if (ext != 0) {
     for (uint32_t b = j0; b < cnt; b += 32) {
       const uint32_t j = b + lane;
-      const uint32_t fb = j < cnt ? lfl[j] : 0u;
+      const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
       nc += __popc(__ballot_sync(0xffffffffu, fb & LF_CAND));
       nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
     }
@@ -252,9 +282,9 @@ __device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, 
     uint32_t hbase = warp_reserve(&p.ctrl->n_hev, nh, lane);
     for (uint32_t b = j0; b < cnt; b += 32) {
       const uint32_t j = b + lane;
-      const uint32_t fb = j < cnt ? lfl[j] : 0u;
+      const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
       uint32_t s = 0, e = 0;
-      if (j < cnt) { s = j ? (uint32_t)tab[j - 1] + 1u : ns; e = tab[j]; }
+      if (j < cnt) { s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns; e = (uint32_t)tab[j] & TAB_POS; }
       const uint32_t line_off = cb + s - PRE;
       const uint32_t mc = __ballot_sync(0xffffffffu, fb & LF_CAND);
       if (fb & LF_CAND) {
@@ -274,7 +304,7 @@ __device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, 
       }
     }
   }
-  next_start = (uint32_t)tab[cnt - 1] + 1u;
+  next_start = ((uint32_t)tab[cnt - 1] & TAB_POS) + 1u;
   skip_first = false;
   __syncwarp();
 }
@@ -291,7 +321,7 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
   line_init(L, s, e);
   while (L.pos < L.e) {
     const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos));
-    if (ext) line_block<true>(L, w, lut, first); else line_block<false>(L, w, lut, first);
+    line_block(L, w, lut, first);
   }
   const uint32_t fl = line_finish(s, e, L.A, L.B, ext, lb, ac);
   if (fl & LF_CAND) {
@@ -306,12 +336,11 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
   }
 }
 
-template <bool kAut>
 __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, uint32_t first,
-                                              const WarpSmem& ws, uint32_t f, uint32_t cb, int ext, int lane) {
+                                              const WarpSmem& ws, uint32_t f, uint32_t cb, uint32_t fo,
+                                              uint32_t size, int ext, int lane) {
   const uint8_t* buf = ws.buf;
   uint16_t* tab = ws.tab;
-  const uint32_t size = (uint32_t)p.len[f];
   const uint32_t ce = min(cb + CH, size);
   const uint32_t le = min(ce + EXT, size);
   const uint32_t lim = PRE + (ce - cb);                  // buffer position just past the owned bytes
@@ -323,7 +352,7 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   // ---- pass 1: newline table of the owned bytes, 512 B per step (16 B per lane, SWAR)
   for (uint32_t tp = PRE; tp < lim; tp += 512) {
     if (cnt + 512 > NL_CAP) {
-      drain<kAut>(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+      drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
       cnt = 0;
     }
     const uint32_t pos = tp + lane * 16;
@@ -350,7 +379,7 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   }
   __syncwarp();
   // ---- the last owned line: starts in the chunk, may end behind it
-  const uint32_t tail_start = cnt ? (uint32_t)tab[cnt - 1] + 1u : next_start;
+  const uint32_t tail_start = cnt ? ((uint32_t)tab[cnt - 1] & TAB_POS) + 1u : next_start;
   const bool owned = !(skip_first && cnt == 0);
   bool have_tail = false, tail_long = false;
   uint32_t tail_end = 0;
@@ -376,14 +405,14 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   }
   if (have_tail) {
     if (cnt == NL_CAP) {
-      drain<kAut>(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+      drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
       cnt = 0;
     }
     if (lane == 0) tab[cnt] = (uint16_t)tail_end;
     ++cnt;
   }
-  drain<kAut>(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-  if (tail_long && lane == 0) long_line(p, lut, first, f, (uint32_t)p.off[f], size, ext, cb + tail_start - PRE, ac);
+  drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+  if (tail_long && lane == 0) long_line(p, lut, first, f, fo, size, ext, cb + tail_start - PRE, ac);
   // ---- per-file counters: warp reduce, then one store (single-chunk file) or one atomic per counter
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
@@ -407,49 +436,64 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   }
 }
 
-// Stage the bytes [max(cb-16,0), min(cb+CH+EXT, size)) of file f so that file byte cb sits at buf+PRE.
-__device__ __forceinline__ void issue_load(const ScanParams& p, uint8_t* buf, uint64_t* bar, uint32_t f, uint32_t cb) {
-  const uint32_t size = (uint32_t)p.len[f];
+// Stage the bytes [max(cb-16,0), min(cb+CH+EXT, size)) of a file so that file byte cb sits at buf+PRE.
+__device__ __forceinline__ void issue_load(const ScanParams& p, uint8_t* buf, uint64_t* bar, uint32_t fo,
+                                           uint32_t size, uint32_t cb) {
   const uint32_t lb = cb ? cb - PRE : 0u;
   const uint32_t le = min(cb + CH + EXT, size);
   const uint32_t bytes = (le - lb + 15u) & ~15u;          // the pad up to the 128-B file boundary is readable
   mbar_expect_tx(bar, bytes);
-  bulk_load(buf + PRE - (cb - lb), p.arena + (size_t)(uint32_t)p.off[f] + lb, bytes, bar);
+  bulk_load(buf + PRE - (cb - lb), p.arena + (size_t)fo + lb, bytes, bar);
+}
+
+struct Unit { uint32_t u, f, cb, fo, size; int ext; };
+
+// Claim the next work unit and fetch its metadata (4 dependent global loads: issued one chunk
+// ahead so that their latency hides behind the current chunk).
+__device__ __forceinline__ Unit claim_unit(const ScanParams& p, uint32_t n_units, int lane) {
+  Unit x{0, 0, 0, 0, 0, 0};
+  if (lane == 0) x.u = atomicAdd(&p.slab->work, 1u);
+  x.u = __shfl_sync(0xffffffffu, x.u, 0);
+  if (x.u < n_units) {
+    x.f = p.unit_file[p.unit_base + x.u];
+    x.cb = p.unit_begin[p.unit_base + x.u];
+    x.fo = (uint32_t)p.off[x.f];
+    x.size = (uint32_t)p.len[x.f];
+    x.ext = p.ext[x.f];
+  }
+  return x;
 }
 
 __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t* lut_py = reinterpret_cast<uint32_t*>(smem);
   uint32_t* lut_cj = lut_py + 256;
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) lut_py[i] = c_lut[i];
+  uint32_t* lut_zero = lut_py + 512;
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_py[i] = i < 512 ? c_lut[i] : 0u;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wb = smem + LUT_BYTES + warp * WARP_SMEM;
   WarpSmem ws;
   ws.buf = wb;
   ws.tab = reinterpret_cast<uint16_t*>(wb + BUF);
-  ws.lfl = wb + BUF + TAB_BYTES;
-  ws.rawB = reinterpret_cast<unsigned long long*>(wb + BUF + TAB_BYTES + LFL_BYTES);
-  ws.rawA = reinterpret_cast<uint32_t*>(wb + BUF + TAB_BYTES + LFL_BYTES + 8 * WALK_BATCH);
-  ws.bar = reinterpret_cast<uint64_t*>(wb + BUF + TAB_BYTES + LFL_BYTES + 12 * WALK_BATCH);
+  ws.rawB = reinterpret_cast<unsigned long long*>(wb + BUF + TAB_BYTES);
+  ws.rawA = reinterpret_cast<uint32_t*>(wb + BUF + TAB_BYTES + 8 * WALK_BATCH);
+  ws.bar = reinterpret_cast<uint64_t*>(wb + BUF + TAB_BYTES + 12 * WALK_BATCH);
   if (lane == 0) { mbar_init(ws.bar, 1); fence_mbar_init(); }
   __syncwarp();
   const uint32_t n_units = p.slab->n_units;
   uint32_t phase = 0;
-  while (true) {
-    uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(&p.slab->work, 1u);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if (u >= n_units) break;
-    const uint32_t f = p.unit_file[p.unit_base + u], cb = p.unit_begin[p.unit_base + u];
-    if (lane == 0) issue_load(p, ws.buf, ws.bar, f, cb);
-    const int ext = p.ext[f];
+  Unit cur = claim_unit(p, n_units, lane);
+  while (cur.u < n_units) {
+    if (lane == 0) issue_load(p, ws.buf, ws.bar, cur.fo, cur.size, cur.cb);
+    const Unit nxt = claim_unit(p, n_units, lane);       // metadata of the next unit arrives during this chunk
     while (!mbar_try_wait(ws.bar, phase)) {}
     phase ^= 1;
-    if (ext == 0) process_chunk<false>(p, lut_py, 0u, ws, f, cb, 0, lane);
-    else if (ext == TSM_EXT_PY) process_chunk<true>(p, lut_py, PY_FIRST, ws, f, cb, ext, lane);
-    else process_chunk<true>(p, lut_cj, CJ_FIRST, ws, f, cb, ext, lane);
+    const uint32_t* lut = cur.ext == 0 ? lut_zero : (cur.ext == TSM_EXT_PY ? lut_py : lut_cj);
+    const uint32_t first = cur.ext == 0 ? 0u : (cur.ext == TSM_EXT_PY ? PY_FIRST : CJ_FIRST);
+    process_chunk(p, lut, first, ws, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
     __syncwarp();
+    cur = nxt;
   }
 }
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtosemscan.so")
+LIB_PATH = os.environ.get("TOSEMSCAN_LIB") or os.path.join(_HERE, "libtosemscan.so")   # env override: tuning variants
 
 K = 128
 ALIGN = 128
