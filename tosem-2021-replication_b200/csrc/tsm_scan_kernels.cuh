@@ -572,24 +572,26 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
     const uint32_t size = (uint32_t)p.len[f];
     FileBytes rd(p.arena + (size_t)(uint32_t)p.off[f]);
-    // ---- one pass: T = [t0, last), L = trailing identifier run [run, last) if in_run
+    // ---- T = [t0, last): skip the indentation, find the first '(' / LF a word at a time (SWAR),
+    //      strip blanks backwards; L = the identifier run that ends at `last`
     uint32_t q = line_off;
     while (q < size && (cls[rd.get(q)] & CC_W)) ++q;     // LF is not blank: stops at the line end too
     const uint32_t t0 = q;
-    uint32_t last = t0, run = t0;
-    bool in_run = false, gap = false;
-    while (q < size) {
-      const uint32_t k = cls[rd.get(q)];
-      if (k & CC_STOP) break;
-      if (k & CC_W) gap = true;
-      else {
-        if (k & CC_IDENT) { if (!in_run || gap) run = q; in_run = true; } else in_run = false;
-        gap = false; last = q + 1;
-      }
-      ++q;
+    uint32_t stop = size;
+    for (uint32_t wb = t0 & ~7u; wb < size; wb += 8) {
+      unsigned long long w = __ldg(rd.base + (wb >> 3));
+      const unsigned long long x1 = w ^ 0x2828282828282828ull, x2 = w ^ 0x0A0A0A0A0A0A0A0Aull;
+      const unsigned long long k7 = 0x7F7F7F7F7F7F7F7Full;
+      unsigned long long z = (~(((x1 & k7) + k7) | x1 | k7)) | (~(((x2 & k7) + k7) | x2 | k7));   // 0x80 per '(' or LF
+      if (wb < t0) z &= ~0ull << (8u * (t0 - wb));
+      if (z) { stop = wb + ((uint32_t)__ffsll((long long)z) - 1u) / 8u; break; }
     }
-    const uint32_t tlen = last - t0;
-    const uint32_t Ls = in_run ? run : last, Ln = last - Ls;
+    stop = min(stop, size);
+    uint32_t last = stop;
+    while (last > t0 && (cls[rd.get(last - 1)] & CC_W)) --last;
+    uint32_t Ls = last;
+    while (Ls > t0 && (cls[rd.get(Ls - 1)] & CC_IDENT)) --Ls;
+    const uint32_t tlen = last - t0, Ln = last - Ls;
     // ---- category (SPEC section 6), first match wins
     int cat = 0;
     bool done = false;
