@@ -167,6 +167,7 @@ def run_b200(args):
         raise SystemExit("no CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if n > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nf = args.files_per_gpu
     corpus = ts.gen_corpus(SEED_C2, nf, 0, FILE_SIZE, first_index=rank, index_stride=n, n_groups=N_GROUPS, pinned=True)
