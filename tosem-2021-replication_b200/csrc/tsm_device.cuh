@@ -26,6 +26,9 @@ constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128
 #ifndef TSM_WALK_BATCH
 #define TSM_WALK_BATCH 256
 #endif
+#ifndef TSM_BLOCKS_PER_ITER
+#define TSM_BLOCKS_PER_ITER 2
+#endif
 #ifndef TSM_SCAN_WARPS
 #define TSM_SCAN_WARPS 4
 #endif

@@ -203,10 +203,9 @@ struct WarpSmem {                                        // per-warp carve-up of
 // Pass 2: lanes walk the lines [lo, hi) of the table, refilling dynamically; raw (A, B) per line to shared.
 // Not inlined on purpose: the hot loop gets its own register allocation (the chunk-level state of
 // the caller is saved once per call instead of competing with the loop for registers).
-__device__ __noinline__ void walk_lines(const WarpSmem& ws, const uint32_t* lut, uint32_t first, uint32_t lo,
-                                        uint32_t hi, uint32_t ns, int lane) {
-  const uint8_t* buf = ws.buf;
-  const uint16_t* tab = ws.tab;
+__device__ __noinline__ void walk_lines(const uint8_t* buf, const uint16_t* tab, uint32_t* rawA,
+                                        unsigned long long* rawB, const uint32_t* lut, uint32_t first,
+                                        uint32_t lo, uint32_t hi, uint32_t ns, int lane) {
   uint32_t next = lo;
   bool active = false;
   uint32_t myj = 0;
@@ -224,11 +223,12 @@ __device__ __noinline__ void walk_lines(const WarpSmem& ws, const uint32_t* lut,
     }
     if (!__any_sync(0xffffffffu, active)) break;
     if (active) {
-      if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
-      if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
+#pragma unroll
+      for (int rep = 0; rep < TSM_BLOCKS_PER_ITER; ++rep)  // 8-byte blocks per refill round (tuned: profiles/)
+        if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
       if (L.pos >= L.e) {
-        ws.rawA[myj - lo] = L.A;
-        ws.rawB[myj - lo] = L.B;
+        rawA[myj - lo] = L.A;
+        rawB[myj - lo] = L.B;
         active = false;
       }
     }
@@ -237,15 +237,16 @@ __device__ __noinline__ void walk_lines(const WarpSmem& ws, const uint32_t* lut,
 }
 
 // Pass 3: balanced finalise, one lane per line.
-__device__ __noinline__ void finish_lines(const WarpSmem& ws, uint32_t lo, uint32_t hi, uint32_t ns, int ext,
-                                          int lane, Accum& ac) {
-  const SmemByte lb{ws.buf};
+__device__ __noinline__ void finish_lines(const uint8_t* buf, uint16_t* tab, const uint32_t* rawA,
+                                          const unsigned long long* rawB, uint32_t lo, uint32_t hi, uint32_t ns,
+                                          int ext, int lane, Accum& ac) {
+  const SmemByte lb{buf};
   Accum a = ac;
   for (uint32_t j = lo + lane; j < hi; j += 32) {
-    const uint32_t s = j ? ((uint32_t)ws.tab[j - 1] & TAB_POS) + 1u : ns;
-    const uint32_t e = (uint32_t)ws.tab[j] & TAB_POS;
-    const uint32_t fl = line_finish(s, e, ws.rawA[j - lo], ws.rawB[j - lo], ext, lb, a);
-    ws.tab[j] = (uint16_t)(e | (fl << 13));              // flags ride in the 3 spare bits of the entry
+    const uint32_t s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns;
+    const uint32_t e = (uint32_t)tab[j] & TAB_POS;
+    const uint32_t fl = line_finish(s, e, rawA[j - lo], rawB[j - lo], ext, lb, a);
+    tab[j] = (uint16_t)(e | (fl << 13));                 // flags ride in the 3 spare bits of the entry
   }
   ac = a;
   __syncwarp();
@@ -262,8 +263,8 @@ __device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, 
   const uint32_t ns = next_start;
   for (uint32_t lo = j0; lo < cnt; lo += WALK_BATCH) {
     const uint32_t hi = min(cnt, lo + WALK_BATCH);
-    walk_lines(ws, lut, first, lo, hi, ns, lane);          // pass 2
-    finish_lines(ws, lo, hi, ns, ext, lane, ac);                 // pass 3
+    walk_lines(ws.buf, ws.tab, ws.rawA, ws.rawB, lut, first, lo, hi, ns, lane);   // pass 2
+    finish_lines(ws.buf, ws.tab, ws.rawA, ws.rawB, lo, hi, ns, ext, lane, ac);    // pass 3
   }
   // ---- pass 4: candidates (always) and header events (on request) to their global lists
   const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
