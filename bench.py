@@ -64,7 +64,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -254,6 +254,13 @@ def run_b200(args):
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic, traffic_src = None, None
+        try:   # one `ncu --set full` capture of this kernel on this workload (tools/ncu_summary.py --traffic)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k_scan_traffic.json")))["k_scan"]
+            if nf == FILES_PER_GPU:
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         scan_ms = sums[1] / max(nscan, 1)
         achieved = corpus.algorithmic_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
         out = {"metric": METRIC, "value": src * n * args.steps / (ms * 1e-3) / 1e6, "unit": "MB/s", "n_gpus": n,
@@ -261,7 +268,7 @@ def run_b200(args):
                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config(args, n),
                "files_per_s": nf * n * args.steps / (ms * 1e-3),
                "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None,
+                            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                             "algorithmic_bytes_per_launch": corpus.algorithmic_bytes,
                             "kernel_ms": {"k_plan": sums[0] / max(nscan, 1), "k_scan": scan_ms,

@@ -41,7 +41,17 @@ def main():
     md = ["# ncu summary of `%s`" % rep, "",
           "Captured with `ncu --set full --clock-control none --import-source on` under gpurun; read here with `ncu -i`.",
           "Per-launch values (one replayed launch per row; cold cache, serialised - compare shares, not absolutes).", ""]
+    traffic = {}
     for r in raw[2:]:
+        name = r[ix["Kernel Name"]].split("(")[0]
+        try:
+            def tobytes(v, u):
+                return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+            traffic.setdefault(name, {"dram_bytes_read": tobytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]),
+                                      "dram_bytes_write": tobytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]]),
+                                      "source": out + ".md"})
+        except (KeyError, ValueError):
+            pass
         md.append("## %s" % r[ix["Kernel Name"]])
         md.append("")
         md.append("| metric | value | unit |")
@@ -97,6 +107,9 @@ def main():
             md.append("| %s | %d | %.0f | %.1f %% |" % (k, len(v), sum(v) / len(v), 100.0 * sum(v) / total))
         md.append("")
     open(out + ".md", "w").write("\n".join(md))
+    if "--traffic" in sys.argv:
+        import json
+        json.dump(traffic, open(sys.argv[sys.argv.index("--traffic") + 1], "w"), indent=1)
     print("wrote", out + ".md")
 
 
