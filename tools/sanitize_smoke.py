@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Small scan + diff + reduce under compute-sanitizer (run: compute-sanitizer --tool memcheck python tools/sanitize_smoke.py)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tosem-2021-replication_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import corpus_util as cu
+import tosemscan as ts
+
+s = ts.Scanner(0, 1 << 24, 4096, 16)
+files, exts, grps = cu.edge_corpus()
+r = s.scan(ts.pack(files, exts, grps, 3), 3)
+files, exts, grps = cu.fuzz_corpus(5, 120, 30000, long_lines=True)
+r2 = s.scan(ts.pack(files, exts, grps, 5), 3)
+c = ts.gen_corpus(3, 300, 1, n_groups=4, pinned=False)
+r3 = s.scan(c, 0)
+a = ts.pack([b"a\nb\nc\n", b"x\n" * 50, b""], [1, 1, 1])
+b = ts.pack([b"a\nc\nd\n", b"y\n" * 40, b"q\n"], [1, 1, 1])
+print(s.diff_pairs(a, b))
+fl = (np.random.default_rng(1).random((500, 7)) < 0.3).astype(np.uint8)
+print(s.reduce(fl, np.arange(500) % 3, np.arange(500) % 41, 3, 41)[1])
+print("totals", r["totals"], r2["totals"], r3["totals"])

@@ -242,11 +242,17 @@ __device__ __noinline__ void finish_lines(const uint8_t* buf, uint16_t* tab, con
                                           int ext, int lane, Accum& ac) {
   const SmemByte lb{buf};
   Accum a = ac;
-  for (uint32_t j = lo + lane; j < hi; j += 32) {
-    const uint32_t s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns;
-    const uint32_t e = (uint32_t)tab[j] & TAB_POS;
-    const uint32_t fl = line_finish(s, e, rawA[j - lo], rawB[j - lo], ext, lb, a);
-    tab[j] = (uint16_t)(e | (fl << 13));                 // flags ride in the 3 spare bits of the entry
+  for (uint32_t base = lo; base < hi; base += 32) {      // uniform trip count: the warp syncs inside
+    const uint32_t j = base + lane;
+    const bool valid = j < hi;
+    uint32_t s = 0, e = 0;
+    if (valid) { s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns; e = (uint32_t)tab[j] & TAB_POS; }
+    __syncwarp();                                        // every neighbour entry is read before any is rewritten
+    if (valid) {
+      const uint32_t fl = line_finish(s, e, rawA[j - lo], rawB[j - lo], ext, lb, a);
+      tab[j] = (uint16_t)(e | (fl << 13));               // flags ride in the 3 spare bits of the entry
+    }
+    __syncwarp();
   }
   ac = a;
   __syncwarp();
