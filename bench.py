@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W             # this repo's sm_100a path
     python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement on the host cores
 
-A step = one pass of the hot path (k_plan, k_scan, k_classify, k_totals, and for N > 1 the single
+A step = one pass of the hot path (k_plan, k_scan, k_classify, and for N > 1 the single
 allreduce of the count table) over one batch of synthetic input: BASELINE config C2, 100 000 files
 x 4 KiB per GPU (weak scaling; rank r holds logical files r, r+N, ... of one N*100k corpus).
 `value`  = source MB/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks.
@@ -272,7 +272,7 @@ def run_b200(args):
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                             "algorithmic_bytes_per_launch": corpus.algorithmic_bytes,
                             "kernel_ms": {"k_plan": sums[0] / max(nscan, 1), "k_scan": scan_ms,
-                                          "k_classify": sums[2] / max(nscan, 1), "k_totals": sums[3] / max(nscan, 1)},
+                                          "k_classify": sums[2] / max(nscan, 1)},
                             "scans_timed": nscan},
                "e2e": {"value": src * n * ke / e2e_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,

@@ -109,7 +109,8 @@ int tsm_device_counts(tsm_ctx* ctx, void** dptr, int64_t* n_int64);
 /* Kernel launches issued by the last tsm_scan / tsm_scan_resident call. */
 int tsm_last_launch_count(tsm_ctx* ctx);
 /* Device time (CUDA events on the launching stream) of the kernels of the last scan, in launch
- * order: k_plan, k_scan, k_classify, k_totals.  Synchronises on the last of them. */
+ * order: k_plan, k_scan, k_classify (+ a 4th slot that is 0: the totals are fused into k_classify).
+ * Synchronises on the last of them. */
 int tsm_last_kernel_ms(tsm_ctx* ctx, float* ms4);
 /* Per-kernel device time summed over every scan since the last reset (event ring, no host sync
  * inside a back-to-back series); waits for scans still in flight. */

@@ -258,7 +258,7 @@ static ScanParams make_params(const tsm_ctx* c, uint32_t flags) {
   return p;
 }
 
-// One scan = [memsets] + per slab (k_plan, k_scan) + k_classify + k_totals on `st`.  With host != NULL
+// One scan = [memsets] + per slab (k_plan, k_scan) + k_classify on `st`.  With host != NULL
 // the arena slabs are copied on the ctx's copy stream and each slab's kernels wait for its copy only,
 // so the H2D of slab s+1 overlaps the scan of slab s (the e2e path); with host == NULL the arena is
 // already resident and there is a single slab.
@@ -311,11 +311,10 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     const size_t hist = sizeof(uint32_t) * (256 + (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0));
     k_classify<<<c->sms * 8, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
-    k_totals<<<std::min((n + 255) / 256, c->sms * 4), 256, 0, st>>>(p);
-    cudaEventRecord(ev[4], st);
+    cudaEventRecord(ev[4], st);                           // (slot of the former k_totals, now fused into k_classify)
     c->ev_used[es] = (n_slabs == 1);
     c->ev_last = es;
-    c->launches = 2 * n_slabs + 2;
+    c->launches = 2 * n_slabs + 1;
     CU(cudaGetLastError());
   }
   c->last_flags = flags;

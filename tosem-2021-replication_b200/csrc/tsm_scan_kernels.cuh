@@ -6,8 +6,9 @@
 //               mbarrier, double buffered), pass 1 = SWAR newline table, pass 2 = lane-per-line
 //               Shift-And automaton + Mersenne-61 line hash, then per-file counters, digest and
 //               the candidate (assertion-line) list.
-//   k_classify  one thread per candidate: statement, last identifier, category (S5), events, and
-//               the cross-file aggregate into a shared-memory privatised [group][category] table.
+//   k_classify  one thread per candidate: statement, last identifier, category (S5), events, the
+//               cross-file aggregate into a shared-memory privatised [group][category] table, and
+//               the totals of the per-file records.
 //
 // There is no reference kernel: the reference ships data only.  Rules cite
 // docs/SPEC.md, which cites the artefacts.
@@ -685,6 +686,26 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
       } else p.ctrl->overflow = 1;
     }
   }
+  // ---- totals of the per-file records (lines, assertion lines, headers, fixture headers) behind the table
+  {
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_files; f += gridDim.x * blockDim.x) {
+      const tsm_file_stat s = p.stats[f];
+      t0 += s.n_lines; t1 += s.n_assert; t2 += s.n_headers; t3 += s.n_fixture;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, d); t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, d); t3 += __shfl_xor_sync(0xffffffffu, t3, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* tot = p.counts + (size_t)(p.n_groups + 1) * TSM_K;
+      if (t0) atomicAdd(&tot[0], t0);
+      if (t1) atomicAdd(&tot[1], t1);
+      if (t2) atomicAdd(&tot[2], t2);
+      if (t3) atomicAdd(&tot[3], t3);
+    }
+  }
   if (use_smem) {
     __syncthreads();
     for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) {
@@ -694,27 +715,6 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
         atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + (i & (TSM_K - 1))], (unsigned long long)v);
       }
     }
-  }
-}
-
-// Totals of the per-file records (lines, assertion lines, headers, fixture headers).
-__global__ void k_totals(ScanParams p) {
-  unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_files; f += gridDim.x * blockDim.x) {
-    const tsm_file_stat s = p.stats[f];
-    t0 += s.n_lines; t1 += s.n_assert; t2 += s.n_headers; t3 += s.n_fixture;
-  }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    t0 += __shfl_xor_sync(0xffffffffu, t0, d); t1 += __shfl_xor_sync(0xffffffffu, t1, d);
-    t2 += __shfl_xor_sync(0xffffffffu, t2, d); t3 += __shfl_xor_sync(0xffffffffu, t3, d);
-  }
-  if ((threadIdx.x & 31) == 0) {                         // the totals live behind the count table
-    unsigned long long* tot = p.counts + (size_t)(p.n_groups + 1) * TSM_K;
-    if (t0) atomicAdd(&tot[0], t0);
-    if (t1) atomicAdd(&tot[1], t1);
-    if (t2) atomicAdd(&tot[2], t2);
-    if (t3) atomicAdd(&tot[3], t3);
   }
 }
 

@@ -327,7 +327,7 @@ class Scanner:
         return lib().tsm_last_launch_count(self._ctx)
 
     def last_kernel_ms(self):
-        """Device time of k_plan, k_scan, k_classify, k_totals of the last scan (CUDA events)."""
+        """Device time of k_plan, k_scan, k_classify of the last scan (4th slot is 0: k_totals is fused)."""
         ms = (C.c_float * 4)()
         rc = lib().tsm_last_kernel_ms(self._ctx, C.byref(ms))
         if rc:
