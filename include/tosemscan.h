@@ -121,6 +121,13 @@ int tsm_kernel_ms_stats(tsm_ctx* ctx, double* sum_ms4, int64_t* n_scans, int res
 int tsm_diff_pairs(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
                    int64_t* added, int64_t* removed, void* stream);
 
+/* The same plus, per pair, the hunks of the canonical edit script (docs/SPEC.md section 8) classified as
+ * add / del / mod, and how many inserted / deleted lines are assertion lines (BASELINE config C5,
+ * "per-hunk diff + classify").  `ext` of both corpora is used for the assertion rule. */
+typedef struct tsm_diff_detail { int64_t hunks_add, hunks_del, hunks_mod, added_assert, removed_assert; } tsm_diff_detail;
+int tsm_diff_pairs_detail(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
+                          int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream);
+
 /* S10 reduce (RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/
  * tests_methods_v2.csv): out[f*n_repos+r] = distinct case ids with flags[row*n_flags+f] != 0 in
  * repo r; cases_per_repo[r] = distinct case ids of repo r. Host arrays; integer work on device. */

@@ -344,6 +344,107 @@ int orc_diff_pairs(const uint8_t* arena_old, const int32_t* off_old, const int32
   return 0;
 }
 
+/* SPEC section 8, hunks: Myers' greedy D-path search with the rows of V kept for the canonical backtrack.
+ * BASELINE.json configs[4] ("per-hunk diff+classify"); no artefact pins it (parity unpinned). */
+int64_t orc_diff_script(const uint64_t* a, int64_t n, const uint64_t* b, int64_t m, const uint8_t* fa,
+                        const uint8_t* fb, orc_diff_detail* out) {
+  orc_diff_detail d = {0, 0, 0, 0, 0};
+  int64_t pre = 0;
+  while (pre < n && pre < m && a[pre] == b[pre]) ++pre;
+  int64_t suf = 0;
+  while (suf < n - pre && suf < m - pre && a[n - 1 - suf] == b[m - 1 - suf]) ++suf;
+  a += pre; b += pre; if (fa) fa += pre; if (fb) fb += pre;
+  n -= pre + suf; m -= pre + suf;
+  int64_t D = 0;
+  if (n == 0 || m == 0) {
+    D = n + m;
+    if (n) { d.hunks_del = 1; if (fa) for (int64_t i = 0; i < n; ++i) d.removed_assert += fa[i] != 0; }
+    if (m) { d.hunks_add = 1; if (fb) for (int64_t i = 0; i < m; ++i) d.added_assert += fb[i] != 0; }
+    if (out) *out = d;
+    return D;
+  }
+  const int64_t off = n + m + 1;
+  int64_t* V = (int64_t*)calloc((size_t)(2 * (n + m) + 3), sizeof(int64_t));
+  int64_t** rows = (int64_t**)calloc((size_t)(n + m + 1), sizeof(int64_t*));   /* rows[d][k + d] */
+  if (!V || !rows) { free(V); free(rows); return -1; }
+  int found = 0;
+  V[off + 1] = 0;
+  for (D = 0; D <= n + m && !found; ++D) {
+    for (int64_t k = -D; k <= D; k += 2) {
+      int64_t x = (k == -D || (k != D && V[off + k - 1] < V[off + k + 1])) ? V[off + k + 1] : V[off + k - 1] + 1;
+      int64_t y = x - k;
+      while (x < n && y < m && a[x] == b[y]) { ++x; ++y; }
+      V[off + k] = x;
+      if (x >= n && y >= m) found = 1;
+    }
+    rows[D] = (int64_t*)malloc(sizeof(int64_t) * (size_t)(2 * D + 1));
+    if (!rows[D]) { found = -1; break; }
+    memcpy(rows[D], V + off - D, sizeof(int64_t) * (size_t)(2 * D + 1));
+  }
+  if (found == 1) {
+    --D;
+    /* backtrack: edits from the last to the first; snake_after = matches between this edit and the next */
+    int64_t x = n, y = m;
+    int in_hunk = 0, has_add = 0, has_del = 0;
+    for (int64_t dd = D; dd >= 1; --dd) {
+      const int64_t k = x - y;
+      const int64_t* P = rows[dd - 1];                    /* P[kk + dd - 1] */
+      const int down = (k == -dd || (k != dd && P[k - 1 + dd - 1] < P[k + 1 + dd - 1]));
+      const int64_t pk = down ? k + 1 : k - 1;
+      const int64_t px = P[pk + dd - 1], py = px - pk;
+      const int64_t midx = down ? px : px + 1;
+      const int64_t snake_after = x - midx;
+      if (in_hunk && snake_after > 0) {                   /* a match separates this edit from the later hunk */
+        if (has_add && has_del) d.hunks_mod++; else if (has_add) d.hunks_add++; else d.hunks_del++;
+        has_add = has_del = 0;
+      }
+      in_hunk = 1;
+      if (down) { has_add = 1; if (fb) d.added_assert += fb[py] != 0; }
+      else { has_del = 1; if (fa) d.removed_assert += fa[px] != 0; }
+      x = px; y = py;
+    }
+    if (in_hunk) { if (has_add && has_del) d.hunks_mod++; else if (has_add) d.hunks_add++; else d.hunks_del++; }
+  }
+  for (int64_t i = 0; i <= n + m; ++i) free(rows[i]);
+  free(rows); free(V);
+  if (found != 1) return -1;
+  if (out) *out = d;
+  return D;
+}
+
+static int64_t file_line_hashes_flags(const uint8_t* p, uint32_t size, int ext, uint64_t** out, uint8_t** flags) {
+  int64_t n = file_line_hashes(p, size, out);
+  if (n < 0) return n;
+  uint8_t* f = (uint8_t*)calloc((size_t)(n ? n : 1), 1);
+  if (!f) return -1;
+  uint32_t pos = 0; int64_t i = 0;
+  while (pos < size) {
+    const uint8_t* nlp = memchr(p + pos, '\n', size - pos);
+    uint32_t end = nlp ? (uint32_t)(nlp - p) : size;
+    f[i++] = (uint8_t)(ext != 0 && orc_is_assert_line(p + pos, end - pos));
+    pos = end + 1;
+  }
+  *flags = f;
+  return n;
+}
+
+int orc_diff_pairs_detail(const uint8_t* arena_old, const int32_t* off_old, const int32_t* len_old, const uint8_t* ext_old,
+                          const uint8_t* arena_new, const int32_t* off_new, const int32_t* len_new, const uint8_t* ext_new,
+                          int32_t n_pairs, int64_t* added, int64_t* removed, orc_diff_detail* detail) {
+  for (int32_t i = 0; i < n_pairs; ++i) {
+    uint64_t *a = NULL, *b = NULL; uint8_t *fa = NULL, *fb = NULL;
+    int64_t n = file_line_hashes_flags(arena_old + off_old[i], (uint32_t)len_old[i], ext_old ? ext_old[i] : 0, &a, &fa);
+    int64_t m = file_line_hashes_flags(arena_new + off_new[i], (uint32_t)len_new[i], ext_new ? ext_new[i] : 0, &b, &fb);
+    int64_t D = (n < 0 || m < 0) ? -1 : orc_diff_script(a, n, b, m, fa, fb, &detail[i]);
+    free(a); free(b); free(fa); free(fb);
+    if (D < 0) return -1;
+    const int64_t l = (n + m - D) / 2;
+    removed[i] = n - l;
+    added[i] = m - l;
+  }
+  return 0;
+}
+
 /* ---------------------------------------------------------------- SPEC section 9 (S10)
  * RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/tests_methods_v2.csv. */
 int orc_reduce(const uint8_t* flags, const int32_t* repo, const int32_t* case_id, int32_t n_rows,

@@ -60,6 +60,15 @@ int orc_diff_pairs(const uint8_t* arena_old, const int32_t* off_old, const int32
                    const uint8_t* arena_new, const int32_t* off_new, const int32_t* len_new,
                    int32_t n_pairs, int64_t* added, int64_t* removed);
 
+/* SPEC section 8, hunks: canonical edit script of two hash sequences; fa/fb = per-line assertion flags (may be
+ * NULL).  Returns the edit distance D (insertions + deletions) or -1. */
+typedef struct { int64_t hunks_add, hunks_del, hunks_mod, added_assert, removed_assert; } orc_diff_detail;
+int64_t orc_diff_script(const uint64_t* a, int64_t n, const uint64_t* b, int64_t m, const uint8_t* fa,
+                        const uint8_t* fb, orc_diff_detail* out);
+int orc_diff_pairs_detail(const uint8_t* arena_old, const int32_t* off_old, const int32_t* len_old, const uint8_t* ext_old,
+                          const uint8_t* arena_new, const int32_t* off_new, const int32_t* len_new, const uint8_t* ext_new,
+                          int32_t n_pairs, int64_t* added, int64_t* removed, orc_diff_detail* detail);
+
 /* SPEC section 9: out[f*n_repos + r] = distinct cases with flag f set in repo r;
  * cases_per_repo[r] = distinct cases of repo r.  case ids < n_cases. */
 int orc_reduce(const uint8_t* flags, const int32_t* repo, const int32_t* case_id, int32_t n_rows,

@@ -19,6 +19,8 @@ ASSERT_EVENT = np.dtype([("file", "<u4"), ("line_off", "<u4"), ("stmt_off", "<u4
                          ("stmt_len", "<u2"), ("cat", "<u2"), ("ident_off", "<u4"),
                          ("ident_len", "<u2"), ("pad", "<u2"), ("stmt_hash", "<u8")])
 HEADER_EVENT = np.dtype([("file", "<u4"), ("line_off", "<u4"), ("line_len", "<u4"), ("kind", "<u4")])
+DIFF_DETAIL = np.dtype([("hunks_add", "<i8"), ("hunks_del", "<i8"), ("hunks_mod", "<i8"),
+                        ("added_assert", "<i8"), ("removed_assert", "<i8")])
 assert FILE_STAT.itemsize == 24 and ASSERT_EVENT.itemsize == 32 and HEADER_EVENT.itemsize == 16
 
 _lib = None
@@ -59,6 +61,10 @@ def lib():
         L.orc_lcs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         L.orc_diff_pairs.restype = C.c_int
         L.orc_diff_pairs.argtypes = [C.c_void_p] * 6 + [C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_diff_pairs_detail.restype = C.c_int
+        L.orc_diff_pairs_detail.argtypes = [C.c_void_p] * 8 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_diff_script.restype = C.c_int64
+        L.orc_diff_script.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_reduce.restype = C.c_int
         L.orc_reduce.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
         _lib = L
@@ -177,6 +183,32 @@ def diff_pairs(old, new):
     if rc != 0:
         raise ValueError("orc_diff_pairs failed")
     return added, removed
+
+
+def diff_pairs_detail(old, new):
+    """old/new: (arena, off, len, ext).  Returns added, removed, detail (DIFF_DETAIL records)."""
+    n = len(old[2])
+    added = np.zeros(n, np.int64)
+    removed = np.zeros(n, np.int64)
+    det = np.zeros(max(n, 1), DIFF_DETAIL)
+    a = [np.ascontiguousarray(old[0], np.uint8), np.ascontiguousarray(old[1], np.int32),
+         np.ascontiguousarray(old[2], np.int32), np.ascontiguousarray(old[3], np.uint8)]
+    b = [np.ascontiguousarray(new[0], np.uint8), np.ascontiguousarray(new[1], np.int32),
+         np.ascontiguousarray(new[2], np.int32), np.ascontiguousarray(new[3], np.uint8)]
+    rc = lib().orc_diff_pairs_detail(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]),
+                                     n, _p(added), _p(removed), _p(det))
+    if rc != 0:
+        raise ValueError("orc_diff_pairs_detail failed")
+    return added, removed, det[:n]
+
+
+def diff_script(a, b, fa=None, fb=None):
+    a = np.ascontiguousarray(a, np.uint64)
+    b = np.ascontiguousarray(b, np.uint64)
+    det = np.zeros(1, DIFF_DETAIL)
+    D = lib().orc_diff_script(_p(a), a.size, _p(b), b.size, None if fa is None else _p(np.ascontiguousarray(fa, np.uint8)),
+                              None if fb is None else _p(np.ascontiguousarray(fb, np.uint8)), _p(det))
+    return int(D), det[0]
 
 
 def reduce(flags, repo, case_id, n_repos, n_cases):

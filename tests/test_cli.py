@@ -172,7 +172,7 @@ def test_diff_trees(tmp_path):
     os.makedirs(old / "a")
     os.makedirs(new / "a")
     (old / "a" / "x.py").write_bytes(b"1\n2\n3\n4\n")
-    (new / "a" / "x.py").write_bytes(b"1\n3\n4\n5\n6\n")
+    (new / "a" / "x.py").write_bytes(b"1\n3\n4\nassert 5\n6\n")
     (old / "gone.c").write_bytes(b"a\nb\n")
     (new / "fresh.c").write_bytes(b"c\n")
     (old / "same.h").write_bytes(b"s\n")
@@ -182,4 +182,6 @@ def test_diff_trees(tmp_path):
     assert out.returncode == 0, out.stderr
     assert out.stdout.replace("\r\n", "\n").strip().split("\n") == ["cloc,added,removed", "6,3,3"]
     got = {r[0]: r[1:] for r in read_csv(outp)[1:]}
-    assert got == {"a/x.py": ["3", "2", "1"], "gone.c": ["2", "0", "2"], "fresh.c": ["1", "1", "0"]}
+    # cloc, added, removed, hunks_add, hunks_del, hunks_mod, added_assert, removed_assert
+    assert got == {"a/x.py": ["3", "2", "1", "1", "1", "0", "1", "0"], "gone.c": ["2", "0", "2", "0", "1", "0", "0", "0"],
+                   "fresh.c": ["1", "1", "0", "1", "0", "0", "0", "0"]}

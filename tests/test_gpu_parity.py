@@ -226,3 +226,30 @@ def test_diff_heavy_edits_and_unrelated_files(scanner):
     olds2, _ = _pairs(3, 40, 12000)
     _, news2 = _pairs(4, 40, 12000)
     check_diff(scanner, olds2, news2)          # unrelated files: D close to n + m
+
+
+def check_diff_detail(scanner, olds, news, exts):
+    a = ts.pack(olds, exts)
+    b = ts.pack(news, exts)
+    add, rem, det = scanner.diff_pairs(a, b, detail=True)
+    wadd, wrem, wdet = orc.diff_pairs_detail((a.arena, a.off, a.len, a.ext), (b.arena, b.off, b.len, b.ext))
+    assert np.array_equal(add, wadd) and np.array_equal(rem, wrem)
+    for f in det.dtype.names:
+        bad = np.nonzero(det[f] != wdet[f])[0]
+        assert bad.size == 0, (f, bad[:5], det[bad[:5]], wdet[bad[:5]])
+    return add, rem, det
+
+
+def test_diff_hunks_and_classification(scanner):
+    olds = [b"a\nb\nc\n", b"a\nb\nc\n", b"def t():\n  assert x\n  y = 1\n", b"", b"k\n" * 9, b"EXPECT_EQ(a, b);\nfoo\n"]
+    news = [b"a\nc\n", b"a\nB\nc\nd\n", b"def t():\n  assert x == 2\n  y = 1\n  assert y\n", b"assert q\n", b"", b"foo\nEXPECT_EQ(a, b);\n"]
+    add, rem, det = check_diff_detail(scanner, olds, news, [1, 1, 1, 1, 1, 2])
+    assert (det["hunks_del"][0], det["hunks_mod"][1], det["hunks_add"][1]) == (1, 1, 1)
+    assert (det["added_assert"][2], det["removed_assert"][2]) == (2, 1)
+    assert det["hunks_add"][3] == 1 and det["added_assert"][3] == 1 and det["hunks_del"][4] == 1
+    o2, n2 = _pairs(7, 300, 40000)
+    exts = [1 + (i % 2) for i in range(300)]
+    add, rem, det = check_diff_detail(scanner, o2, n2, exts)
+    assert int((det["hunks_add"] + det["hunks_del"] + det["hunks_mod"]).sum()) > 300
+    o3, n3 = _pairs(8, 40, 15000, lam=60.0)
+    check_diff_detail(scanner, o3, n3, [1] * 40)

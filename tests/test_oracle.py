@@ -180,6 +180,27 @@ def test_lcs_oracle_against_bruteforce():
         assert orc.lcs(np.array(a, np.uint64), np.array(b, np.uint64)) == brute(a, b)
 
 
+def test_diff_script_distance_and_hunks():
+    """SPEC section 8: D equals n + m - 2 LCS, and the hunk bookkeeping on hand-checked cases."""
+    rng = random.Random(11)
+    for _ in range(300):
+        a = [rng.randrange(5) for _ in range(rng.randrange(0, 25))]
+        b = [rng.randrange(5) for _ in range(rng.randrange(0, 25))]
+        D, det = orc.diff_script(a, b)
+        assert D == len(a) + len(b) - 2 * orc.lcs(np.array(a, np.uint64), np.array(b, np.uint64))
+        # every hunk has at least one edit; a mod hunk has at least two
+        assert det["hunks_add"] + det["hunks_del"] + 2 * det["hunks_mod"] <= D or D == 0
+        assert (D == 0) == (det["hunks_add"] + det["hunks_del"] + det["hunks_mod"] == 0)
+    cases = [([1, 2, 3], [1, 2, 3], (0, 0, 0)), ([1, 2, 3], [1, 3], (0, 1, 0)), ([1, 3], [1, 2, 3], (1, 0, 0)),
+             ([1, 2, 3], [1, 9, 3], (0, 0, 1)), ([], [5, 6], (1, 0, 0)), ([5, 6], [], (0, 1, 0)),
+             ([1, 2, 3, 4, 5], [1, 8, 3, 9, 5], (0, 0, 2)), ([1, 2, 3, 4, 5, 6, 7], [2, 3, 4, 5, 6, 7, 8], (1, 1, 0))]
+    for a, b, want in cases:
+        D, det = orc.diff_script(a, b)
+        assert (det["hunks_add"], det["hunks_del"], det["hunks_mod"]) == want, (a, b, det)
+    D, det = orc.diff_script([1, 2, 3, 4], [1, 7, 4], fa=[0, 1, 1, 0], fb=[0, 1, 0])
+    assert D == 3 and det["removed_assert"] == 2 and det["added_assert"] == 1 and det["hunks_mod"] == 1
+
+
 def test_scan_on_edge_corpus_matches_python_restatement():
     files, exts, grps = cu.edge_corpus()
     arena, off, ln = orc.pack(files)

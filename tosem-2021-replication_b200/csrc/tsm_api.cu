@@ -482,12 +482,12 @@ struct DevBuf {                                           // cudaMalloc'd scratc
 };
 
 struct HostSide {                                         // device image of one side of the pairs
-  DevBuf arena, off, len, n_lines, line_base, line_end, line_hash;
+  DevBuf arena, off, len, n_lines, line_base, line_end, line_hash, ext, line_flag;
   std::vector<unsigned long long> base;                   // host copy of line_base
   DiffSide d{};
 };
 
-int side_lines(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
+int side_lines(const tsm_corpus* k, HostSide& h, cudaStream_t st, bool want_flags) {
   const int32_t n = k->n_files;
   const size_t ab = (size_t)k->off[n];
   if (!h.arena.alloc(ab + 4096) || !h.off.alloc(sizeof(int32_t) * ((size_t)n + 1)) || !h.len.alloc(sizeof(int32_t) * (size_t)n) ||
@@ -512,6 +512,14 @@ int side_lines(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
   h.d.line_base = h.line_base.as<unsigned long long>();
   h.d.line_end = h.line_end.as<uint32_t>();
   h.d.line_hash = h.line_hash.as<unsigned long long>();
+  h.d.ext = nullptr; h.d.line_flag = nullptr;
+  if (want_flags) {
+    if (!h.line_flag.alloc((size_t)total) || !h.ext.alloc((size_t)n)) return TSM_E_CUDA;
+    if (k->ext) CU(cudaMemcpyAsync(h.ext.p, k->ext, (size_t)n, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(h.ext.p, 0, (size_t)n, st));
+    h.d.ext = h.ext.as<uint8_t>();
+    h.d.line_flag = h.line_flag.as<uint8_t>();
+  }
   k_mark_lines<<<(n * 32 + 255) / 256, 256, 0, st>>>(h.d, n);
   if (total) k_hash_lines<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h.d, n, total);
   CU(cudaGetLastError());
@@ -519,22 +527,23 @@ int side_lines(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
 }
 }  // namespace
 
-extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
-                              int64_t* added, int64_t* removed, void* stream) {
+extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
+                                     int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream) {
   if (!c || !olds || !news || !added || !removed || olds->n_files != news->n_files) return TSM_E_ARG;
   const int32_t n = olds->n_files;
   if (n == 0) return TSM_OK;
   for (const tsm_corpus* k : {olds, news}) {              // same layout rules as the scan (SPEC section 1)
     if (!k->arena || !k->off || !k->len) return TSM_E_ARG;
     for (int32_t i = 0; i < n; ++i)
-      if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1])
+      if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1] ||
+          (detail && k->ext && k->ext[i] > TSM_EXT_H))
         return TSM_E_LAYOUT;
   }
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   HostSide A, B;
-  int rc = side_lines(olds, A, st);
-  if (rc == TSM_OK) rc = side_lines(news, B, st);
+  int rc = side_lines(olds, A, st, detail != nullptr);
+  if (rc == TSM_OK) rc = side_lines(news, B, st, detail != nullptr);
   if (rc != TSM_OK) return rc;
   std::vector<unsigned long long> vbase((size_t)n + 1, 0);
   for (int32_t i = 0; i < n; ++i)
@@ -553,5 +562,45 @@ extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corp
   CU(cudaMemcpyAsync(removed, d_rem.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   c->launches = 7;
+  if (!detail) return TSM_OK;
+  // ---- hunks: second search with the rows of V kept; rows sized from the distances just computed,
+  //      pairs processed in batches of at most 2^28 trace ints (1 GiB)
+  d_v.~DevBuf(); d_v.p = nullptr;
+  DevBuf d_detail, d_tbase;
+  if (!d_detail.alloc(sizeof(tsm_diff_detail) * (size_t)n) || !d_tbase.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
+    return TSM_E_CUDA;
+  std::vector<unsigned long long> tbase((size_t)n + 1, 0);
+  const unsigned long long kBatch = 1ull << 28;
+  int32_t p0 = 0;
+  while (p0 < n) {
+    int32_t p1 = p0;
+    unsigned long long tot = 0;
+    while (p1 < n) {
+      const unsigned long long D = (unsigned long long)(added[p1] + removed[p1]);
+      const unsigned long long need = (D + 1) * (D + 2) / 2;
+      if (p1 > p0 && tot + need > kBatch) break;
+      tbase[(size_t)p1] = tot;
+      tot += need;
+      ++p1;
+    }
+    DevBuf d_trace;
+    if (!d_trace.alloc(sizeof(int32_t) * (size_t)tot)) return TSM_E_CAPACITY;   // one pair alone exceeds device memory
+    CU(cudaMemcpyAsync(d_tbase.as<unsigned long long>() + p0, tbase.data() + p0, sizeof(unsigned long long) * (size_t)(p1 - p0),
+                       cudaMemcpyHostToDevice, st));
+    k_myers_trace<<<((p1 - p0) * 32 + 127) / 128, 128, 0, st>>>(
+        A.d.line_hash, A.d.line_base, A.d.line_flag, B.d.line_hash, B.d.line_base, B.d.line_flag, p0, p1 - p0,
+        d_trace.as<int32_t>(), d_tbase.as<unsigned long long>(), d_detail.as<tsm_diff_detail>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    c->launches++;
+    p0 = p1;
+  }
+  CU(cudaMemcpyAsync(detail, d_detail.p, sizeof(tsm_diff_detail) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return TSM_OK;
+}
+
+extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
+                              int64_t* added, int64_t* removed, void* stream) {
+  return tsm_diff_pairs_detail(c, olds, news, added, removed, nullptr, stream);
 }

@@ -504,15 +504,24 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
   ck(tsm_create(&ctx, 0, 1 << 20, 16, 1, 0), "tsm_create");
   tsm_corpus ca{A.arena, A.off.data(), A.len.data(), A.ext.data(), A.grp.data(), (int32_t)A.count, 1};
   tsm_corpus cn{N.arena, N.off.data(), N.len.data(), N.ext.data(), N.grp.data(), (int32_t)N.count, 1};
+  // ext tags of both sides feed the assertion-line classification of the changed lines
+  for (size_t i = 0; i < pairs.size(); ++i) { A.ext[i] = (uint8_t)ext_tag(pairs[i].rel); N.ext[i] = A.ext[i]; }
   std::vector<int64_t> added(pairs.size()), removed(pairs.size());
-  ck(tsm_diff_pairs(ctx, &ca, &cn, added.data(), removed.data(), nullptr), "tsm_diff_pairs");
+  std::vector<tsm_diff_detail> det(pairs.size());
+  ck(tsm_diff_pairs_detail(ctx, &ca, &cn, added.data(), removed.data(), det.data(), nullptr), "tsm_diff_pairs_detail");
   tsm_destroy(ctx);
   std::ofstream os;
-  if (!out_path.empty()) { os.open(out_path, std::ios::binary); csv_row(os, {"fileName", "cloc", "added", "removed"}); }
+  if (!out_path.empty()) {
+    os.open(out_path, std::ios::binary);
+    csv_row(os, {"fileName", "cloc", "added", "removed", "hunks_add", "hunks_del", "hunks_mod", "added_assert", "removed_assert"});
+  }
   int64_t ta_ = 0, tr_ = 0;
   for (size_t i = 0; i < pairs.size(); ++i) {
     ta_ += added[i]; tr_ += removed[i];
-    if (os.is_open() && (added[i] || removed[i])) csv_row(os, {pairs[i].rel, std::to_string(added[i] + removed[i]), std::to_string(added[i]), std::to_string(removed[i])});
+    if (os.is_open() && (added[i] || removed[i]))
+      csv_row(os, {pairs[i].rel, std::to_string(added[i] + removed[i]), std::to_string(added[i]), std::to_string(removed[i]),
+                   std::to_string(det[i].hunks_add), std::to_string(det[i].hunks_del), std::to_string(det[i].hunks_mod),
+                   std::to_string(det[i].added_assert), std::to_string(det[i].removed_assert)});
   }
   printf("cloc,added,removed\r\n%lld,%lld,%lld\r\n", (long long)(ta_ + tr_), (long long)ta_, (long long)tr_);
   tsm_host_free(A.arena); tsm_host_free(N.arena);

@@ -25,11 +25,13 @@ ASSERT_EVENT = np.dtype([("file", "<u4"), ("line_off", "<u4"), ("stmt_off", "<u4
                          ("stmt_len", "<u2"), ("cat", "<u2"), ("ident_off", "<u4"),
                          ("ident_len", "<u2"), ("pad", "<u2"), ("stmt_hash", "<u8")])
 HEADER_EVENT = np.dtype([("file", "<u4"), ("line_off", "<u4"), ("line_len", "<u4"), ("kind", "<u4")])
+DIFF_DETAIL = np.dtype([("hunks_add", "<i8"), ("hunks_del", "<i8"), ("hunks_mod", "<i8"),
+                        ("added_assert", "<i8"), ("removed_assert", "<i8")])
 
 # every symbol include/tosemscan.h declares (tests check the library exports exactly these)
 SYMBOLS = ["tsm_abi_version", "tsm_strerror", "tsm_category_name", "tsm_create", "tsm_destroy", "tsm_scan",
            "tsm_upload", "tsm_scan_resident", "tsm_download", "tsm_device_counts", "tsm_last_launch_count", "tsm_last_kernel_ms", "tsm_kernel_ms_stats",
-           "tsm_diff_pairs", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
+           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
            "tsm_gen_fill", "tsm_gen_edit"]
 
 
@@ -89,6 +91,9 @@ def lib():
         L.tsm_kernel_ms_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double * 4), C.POINTER(C.c_int64), C.c_int]
         L.tsm_diff_pairs.restype = C.c_int
         L.tsm_diff_pairs.argtypes = [C.c_void_p, C.POINTER(_Corpus), C.POINTER(_Corpus), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tsm_diff_pairs_detail.restype = C.c_int
+        L.tsm_diff_pairs_detail.argtypes = [C.c_void_p, C.POINTER(_Corpus), C.POINTER(_Corpus), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
         L.tsm_reduce.restype = C.c_int
         L.tsm_reduce.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3
         L.tsm_host_alloc.restype = C.c_void_p
@@ -355,12 +360,19 @@ class Scanner:
             raise TsmError(rc, "tsm_reduce")
         return out, cpr
 
-    def diff_pairs(self, olds, news, stream=None):
+    def diff_pairs(self, olds, news, stream=None, detail=False):
+        """S8 churn per pair; with detail=True also the hunks of the canonical edit script (SPEC section 8)."""
         n = olds.n_files
         added = np.zeros(n, np.int64)
         removed = np.zeros(n, np.int64)
         a, b = olds.c_struct(), news.c_struct()
-        rc = lib().tsm_diff_pairs(self._ctx, C.byref(a), C.byref(b), _p(added), _p(removed), stream)
+        if not detail:
+            rc = lib().tsm_diff_pairs(self._ctx, C.byref(a), C.byref(b), _p(added), _p(removed), stream)
+            if rc:
+                raise TsmError(rc, "tsm_diff_pairs")
+            return added, removed
+        det = np.zeros(max(n, 1), DIFF_DETAIL)
+        rc = lib().tsm_diff_pairs_detail(self._ctx, C.byref(a), C.byref(b), _p(added), _p(removed), _p(det), stream)
         if rc:
-            raise TsmError(rc, "tsm_diff_pairs")
-        return added, removed
+            raise TsmError(rc, "tsm_diff_pairs_detail")
+        return added, removed, det[:n]
