@@ -167,8 +167,20 @@ def run_b200(args):
         raise SystemExit("no CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if n > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (no "NCCL version" banner)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep stdout to the one JSON line: NCCL prints its version banner there under NCCL_DEBUG=VERSION,
+        # so stdout is pointed at stderr while the communicator comes up
+        os.environ["NCCL_DEBUG"] = "WARN"
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     nf = args.files_per_gpu
     corpus = ts.gen_corpus(SEED_C2, nf, 0, FILE_SIZE, first_index=rank, index_stride=n, n_groups=N_GROUPS, pinned=True)
     sc = ts.Scanner(device=local, max_arena_bytes=int(corpus.off[-1]) + 4096, max_files=nf, max_groups=16)

@@ -185,3 +185,28 @@ def test_diff_trees(tmp_path):
     # cloc, added, removed, hunks_add, hunks_del, hunks_mod, added_assert, removed_assert
     assert got == {"a/x.py": ["3", "2", "1", "1", "1", "0", "1", "0"], "gone.c": ["2", "0", "2", "0", "1", "0", "0", "0"],
                    "fresh.c": ["1", "1", "0", "1", "0", "0", "0", "0"]}
+
+
+@pytest.mark.gpu
+def test_scan_two_gpus_matches_one(tmp_path):
+    """`--gpus 2`: batches dealt to two host threads / contexts, one ncclAllReduce of the count table."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import tosemscan as ts
+    root = tmp_path / "big"
+    c = ts.gen_corpus(21, 600, 1, n_groups=1, pinned=False)      # Zipf sizes; forces several batches? (no: one) -> two roots
+    for r in ("a_tests", "b_tests"):
+        os.makedirs(root / r)
+    for i in range(c.n_files):
+        ext = {1: "py", 2: "cc", 4: "java"}[int(c.ext[i])]
+        (root / ("a_tests" if i % 2 else "b_tests") / ("f%04d_test.%s" % (i, ext))).write_bytes(c.file_bytes(i))
+    outs = []
+    for g in (1, 2):
+        rows_p = str(tmp_path / ("rows%d.csv" % g))
+        out = subprocess.run([CLI, "scan", str(root / "a_tests"), str(root / "b_tests"), "--rows", rows_p, "--gpus", str(g)],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        outs.append((out.stdout, open(rows_p, "rb").read(), out.stderr.strip().split("\n")[-1]))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert outs[0][2].replace("on 1 GPU(s)", "") == outs[1][2].replace("on 2 GPU(s)", "")

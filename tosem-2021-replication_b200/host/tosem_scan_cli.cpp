@@ -22,7 +22,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <filesystem>
 #include <fstream>
 #include <map>
@@ -239,7 +241,18 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
   std::vector<ncclComm_t> comms(gpus);
   std::vector<int> devs(gpus);
   for (int i = 0; i < gpus; ++i) devs[i] = i;
-  if (gpus > 1 && ncclCommInitAll(comms.data(), gpus, devs.data()) != ncclSuccess) die("ncclCommInitAll failed");
+  if (gpus > 1) {
+    // stdout carries the aggregate CSV: whatever NCCL prints while initialising (its version banner
+    // under NCCL_DEBUG=VERSION) is routed to stderr
+    fflush(stdout);
+    const int saved = dup(1);
+    dup2(2, 1);
+    const ncclResult_t nr = ncclCommInitAll(comms.data(), gpus, devs.data());
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+    if (nr != ncclSuccess) die("ncclCommInitAll failed");
+  }
   const size_t table = (size_t)(n_groups + 1) * TSM_NUM_CATEGORIES + 4;
   std::vector<std::vector<int64_t>> totals(gpus, std::vector<int64_t>(table, 0));
   auto worker = [&](int g) {
