@@ -115,6 +115,15 @@ static void build_lut(uint32_t* lut) {                   // lut[0..256) = PY tab
   fill(lut + 256, cj, 7);
 }
 
+static void build_elut(uint32_t* lut) {                  // operator patterns of SPEC section 6 rule 2
+  struct Pat { const char* s; int first; };
+  static const Pat pats[] = {{" not ", 0}, {" in ", 5}, {" is not ", 9}, {"True", 17}, {"==", 21}, {"!=", 23},
+                             {"<=", 25}, {">=", 27}, {"<", 29}, {">", 30}};
+  memset(lut, 0, 256 * sizeof(uint32_t));
+  for (const Pat& p : pats)
+    for (int k = 0; p.s[k]; ++k) lut[(unsigned char)p.s[k]] |= 1u << (p.first + k);
+}
+
 extern "C" void tsm_destroy(tsm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -178,7 +187,10 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
     static const uint8_t slot[TSM_CAT_SLOTS] = TSM_CAT_SLOT_INIT;
     static const uint16_t offs[TSM_CAT_NAMED + 1] = TSM_CAT_OFF_INIT;
     static const char blob[] = TSM_CAT_BLOB_INIT;
+    uint32_t elut[256];
+    build_elut(elut);
     if (cudaMemcpyToSymbol(c_lut, lut, sizeof lut) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_elut, elut, sizeof elut) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_slot, slot, sizeof slot) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_off, offs, sizeof offs) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_blob, blob, TSM_CAT_BLOB_LEN + 1) != cudaSuccess ||
@@ -308,7 +320,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     }
     if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);
-    const size_t hist = sizeof(uint32_t) * (256 + (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0));
+    const size_t hist = sizeof(uint32_t) * (512 + (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0));
     k_classify<<<c->sms * 8, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
     cudaEventRecord(ev[4], st);                           // (slot of the former k_totals, now fused into k_classify)

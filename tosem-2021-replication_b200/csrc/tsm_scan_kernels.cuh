@@ -18,6 +18,7 @@
 namespace tsm {
 
 __constant__ uint32_t c_lut[512];                       // automaton byte classes: [0,256) PY, [256,512) C/C++/Java
+__constant__ uint32_t c_elut[256];                      // bare-assert operator automaton (k_classify)
 __constant__ uint8_t c_cat_slot[TSM_CAT_SLOTS];         // perfect hash slot -> category id
 __constant__ uint16_t c_cat_off[TSM_CAT_NAMED + 1];
 __constant__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
@@ -511,6 +512,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(Scan
 // stripped start, the right-stripped end and the last identifier L; everything else (gtest stem,
 // bare-assert operators, table lookup of L, statement hash) touches only the few bytes it needs.
 constexpr uint32_t CC_W = 1, CC_IDENT = 2, CC_STOP = 4;  // byte classes: blank, [A-Za-z0-9_], '(' or LF
+constexpr uint32_t E_FIRST = (1u << 0) | (1u << 5) | (1u << 9) | (1u << 17) | (1u << 21) | (1u << 23) | (1u << 25) |
+                             (1u << 27) | (1u << 29) | (1u << 30);
 
 struct FileBytes {                                       // 8-byte buffered reader over one file in HBM
   const unsigned long long* base; uint32_t cur_blk; unsigned long long w;
@@ -565,11 +568,13 @@ __device__ __forceinline__ int stem_lookup(FileBytes& rd, uint32_t s, uint32_t n
 __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
   extern __shared__ uint32_t csm[];                      // [256] byte classes, then [n_groups][K] histogram
   uint32_t* cls = csm;
-  uint32_t* hist = csm + 256;
+  uint32_t* elut = csm + 256;
+  uint32_t* hist = csm + 512;
   const bool use_smem = p.n_groups <= 16;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const uint32_t c = (uint32_t)i;
     cls[i] = (is_w(c) ? CC_W : 0u) | (is_ident(c) ? CC_IDENT : 0u) | ((c == '(' || c == '\n') ? CC_STOP : 0u);
+    elut[i] = c_elut[i];
   }
   if (use_smem) for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) hist[i] = 0;
   __syncthreads();
@@ -614,25 +619,18 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
       else if (a6 && tlen >= 8 && ((h >> 48) & 0xFF) == 0x20) {
         done = true;
         const uint32_t e0 = t0 + 7, en = tlen - 7;       // e = T[7:]
-        bool f_not = false, f_in = false, f_isnot = false, f_true = false;
-        bool eq = false, ne = false, le = false, ge = false, lt = false, gt = false;
+        // one Shift-And pass over e for the ten operator patterns of rule 2 (table built in tsm_api.cu):
+        //  " not " 0-4 | " in " 5-8 | " is not " 9-16 | "True" 17-20 | "==" 21-22 | "!=" 23-24 | "<=" 25-26 |
+        //  ">=" 27-28 | "<" 29 | ">" 30   (final bits 4, 8, 16, 20, 22, 24, 26, 28, 29, 30)
         const bool f_pre = en >= 4 && (uint32_t)rd.get8(e0) == 0x20746F6Eu;          // "not "
-        unsigned long long win = 0;                      // last 8 bytes of e, newest in the low byte
+        uint32_t D = 0, A = 0;
         for (uint32_t a = 0; a < en; ++a) {
-          const uint32_t c = rd.get(e0 + a);
-          win = (win << 8) | c;
-          const uint32_t w4 = (uint32_t)win, w2 = w4 & 0xFFFFu;
-          if ((win & 0xFFFFFFFFFFull) == 0x206E6F7420ull) f_not = true;              // " not "
-          if (w4 == 0x20696E20u) f_in = true;                                        // " in "
-          if (win == 0x206973206E6F7420ull) f_isnot = true;                          // " is not "
-          if (w4 == 0x54727565u) f_true = true;                                      // "True"
-          if (w2 == 0x3D3Du) eq = true;
-          if (w2 == 0x213Du) ne = true;
-          if (w2 == 0x3C3Du) le = true;
-          if (w2 == 0x3E3Du) ge = true;
-          if (c == '<') lt = true;
-          if (c == '>') gt = true;
+          D = ((D + D) | E_FIRST) & elut[rd.get(e0 + a)];
+          A |= D;
         }
+        const bool f_not = A & (1u << 4), f_in = A & (1u << 8), f_isnot = A & (1u << 16), f_true = A & (1u << 20);
+        const bool eq = A & (1u << 22), ne = A & (1u << 24), le = A & (1u << 26), ge = A & (1u << 28);
+        const bool lt = A & (1u << 29), gt = A & (1u << 30);
         if (f_pre) cat = 2;
         else if ((f_not && f_in) || f_isnot) cat = 4;
         else if (f_true) cat = 3;
