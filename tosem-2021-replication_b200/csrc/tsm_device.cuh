@@ -19,7 +19,9 @@ namespace tsm {
 constexpr uint32_t CH = 4096;                 // bytes of a file owned by one work unit
 constexpr uint32_t PRE = 16;                  // bytes loaded in front (is the chunk start a line start?)
 constexpr uint32_t EXT = 240;                 // bytes loaded behind (terminator of the last owned line)
-constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128
+constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128 = 32 * 136
+constexpr uint32_t STRIPE = BUF / 32;         // 136 = 8 * 17: stride of conflict-free per-lane LDS.64
+static_assert(STRIPE * 32 == BUF && STRIPE % 8 == 0 && (STRIPE / 8) % 2 == 1, "stripe geometry");
 #ifndef TSM_NL_CAP
 #define TSM_NL_CAP 1024
 #endif

@@ -358,35 +358,63 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   uint32_t next_start = PRE;
   Accum ac{0, 0, 0, 0, 0};
   uint32_t cnt = 0;
-  // ---- pass 1: newline table of the owned bytes, 512 B per step (16 B per lane, SWAR)
-  for (uint32_t tp = PRE; tp < lim; tp += 512) {
-    if (cnt + 512 > NL_CAP) {
-      drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-      cnt = 0;
-    }
-    const uint32_t pos = tp + lane * 16;
-    uint32_t bits = 0;
-    if (pos < lim) {
-      bits = nl16(*reinterpret_cast<const uint4*>(buf + pos));
-      const uint32_t valid = lim - pos;
-      if (valid < 16) bits &= (1u << valid) - 1u;
-    }
-    const uint32_t c = __popc(bits);
-    uint32_t incl = c;
+  // ---- pass 1: every lane takes one 136-byte stripe of the 4 352 staged bytes (17 conflict-free
+  //      LDS.64) and keeps the newline positions of its stripe as a 136-bit mask in registers;
+  //      one warp scan then orders them into the u16 line table, NL_CAP entries per window
+  const uint32_t pos0 = (uint32_t)lane * STRIPE;
+  uint32_t own[5], extm[5];                              // newlines at positions [PRE, lim) / [lim, lim2)
+  {
+    uint32_t m[5] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+    for (int i = 0; i < 17; ++i) {
+      const uint32_t pos = pos0 + 8u * (uint32_t)i;
+      uint32_t nl8 = 0;
+      if (pos < lim2) {
+        const uint2 w = *reinterpret_cast<const uint2*>(buf + pos);
+        nl8 = nl_word(w.x) | (nl_word(w.y) << 4);
+      }
+      m[i >> 2] |= nl8 << (8 * (i & 3));
     }
-    uint32_t idx = cnt + incl - c;
-    while (bits) {
-      const uint32_t b = __ffs(bits) - 1;
-      tab[idx++] = (uint16_t)(pos + b);
-      bits &= bits - 1;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const uint32_t b0 = pos0 + 32u * (uint32_t)j;      // position of bit 0 of this word
+      auto below = [&](uint32_t x) -> uint32_t {         // mask of the bits whose position is < x
+        return x <= b0 ? 0u : (x - b0 >= 32u ? 0xFFFFFFFFu : (1u << (x - b0)) - 1u);
+      };
+      own[j] = m[j] & below(lim) & ~below(PRE);
+      extm[j] = m[j] & below(lim2) & ~below(lim);
     }
-    cnt += __shfl_sync(0xffffffffu, incl, 31);
   }
-  __syncwarp();
+  uint32_t mine = __popc(own[0]) + __popc(own[1]) + __popc(own[2]) + __popc(own[3]) + __popc(own[4]);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t base_idx = incl - mine;
+  uint32_t ext_first = 0xFFFFu;                          // first newline behind the owned bytes
+#pragma unroll
+  for (int j = 4; j >= 0; --j)
+    if (extm[j]) ext_first = pos0 + 32u * (uint32_t)j + (uint32_t)(__ffs(extm[j]) - 1);
+  ext_first = __reduce_min_sync(0xffffffffu, ext_first);
+  for (uint32_t wstart = 0;; wstart += NL_CAP) {
+    cnt = min(total - wstart, NL_CAP);
+    uint32_t idx = base_idx;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      uint32_t b = own[j];
+      while (b) {
+        if (idx - wstart < cnt) tab[idx - wstart] = (uint16_t)(pos0 + 32u * (uint32_t)j + (uint32_t)(__ffs(b) - 1));
+        ++idx;
+        b &= b - 1;
+      }
+    }
+    __syncwarp();
+    if (wstart + cnt >= total) break;                    // last window: the tail line joins it below
+    drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+  }
   // ---- the last owned line: starts in the chunk, may end behind it
   const uint32_t tail_start = cnt ? ((uint32_t)tab[cnt - 1] & TAB_POS) + 1u : next_start;
   const bool owned = !(skip_first && cnt == 0);
@@ -394,23 +422,9 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   uint32_t tail_end = 0;
   if (owned && tail_start < lim) {
     if (ce == size) { tail_end = lim; have_tail = true; }              // unterminated last line of the file
-    else {
-      const uint32_t pos = lim + lane * 16;
-      uint32_t bits = 0;
-      if (pos < lim2) {
-        bits = nl16(*reinterpret_cast<const uint4*>(buf + pos));
-        const uint32_t valid = lim2 - pos;
-        if (valid < 16) bits &= (1u << valid) - 1u;
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, bits != 0);
-      if (m) {
-        const int src = __ffs(m) - 1;
-        const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
-        tail_end = lim + src * 16 + (__ffs(b) - 1);
-        have_tail = true;
-      } else if (le == size) { tail_end = lim2; have_tail = true; }    // file ends inside the staged bytes
-      else tail_long = true;
-    }
+    else if (ext_first != 0xFFFFu) { tail_end = ext_first; have_tail = true; }
+    else if (le == size) { tail_end = lim2; have_tail = true; }        // file ends inside the staged bytes
+    else tail_long = true;
   }
   if (have_tail) {
     if (cnt == NL_CAP) {
