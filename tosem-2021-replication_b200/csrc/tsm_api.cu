@@ -488,7 +488,8 @@ extern "C" void tsm_host_free(void* p) { if (p) cudaFreeHost(p); }
 namespace {
 struct DevBuf {                                           // cudaMalloc'd scratch, freed on scope exit
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { reset(); }
+  void reset() { if (p) cudaFree(p); p = nullptr; }
   bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -577,7 +578,7 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
   if (!detail) return TSM_OK;
   // ---- hunks: second search with the rows of V kept; rows sized from the distances just computed,
   //      pairs processed in batches of at most 2^28 trace ints (1 GiB)
-  d_v.~DevBuf(); d_v.p = nullptr;
+  d_v.reset();                                             // the first search's scratch is no longer needed
   DevBuf d_detail, d_tbase;
   if (!d_detail.alloc(sizeof(tsm_diff_detail) * (size_t)n) || !d_tbase.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
     return TSM_E_CUDA;
