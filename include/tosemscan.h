@@ -128,6 +128,14 @@ typedef struct tsm_diff_detail { int64_t hunks_add, hunks_del, hunks_mod, added_
 int tsm_diff_pairs_detail(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
                           int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream);
 
+/* Body statements (docs/SPEC.md section 10; Important-files/ML-Analysis-v4.xlsx!Apollo:R2-R26, golden G2): the
+ * kind of every line of every file - 0 blank, 1 first line of a statement, 2 continuation (lines
+ * are joined while the parentheses are open).  line_base[n_files+1] and *n_lines are always filled;
+ * line_end (file-relative end of each line) and line_kind hold `cap` lines: if cap < *n_lines the call
+ * returns TSM_E_CAPACITY so that the caller can size the arrays and call again. */
+int tsm_statements(tsm_ctx* ctx, const tsm_corpus* corpus, int64_t* line_base, uint32_t* line_end,
+                   uint8_t* line_kind, int64_t cap, int64_t* n_lines, void* stream);
+
 /* S10 reduce (RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/
  * tests_methods_v2.csv): out[f*n_repos+r] = distinct case ids with flags[row*n_flags+f] != 0 in
  * repo r; cases_per_repo[r] = distinct case ids of repo r. Host arrays; integer work on device. */

@@ -445,6 +445,37 @@ int orc_diff_pairs_detail(const uint8_t* arena_old, const int32_t* off_old, cons
   return 0;
 }
 
+/* ---------------------------------------------------------------- SPEC section 10 (body statements, golden G2)
+ * Important-files/ML-Analysis-v4.xlsx!Apollo:R2-R26 = src/apollo/v6.0.0/modules/common/math/aabox2d_test.cc:27-53. */
+int64_t orc_statements(const uint8_t* arena, const int32_t* off, const int32_t* len, int32_t n_files,
+                       int64_t* line_base, uint32_t* line_end, uint8_t* line_kind, int64_t cap) {
+  int64_t nl = 0;
+  for (int32_t f = 0; f < n_files; ++f) {
+    const uint8_t* p = arena + off[f];
+    const uint32_t size = (uint32_t)len[f];
+    if (line_base) line_base[f] = nl;
+    int64_t depth = 0;
+    uint32_t pos = 0;
+    while (pos < size) {
+      const uint8_t* nlp = memchr(p + pos, '\n', size - pos);
+      const uint32_t end = nlp ? (uint32_t)(nlp - p) : size;
+      uint32_t b, e;
+      strip(p + pos, end - pos, &b, &e);
+      uint8_t kind = 0;
+      if (e > b) {
+        kind = depth == 0 ? 1 : 2;
+        for (uint32_t i = pos; i < end; ++i) depth += (p[i] == '(') - (p[i] == ')');
+        if (depth < 0) depth = 0;
+      }
+      if (nl < cap) { if (line_end) line_end[nl] = end; if (line_kind) line_kind[nl] = kind; }
+      ++nl;
+      pos = end + 1;
+    }
+  }
+  if (line_base) line_base[n_files] = nl;
+  return nl;
+}
+
 /* ---------------------------------------------------------------- SPEC section 9 (S10)
  * RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/tests_methods_v2.csv. */
 int orc_reduce(const uint8_t* flags, const int32_t* repo, const int32_t* case_id, int32_t n_rows,

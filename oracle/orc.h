@@ -69,6 +69,12 @@ int orc_diff_pairs_detail(const uint8_t* arena_old, const int32_t* off_old, cons
                           const uint8_t* arena_new, const int32_t* off_new, const int32_t* len_new, const uint8_t* ext_new,
                           int32_t n_pairs, int64_t* added, int64_t* removed, orc_diff_detail* detail);
 
+/* SPEC section 10: per-line statement kinds (0 blank, 1 first line of a statement, 2 continuation).  Fills
+ * line_base[n_files+1]; line_end / line_kind hold up to cap lines (file-relative end offset of every line =
+ * position of its LF or the file size).  Returns the total number of lines, or -1. */
+int64_t orc_statements(const uint8_t* arena, const int32_t* off, const int32_t* len, int32_t n_files,
+                       int64_t* line_base, uint32_t* line_end, uint8_t* line_kind, int64_t cap);
+
 /* SPEC section 9: out[f*n_repos + r] = distinct cases with flag f set in repo r;
  * cases_per_repo[r] = distinct cases of repo r.  case ids < n_cases. */
 int orc_reduce(const uint8_t* flags, const int32_t* repo, const int32_t* case_id, int32_t n_rows,

@@ -65,6 +65,8 @@ def lib():
         L.orc_diff_pairs_detail.argtypes = [C.c_void_p] * 8 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_diff_script.restype = C.c_int64
         L.orc_diff_script.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_statements.restype = C.c_int64
+        L.orc_statements.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_reduce.restype = C.c_int
         L.orc_reduce.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
         _lib = L
@@ -209,6 +211,39 @@ def diff_script(a, b, fa=None, fb=None):
     D = lib().orc_diff_script(_p(a), a.size, _p(b), b.size, None if fa is None else _p(np.ascontiguousarray(fa, np.uint8)),
                               None if fb is None else _p(np.ascontiguousarray(fb, np.uint8)), _p(det))
     return int(D), det[0]
+
+
+def statements(arena, off, length):
+    """SPEC section 10: (line_base, line_end, line_kind) of a packed corpus."""
+    arena = np.ascontiguousarray(arena, np.uint8)
+    off = np.ascontiguousarray(off, np.int32)
+    length = np.ascontiguousarray(length, np.int32)
+    n = len(length)
+    base = np.zeros(n + 1, np.int64)
+    total = lib().orc_statements(_p(arena), _p(off), _p(length), n, _p(base), None, None, 0)
+    end = np.zeros(max(total, 1), np.uint32)
+    kind = np.zeros(max(total, 1), np.uint8)
+    lib().orc_statements(_p(arena), _p(off), _p(length), n, _p(base), _p(end), _p(kind), total)
+    return base, end[:total], kind[:total]
+
+
+def statement_texts(data: bytes):
+    """Statements of one file as the lost tool printed them: stripped lines joined with one blank."""
+    arena, off, length = pack([data])
+    base, end, kind = statements(arena, off, length)
+    out, cur, pos = [], None, 0
+    for e, k in zip(end.tolist(), kind.tolist()):
+        line = data[pos:e].strip(b" \t\r\x0b\x0c")
+        if k == 1:
+            if cur is not None:
+                out.append(b" ".join(cur))
+            cur = [line]
+        elif k == 2:
+            cur.append(line)
+        pos = e + 1
+    if cur is not None:
+        out.append(b" ".join(cur))
+    return out
 
 
 def reduce(flags, repo, case_id, n_repos, n_cases):

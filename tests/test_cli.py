@@ -210,3 +210,81 @@ def test_scan_two_gpus_matches_one(tmp_path):
         outs.append((out.stdout, open(rows_p, "rb").read(), out.stderr.strip().split("\n")[-1]))
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
     assert outs[0][2].replace("on 1 GPU(s)", "") == outs[1][2].replace("on 2 GPU(s)", "")
+
+
+def py_case_name(ext, line):
+    s = line.strip(b" \t\r\x0b\x0c").decode("latin-1")
+    if ext == 1:
+        import re
+        m = re.search(r"def\s*([A-Za-z0-9_]+)", s)
+        if m:
+            return m.group(1)
+    else:
+        if s.startswith(("TEST(", "TEST_F(", "TEST_P(")):
+            c, r = s.find(","), s.find(")")
+            if c >= 0 and (r < 0 or c < r):
+                return s[c + 1:(len(s) if r < 0 else r)].strip(" \t\r\x0b\x0c")
+        if s.startswith("BOOST_AUTO_TEST_CASE("):
+            r = s.find(")")
+            return "TEST_CASE(" + s[21:(len(s) if r < 0 else r)].strip(" \t\r\x0b\x0c") + ")"
+    return orc.method_string(ext, line).decode("latin-1")
+
+
+def expected_body(files):
+    """SPEC section 10 rows from the oracle's statement kinds and header rule."""
+    rows, index, cases = [], 0, 0
+    sel = sorted((r for r in files if "test" in r.lower() and r.rsplit(".", 1)[-1] in EXT), key=lambda r: r.split("/"))
+    for file_id, rel in enumerate(sel, start=1):
+        data, ext = files[rel], EXT[rel.rsplit(".", 1)[-1]]
+        arena, off, length = orc.pack([data])
+        _, end, kind = orc.statements(arena, off, length)
+        in_case, cur, listed, pos = False, None, False, 0
+
+        def flush():
+            nonlocal index, cur
+            if cur is not None and listed and cur.strip(b"{}(); \t\r\x0b\x0c"):
+                index += 1
+                rows.append([str(index), cur.decode("latin-1"), "", str(cases), str(file_id), ""])
+            cur = None
+        for e, k in zip(end.tolist(), kind.tolist()):
+            line = data[pos:e]
+            is_hdr = bool(orc.header_kind(ext, line))
+            if k == 1:
+                flush()
+                listed = in_case and not is_hdr
+                cur = b""
+            if is_hdr:
+                in_case = True
+                cases += 1
+                index += 1
+                rows.append([str(index), py_case_name(ext, line), "", str(cases), str(file_id), ""])
+            if k != 0 and cur is not None:
+                st = line.strip(b" \t\r\x0b\x0c")
+                cur = st if not cur else cur + b" " + st
+            pos = e + 1
+        flush()
+    return rows
+
+
+@pytest.mark.gpu
+def test_body_statements(tmp_path):
+    files = make_tree(str(tmp_path / "proj"))
+    extra = {"tests/math/aabox2d_test.cc": b"TEST(AABox2dTest, GetAllCorners) {\n  AABox2d box1({0, 0}, 4, 2);\n  EXPECT_EQ(\n      box1.DebugString(),\n"
+                                           b"      \"aabox2d ( center = vec2d ( x = 0 ) )\");\n}\n\nBOOST_AUTO_TEST_CASE(Query) {\n  BOOST_CHECK_EQUAL(1, 2);\n}\n"}
+    for rel, data in extra.items():
+        p = os.path.join(str(tmp_path / "proj"), rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        open(p, "wb").write(data)
+    files.update(extra)
+    outp = str(tmp_path / "body.csv")
+    out = subprocess.run([CLI, "body", str(tmp_path / "proj"), "--out", outp], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = read_csv(outp)
+    assert got[0] == ["Index", "text", "Category", "cases", "File_ID", "Component"]
+    want = expected_body(files)
+    assert got[1:] == want
+    texts = [r[1] for r in got[1:]]
+    # the reference's own example: ML-Analysis-v4.xlsx!Apollo:R2-R3 and the joined multi-line row :R14
+    assert "GetAllCorners" in texts and "AABox2d box1({0, 0}, 4, 2);" in texts
+    assert 'EXPECT_EQ( box1.DebugString(), "aabox2d ( center = vec2d ( x = 0 ) )");' in texts
+    assert "TEST_CASE(Query)" in texts and "}" not in texts

@@ -253,3 +253,20 @@ def test_diff_hunks_and_classification(scanner):
     assert int((det["hunks_add"] + det["hunks_del"] + det["hunks_mod"]).sum()) > 300
     o3, n3 = _pairs(8, 40, 15000, lam=60.0)
     check_diff_detail(scanner, o3, n3, [1] * 40)
+
+
+def test_statement_kinds(scanner):
+    """SPEC section 10 line kinds: GPU (SWAR parenthesis counts + clamped warp scan) against the oracle."""
+    corpora = []
+    files, exts, grps = cu.edge_corpus()
+    corpora.append(ts.pack(files, exts))
+    files, exts, grps = cu.fuzz_corpus(31, 300, 20000, long_lines=True)
+    corpora.append(ts.pack(files, exts))
+    corpora.append(ts.gen_corpus(0x7053454D0004, 800, 1, pinned=False))
+    corpora.append(ts.pack([b"(" * 100 + b"\n" + b"x\n" * 50 + b")" * 100 + b"\ny\n", b"\n" * 3000 + b"f(\n" * 40, b""], [2, 1, 1]))
+    for c in corpora:
+        gb, ge, gk = scanner.statements(c)
+        ob, oe, ok = orc.statements(c.arena, c.off, c.len)
+        assert np.array_equal(gb, ob) and np.array_equal(ge, oe)
+        bad = np.nonzero(gk != ok)[0]
+        assert bad.size == 0, (bad[:10], gk[bad[:10]], ok[bad[:10]])

@@ -201,6 +201,38 @@ def test_diff_script_distance_and_hunks():
     assert D == 3 and det["removed_assert"] == 2 and det["added_assert"] == 1 and det["hunks_mod"] == 1
 
 
+def test_statements_match_python_restatement():
+    """SPEC section 10 against the three-line Python rule the golden G2 recall was measured with."""
+    def py_statements(data):
+        out, cur, depth = [], [], 0
+        for line in data.split(b"\n"):
+            s = line.strip(b" \t\r\x0b\x0c")
+            if not s:
+                continue
+            cur.append(s)
+            depth += s.count(b"(") - s.count(b")")
+            if depth <= 0:
+                out.append(b" ".join(cur))
+                cur, depth = [], 0
+        if cur:
+            out.append(b" ".join(cur))
+        return out
+    files, _, _ = cu.edge_corpus()
+    rng = random.Random(4)
+    files = list(files) + [cu.fuzz_file(rng, rng.randrange(1, 3000), nl_rate=0.15) for _ in range(60)]
+    files += [b"EXPECT_EQ(\n    box1.DebugString(),\n    \"aabox2d ( x )\");\nfoo();\n", b"a(\n\n b(\n))\n)\n)\nx\n", b"((((\n"]
+    for f in files:
+        assert orc.statement_texts(f) == py_statements(f), f[:60]
+    assert orc.statement_texts(files[-3]) == [b'EXPECT_EQ( box1.DebugString(), "aabox2d ( x )");', b"foo();"]
+
+
+def test_g2_recall_ledger():
+    """Golden G2 (ML-Analysis-v4.xlsx body statements): recall recorded by tools/make_golden.py with the oracle."""
+    g2 = json.load(open(os.path.join(GOLD, "ledger.json")))["G2"]["subjects"]
+    assert g2["Apollo"]["rows_recalled"] == [5644, 5947] and g2["DeepSpeech2"]["rows_recalled"] == [1657, 1813]
+    assert g2["autokeras"]["rows_recalled"] == [351, 406] and g2["Nupic"]["rows_recalled"][0] >= 3934
+
+
 def test_scan_on_edge_corpus_matches_python_restatement():
     files, exts, grps = cu.edge_corpus()
     arena, off, ln = orc.pack(files)

@@ -311,6 +311,74 @@ def c1_summary(ledger, write=True):
     print("C1", summ["n_files"], summ["bytes"], summ["n_lines"], summ["n_assert"], summ["n_headers"])
 
 
+ANNOTATION = re.compile(r"^(compare|approximate|approximation|error-handling|value-range( nested)?|logical statement|else:|check)\s+", re.I)
+
+
+def ledger_g2(ledger):
+    """Golden G2 (body statements, SPEC section 10): recall of the verbatim sheet rows of ML-Analysis-v4.xlsx among the
+    oracle's statements of the FileID-mapped source file (SURVEY.md appendix A for the FileID -> path joins)."""
+    def idmap_xlsx(path, ci, cp):
+        sh = list(read_xlsx(path).values())[0]
+        out = {}
+        for _, row in sh[1:]:
+            if len(row) > max(ci, cp) and row[ci]:
+                try:
+                    out[int(float(row[ci]))] = row[cp]
+                except ValueError:
+                    pass
+        return out
+
+    def idmap_csv(path):
+        out = {}
+        for row in csv.DictReader(open(path, newline="", encoding="utf-8")):
+            try:
+                out[int(float(row["Id"]))] = row["FileName"]
+            except (ValueError, KeyError):
+                pass
+        return out
+    lab = os.path.join(REF, "selection/completed-labels")
+    subjects = {"Apollo": (idmap_xlsx(os.path.join(lab, "Release-Meta-Apollo_2.xlsx"), 0, 1), "src/apollo/v6.0.0"),
+                "DeepSpeech2": (idmap_xlsx(os.path.join(lab, "Release-Meta-Deepspeech_2.xlsx"), 1, 2), "src/DeepSpeech/v0.9.3"),
+                "Nupic": (idmap_xlsx(os.path.join(lab, "Release-Meta-nupic_22.xlsx"), 1, 2), "src/nupic/1.0.5"),
+                "autokeras": (idmap_csv(os.path.join(lab, "Release-Meta-autokeras.csv")), "src/autokeras/1.0.12")}
+    v4 = read_xlsx(os.path.join(REF, "Important-files/ML-Analysis-v4.xlsx"), only=set(subjects))
+
+    def norm(t):
+        return re.sub(r"\s+", " ", t).strip()
+    out = {}
+    for name, (fid, root) in subjects.items():
+        by = collections.defaultdict(list)
+        for _, r in v4[name][1:]:
+            if len(r) >= 5 and r[4]:
+                try:
+                    by[int(float(r[4]))].append(r[1])
+                except ValueError:
+                    pass
+        hit = tot = files = 0
+        for f, texts in by.items():
+            p = fid.get(f)
+            if not p or not os.path.exists(os.path.join(REF, root, p)):
+                continue
+            files += 1
+            data = open(os.path.join(REF, root, p), "rb").read()
+            text = data.decode("utf-8", "replace")
+            have = {norm(x.decode("utf-8", "replace")) for x in orc.statement_texts(data)}
+            for t in texts:
+                t = norm(t)
+                if not t:
+                    continue
+                tot += 1
+                if t in have or norm(ANNOTATION.sub("", t)) in have:
+                    hit += 1
+                elif re.match(r"^[A-Za-z_0-9(), .:]+$", t) and len(t) < 80 and (t in text or t.split("(")[0] in text):
+                    hit += 1                                   # case-name rows (GetAllCorners, TEST_CASE(Query), testNoShift)
+        out[name] = {"files_in_bundle": files, "rows_recalled": [hit, tot]}
+        print("G2", name, hit, tot)
+    ledger["G2"] = {"source": "Important-files/ML-Analysis-v4.xlsx!{Apollo,DeepSpeech2,Nupic,autokeras} vs the bundled sources",
+                    "rule": "docs/SPEC.md section 10 (lines joined while the parentheses are open)", "subjects": out,
+                    "note": "recall of verbatim rows; the residue is labeller paraphrase and version skew (SURVEY.md section 8c)"}
+
+
 def main():
     if "--check-c1" in sys.argv:   # recompute config C1 and compare with the committed summary
         want = json.load(open(os.path.join(OUT, "c1_summary.json")))
@@ -326,6 +394,7 @@ def main():
     ledger_headers(v1, ledger)
     ledger_g1(v1, ledger)
     golden_g3(ledger)
+    ledger_g2(ledger)
     c1_summary(ledger)
     json.dump(ledger, open(os.path.join(OUT, "ledger.json"), "w"), indent=1)
 

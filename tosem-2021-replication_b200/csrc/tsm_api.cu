@@ -11,6 +11,7 @@
 #include "tsm_scan_kernels.cuh"
 #include "tsm_reduce_kernels.cuh"
 #include "tsm_diff_kernels.cuh"
+#include "tsm_stmt_kernels.cuh"
 
 using namespace tsm;
 
@@ -616,4 +617,39 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
 extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
                               int64_t* added, int64_t* removed, void* stream) {
   return tsm_diff_pairs_detail(c, olds, news, added, removed, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------- SPEC section 10 statements
+extern "C" int tsm_statements(tsm_ctx* c, const tsm_corpus* k, int64_t* line_base, uint32_t* line_end,
+                              uint8_t* line_kind, int64_t cap, int64_t* n_lines, void* stream) {
+  if (!c || !k || !line_base || !n_lines || cap < 0 || k->n_files < 0) return TSM_E_ARG;
+  const int32_t n = k->n_files;
+  *n_lines = 0;
+  line_base[0] = 0;
+  if (n == 0) return TSM_OK;
+  if (!k->arena || !k->off || !k->len) return TSM_E_ARG;
+  for (int32_t i = 0; i < n; ++i)
+    if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1])
+      return TSM_E_LAYOUT;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  HostSide S;
+  int rc = side_lines(k, S, st, false);                   // newline count, ordered line ends (and hashes)
+  if (rc != TSM_OK) return rc;
+  const unsigned long long total = S.base[(size_t)n];
+  for (int32_t i = 0; i <= n; ++i) line_base[i] = (int64_t)S.base[(size_t)i];
+  *n_lines = (int64_t)total;
+  if ((unsigned long long)cap < total) return TSM_E_CAPACITY;   // line_base / n_lines are filled: allocate and call again
+  if (total == 0) return TSM_OK;
+  if (!line_end || !line_kind) return TSM_E_ARG;
+  DevBuf d_delta, d_kind;
+  if (!d_delta.alloc(sizeof(int32_t) * (size_t)total) || !d_kind.alloc((size_t)total)) return TSM_E_CUDA;
+  k_line_parens<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S.d, n, total, d_delta.as<int32_t>(), d_kind.as<uint8_t>());
+  k_stmt_kinds<<<(n * 32 + 127) / 128, 128, 0, st>>>(S.d, n, d_delta.as<int32_t>(), d_kind.as<uint8_t>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(line_end, S.d.line_end, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(line_kind, d_kind.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  c->launches = 5;
+  return TSM_OK;
 }

@@ -18,7 +18,9 @@
 //   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files]
 //   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
+//   tosem-scan body   <project-root>... [--out F]
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -486,6 +488,110 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------- body statements (SPEC section 10)
+// Case name of a header line: PY - identifier after `def`; C family - 2nd macro argument of TEST / TEST_F /
+// TEST_P, `TEST_CASE(X)` for BOOST_AUTO_TEST_CASE(X); otherwise the SPEC section 5 method string.
+static std::string case_name(int ext, const uint8_t* line, uint32_t len) {
+  uint32_t b = 0, e = len;
+  while (b < e && is_w(line[b])) ++b;
+  while (e > b && is_w(line[e - 1])) --e;
+  const std::string s((const char*)line + b, e - b);
+  if (ext == TSM_EXT_PY) {
+    const size_t d = s.find("def");
+    if (d != std::string::npos) {
+      size_t i = d + 3;
+      while (i < s.size() && is_w((unsigned char)s[i])) ++i;
+      size_t j = i;
+      while (j < s.size() && (isalnum((unsigned char)s[j]) || s[j] == '_')) ++j;
+      if (j > i) return s.substr(i, j - i);
+    }
+  } else {
+    auto trim = [](std::string t) { size_t a = 0, z = t.size(); while (a < z && is_w((unsigned char)t[a])) ++a; while (z > a && is_w((unsigned char)t[z - 1])) --z; return t.substr(a, z - a); };
+    if (s.rfind("TEST(", 0) == 0 || s.rfind("TEST_F(", 0) == 0 || s.rfind("TEST_P(", 0) == 0) {
+      const size_t c = s.find(','), r = s.find(')');
+      if (c != std::string::npos && (r == std::string::npos || c < r)) return trim(s.substr(c + 1, (r == std::string::npos ? s.size() : r) - c - 1));
+    }
+    if (s.rfind("BOOST_AUTO_TEST_CASE(", 0) == 0) {
+      const size_t r = s.find(')');
+      return "TEST_CASE(" + trim(s.substr(21, (r == std::string::npos ? s.size() : r) - 21)) + ")";
+    }
+  }
+  return method_string(ext, line, len);
+}
+
+static int cmd_body(const std::vector<std::string>& roots, const std::string& out_path) {
+  std::vector<FileEntry> files;
+  for (size_t g = 0; g < roots.size(); ++g) walk(roots[g], (int)g, false, files);
+  fprintf(stderr, "tosem-scan: %zu files selected under %zu root(s)\n", files.size(), roots.size());
+  std::ofstream os;
+  if (!out_path.empty()) { os.open(out_path, std::ios::binary); csv_row(os, {"Index", "text", "Category", "cases", "File_ID", "Component"}); }
+  int64_t index = 0, cases = 0, file_id = 0, n_stmt = 0;
+  size_t first = 0;
+  while (first < files.size()) {
+    Batch B; B.first = first;
+    int64_t cur = 0;
+    while (first < files.size() && (B.count == 0 || (cur + files[first].size < (1ll << 29) && B.count < (1u << 19)))) {
+      cur += (files[first].size + 127) / 128 * 128; ++B.count; ++first;
+    }
+    load_batch(files, B);
+    tsm_ctx* ctx = nullptr;
+    ck(tsm_create(&ctx, 0, B.bytes + 4096, (int32_t)B.count, (int32_t)std::max<size_t>(roots.size(), 1), 0), "tsm_create");
+    tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, (int32_t)std::max<size_t>(roots.size(), 1)};
+    const int64_t cap = std::max<int64_t>(B.bytes / 8 + 1024, 1024);
+    std::vector<tsm_header_event> hev((size_t)cap);
+    tsm_result r{};
+    r.hev = hev.data(); r.hev_cap = cap;
+    ck(tsm_scan(ctx, &c, &r, TSM_SCAN_HEADER_EVENTS, nullptr), "tsm_scan");
+    hev.resize((size_t)r.n_hev);
+    std::vector<int64_t> base(B.count + 1);
+    int64_t nl = 0;
+    int rc = tsm_statements(ctx, &c, base.data(), nullptr, nullptr, 0, &nl, nullptr);
+    if (rc != TSM_OK && rc != TSM_E_CAPACITY) ck(rc, "tsm_statements");
+    std::vector<uint32_t> lend((size_t)std::max<int64_t>(nl, 1));
+    std::vector<uint8_t> kind((size_t)std::max<int64_t>(nl, 1));
+    ck(tsm_statements(ctx, &c, base.data(), lend.data(), kind.data(), nl, &nl, nullptr), "tsm_statements");
+    tsm_destroy(ctx);
+    size_t hi = 0;
+    for (size_t i = 0; i < B.count; ++i) {
+      const FileEntry& f = files[B.first + i];
+      const uint8_t* p = B.arena + B.off[i];
+      ++file_id;
+      bool in_case = false;
+      std::string cur_stmt; bool have = false, listed = false;
+      auto flush = [&]() {
+        if (have && listed && cur_stmt.find_first_not_of("{}(); \t\r\x0b\x0c") != std::string::npos) {
+          ++n_stmt;
+          if (os.is_open()) csv_row(os, {std::to_string(++index), cur_stmt, "", std::to_string(cases), std::to_string(file_id), ""});
+        }
+        have = false; cur_stmt.clear();
+      };
+      uint32_t pos = 0;
+      for (int64_t l = base[i]; l < base[i + 1]; ++l) {
+        const uint32_t e = lend[(size_t)l];
+        const bool is_hdr = hi < hev.size() && hev[hi].file == i && hev[hi].line_off == pos;
+        if (kind[(size_t)l] == 1) { flush(); listed = in_case && !is_hdr; have = true; }
+        if (is_hdr) {                                       // a new test case starts here
+          ++hi; in_case = true; ++cases;
+          if (os.is_open()) csv_row(os, {std::to_string(++index), case_name(f.ext, p + pos, e - pos), "", std::to_string(cases), std::to_string(file_id), ""});
+        }
+        if (kind[(size_t)l] != 0 && have) {
+          uint32_t b = pos, z = e;
+          while (b < z && is_w(p[b])) ++b;
+          while (z > b && is_w(p[z - 1])) --z;
+          if (!cur_stmt.empty()) cur_stmt += ' ';
+          cur_stmt.append((const char*)p + b, z - b);
+        }
+        pos = e + 1;
+      }
+      flush();
+      while (hi < hev.size() && hev[hi].file == i) ++hi;
+    }
+    tsm_host_free(B.arena);
+  }
+  printf("files,cases,statements\r\n%lld,%lld,%lld\r\n", (long long)file_id, (long long)cases, (long long)n_stmt);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------- diff (S8)
 static int cmd_diff(const std::string& old_root, const std::string& new_root, const std::string& out_path) {
   std::vector<FileEntry> a, b;
@@ -546,6 +652,7 @@ static void usage() {
           "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files]\n"
           "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
+          "       tosem-scan body   <project-root>... [--out F]\n"
           "Scans run on the GPU through libtosemscan.so (sm_100a); there is no CPU fallback.\n");
 }
 
@@ -563,6 +670,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files); }
   if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"]); }
+  if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
   if (cmd == "diff") { if (pos.size() != 2) die("diff needs <old-root> <new-root>"); return cmd_diff(pos[0], pos[1], opt["--out"]); }
   usage();
   return 2;

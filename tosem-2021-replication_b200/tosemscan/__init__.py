@@ -31,7 +31,7 @@ DIFF_DETAIL = np.dtype([("hunks_add", "<i8"), ("hunks_del", "<i8"), ("hunks_mod"
 # every symbol include/tosemscan.h declares (tests check the library exports exactly these)
 SYMBOLS = ["tsm_abi_version", "tsm_strerror", "tsm_category_name", "tsm_create", "tsm_destroy", "tsm_scan",
            "tsm_upload", "tsm_scan_resident", "tsm_download", "tsm_device_counts", "tsm_last_launch_count", "tsm_last_kernel_ms", "tsm_kernel_ms_stats",
-           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
+           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_statements", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
            "tsm_gen_fill", "tsm_gen_edit"]
 
 
@@ -94,6 +94,9 @@ def lib():
         L.tsm_diff_pairs_detail.restype = C.c_int
         L.tsm_diff_pairs_detail.argtypes = [C.c_void_p, C.POINTER(_Corpus), C.POINTER(_Corpus), C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+        L.tsm_statements.restype = C.c_int
+        L.tsm_statements.argtypes = [C.c_void_p, C.POINTER(_Corpus), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.POINTER(C.c_int64), C.c_void_p]
         L.tsm_reduce.restype = C.c_int
         L.tsm_reduce.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3
         L.tsm_host_alloc.restype = C.c_void_p
@@ -359,6 +362,21 @@ class Scanner:
         if rc:
             raise TsmError(rc, "tsm_reduce")
         return out, cpr
+
+    def statements(self, corpus, stream=None):
+        """SPEC section 10: (line_base[n+1], line_end[lines], line_kind[lines]); kind 0 blank, 1 statement start, 2 continuation."""
+        cs = corpus.c_struct()
+        base = np.zeros(corpus.n_files + 1, np.int64)
+        n = C.c_int64()
+        rc = lib().tsm_statements(self._ctx, C.byref(cs), _p(base), None, None, 0, C.byref(n), stream)
+        if rc not in (0, -3):
+            raise TsmError(rc, "tsm_statements")
+        end = np.zeros(max(n.value, 1), np.uint32)
+        kind = np.zeros(max(n.value, 1), np.uint8)
+        rc = lib().tsm_statements(self._ctx, C.byref(cs), _p(base), _p(end), _p(kind), n.value, C.byref(n), stream)
+        if rc:
+            raise TsmError(rc, "tsm_statements")
+        return base, end[:n.value], kind[:n.value]
 
     def diff_pairs(self, olds, news, stream=None, detail=False):
         """S8 churn per pair; with detail=True also the hunks of the canonical edit script (SPEC section 8)."""
