@@ -288,3 +288,35 @@ def test_body_statements(tmp_path):
     assert "GetAllCorners" in texts and "AABox2d box1({0, 0}, 4, 2);" in texts
     assert 'EXPECT_EQ( box1.DebugString(), "aabox2d ( center = vec2d ( x = 0 ) )");' in texts
     assert "TEST_CASE(Query)" in texts and "}" not in texts
+
+
+@pytest.mark.gpu
+def test_release_presence_matrix(tmp_path):
+    """S7 (SPEC section 11): identities across snapshots by path, by content (pure move), by unique base name."""
+    a = b"def test_a(self):\n    self.assertEqual(1, 2)\n    self.assertEqual(3, 4)\n    assert x\n"
+    b = b"TEST(S, T) {\n  EXPECT_EQ(1, 2);\n}\n"
+    snaps = {
+        "v1": {"tests/test_image_supervised.py": a, "tests/test_search.py": b"def test_s():\n    assert y\n", "unit_test/x_test.cc": b},
+        "v2": {"tests/image/test_image_supervised.py": a, "tests/test_search.py": b"def test_s():\n    assert y\n    assert z\n", "unit_test/x_test.cc": b},
+        "v3": {"tests/image/test_image_supervised.py": a + b"    assert more\n", "lib/tests/x_test.cc": b + b"// moved and edited\n",
+               "tests/test_new.py": b"assert True\n"},
+    }
+    args = []
+    for tag, files in snaps.items():
+        for rel, data in files.items():
+            p = tmp_path / tag / rel
+            os.makedirs(p.parent, exist_ok=True)
+            p.write_bytes(data)
+        args.append("%s=%s" % (tmp_path / tag, tag))
+    outp = str(tmp_path / "release_meta.csv")
+    out = subprocess.run([CLI, "releases"] + args + ["--out", outp], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = read_csv(outp)
+    assert got[0] == ["Id", "FileName", "v1", "v2", "v3", "total assert", "assertion"]
+    assert got[1:] == [
+        ["1", "tests/test_image_supervised.py", "tests/test_image_supervised.py", "tests/image/test_image_supervised.py",
+         "tests/image/test_image_supervised.py", "4", "2:assertEqual, 2:assertTrue"],
+        ["2", "tests/test_search.py", "tests/test_search.py", "tests/test_search.py", "", "2", "2:assertTrue"],
+        ["3", "unit_test/x_test.cc", "unit_test/x_test.cc", "unit_test/x_test.cc", "lib/tests/x_test.cc", "1", "1:assertEqual"],
+        ["4", "tests/test_new.py", "", "", "tests/test_new.py", "1", "1:assertTrue"],
+    ]

@@ -19,6 +19,7 @@
 //   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
+//   tosem-scan releases <snapshot-root>=<tag>... [--out F]
 #include <algorithm>
 #include <cctype>
 #include <cmath>
@@ -592,6 +593,108 @@ static int cmd_body(const std::vector<std::string>& roots, const std::string& ou
   return 0;
 }
 
+// ---------------------------------------------------------------------------------- release presence matrix (S7, SPEC section 11)
+struct SnapFile { std::string rel; uint64_t digest; int64_t size; uint32_t n_assert; std::string hist; };
+
+// Scan one snapshot: per selected test file its digest, assertion total and "n:category, ..." histogram.
+static std::vector<SnapFile> scan_snapshot(const std::string& root) {
+  std::vector<FileEntry> files;
+  walk(root, 0, false, files);
+  std::vector<SnapFile> out;
+  size_t first = 0;
+  while (first < files.size()) {
+    Batch B; B.first = first;
+    int64_t cur = 0;
+    while (first < files.size() && (B.count == 0 || (cur + files[first].size < (1ll << 29) && B.count < (1u << 19)))) {
+      cur += (files[first].size + 127) / 128 * 128; ++B.count; ++first;
+    }
+    load_batch(files, B);
+    tsm_ctx* ctx = nullptr;
+    ck(tsm_create(&ctx, 0, B.bytes + 4096, (int32_t)B.count, 1, 0), "tsm_create");
+    tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, 1};
+    const int64_t cap = std::max<int64_t>(B.bytes / 8 + 1024, 1024);
+    std::vector<tsm_file_stat> stats(B.count);
+    std::vector<tsm_assert_event> aev((size_t)cap);
+    tsm_result r{};
+    r.stats = stats.data(); r.aev = aev.data(); r.aev_cap = cap;
+    ck(tsm_scan(ctx, &c, &r, TSM_SCAN_ASSERT_EVENTS, nullptr), "tsm_scan");
+    tsm_destroy(ctx);
+    size_t ai = 0;
+    for (size_t i = 0; i < B.count; ++i) {
+      const uint8_t* base = B.arena + B.off[i];
+      std::map<std::string, int64_t> hist; std::vector<std::string> order;
+      for (; ai < (size_t)r.n_aev && aev[ai].file == i; ++ai) {
+        const tsm_assert_event& ev = aev[ai];
+        const std::string cat = ev.cat == 127 ? std::string((const char*)base + ev.ident_off, ev.ident_len) : std::string(tsm_category_name(ev.cat));
+        if (!hist.count(cat)) order.push_back(cat);
+        hist[cat]++;
+      }
+      std::stable_sort(order.begin(), order.end(), [&](const std::string& x, const std::string& y) { return hist[x] > hist[y]; });
+      std::string a;
+      for (const std::string& k : order) { if (!a.empty()) a += ", "; a += std::to_string(hist[k]) + ":" + k; }
+      out.push_back({files[B.first + i].rel, stats[i].digest, files[B.first + i].size, stats[i].n_assert, a});
+    }
+    tsm_host_free(B.arena);
+  }
+  return out;
+}
+
+static int cmd_releases(const std::vector<std::string>& specs, const std::string& out_path) {
+  struct Identity { std::string name; std::vector<std::string> path; uint64_t digest; int64_t size; uint32_t n_assert; std::string hist; std::string cur; };
+  std::vector<std::string> tags;
+  std::vector<Identity> ids;
+  for (size_t t = 0; t < specs.size(); ++t) {
+    const size_t eq = specs[t].rfind('=');
+    if (eq == std::string::npos) die("releases arguments are <snapshot-root>=<tag>");
+    tags.push_back(specs[t].substr(eq + 1));
+    const std::vector<SnapFile> snap = scan_snapshot(specs[t].substr(0, eq));
+    std::vector<char> id_taken(ids.size(), 0), f_done(snap.size(), 0);
+    auto base_of = [](const std::string& p) { const size_t s = p.rfind('/'); return s == std::string::npos ? p : p.substr(s + 1); };
+    auto bind = [&](size_t fi, size_t id) {
+      const SnapFile& f = snap[fi];
+      ids[id].path[t] = f.rel; ids[id].cur = f.rel; ids[id].digest = f.digest; ids[id].size = f.size;
+      ids[id].n_assert = f.n_assert; ids[id].hist = f.hist; id_taken[id] = 1; f_done[fi] = 1;
+    };
+    for (Identity& I : ids) I.path.resize(t + 1);
+    for (size_t fi = 0; fi < snap.size(); ++fi)                       // (1) same relative path
+      for (size_t id = 0; id < id_taken.size(); ++id)
+        if (!id_taken[id] && ids[id].cur == snap[fi].rel) { bind(fi, id); break; }
+    for (size_t fi = 0; fi < snap.size(); ++fi)                       // (2) same content: a pure move
+      if (!f_done[fi])
+        for (size_t id = 0; id < id_taken.size(); ++id)
+          if (!id_taken[id] && ids[id].size == snap[fi].size && ids[id].digest == snap[fi].digest) { bind(fi, id); break; }
+    for (size_t fi = 0; fi < snap.size(); ++fi) {                     // (3) same base name, unambiguous
+      if (f_done[fi]) continue;
+      int hit = -1, n = 0;
+      for (size_t id = 0; id < id_taken.size(); ++id)
+        if (!id_taken[id] && base_of(ids[id].cur) == base_of(snap[fi].rel)) { hit = (int)id; ++n; }
+      if (n == 1) bind(fi, (size_t)hit);
+    }
+    for (size_t fi = 0; fi < snap.size(); ++fi)                       // new identities, in walk order
+      if (!f_done[fi]) {
+        Identity I; I.name = snap[fi].rel; I.path.assign(t + 1, "");
+        ids.push_back(I); id_taken.push_back(0);
+        bind(fi, ids.size() - 1);
+      }
+  }
+  std::ofstream os;
+  if (!out_path.empty()) {
+    os.open(out_path, std::ios::binary);
+    std::vector<std::string> h = {"Id", "FileName"};
+    for (const std::string& g : tags) h.push_back(g);
+    h.push_back("total assert"); h.push_back("assertion");
+    csv_row(os, h);
+    for (size_t i = 0; i < ids.size(); ++i) {
+      std::vector<std::string> row = {std::to_string(i + 1), ids[i].name};
+      for (size_t t = 0; t < tags.size(); ++t) row.push_back(t < ids[i].path.size() ? ids[i].path[t] : "");
+      row.push_back(std::to_string(ids[i].n_assert)); row.push_back(ids[i].hist);
+      csv_row(os, row);
+    }
+  }
+  printf("identities,snapshots\r\n%zu,%zu\r\n", ids.size(), tags.size());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------- diff (S8)
 static int cmd_diff(const std::string& old_root, const std::string& new_root, const std::string& out_path) {
   std::vector<FileEntry> a, b;
@@ -653,6 +756,7 @@ static void usage() {
           "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
+          "       tosem-scan releases <snapshot-root>=<tag>... [--out F]\n"
           "Scans run on the GPU through libtosemscan.so (sm_100a); there is no CPU fallback.\n");
 }
 
@@ -670,6 +774,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files); }
   if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"]); }
+  if (cmd == "releases") { if (pos.empty()) die("releases needs <root>=<tag>..."); return cmd_releases(pos, opt["--out"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
   if (cmd == "diff") { if (pos.size() != 2) die("diff needs <old-root> <new-root>"); return cmd_diff(pos[0], pos[1], opt["--out"]); }
   usage();
