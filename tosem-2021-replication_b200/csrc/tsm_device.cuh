@@ -23,28 +23,40 @@ constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128 = 32 * 136
 constexpr uint32_t STRIPE = BUF / 32;         // 136 = 8 * 17: stride of conflict-free per-lane LDS.64
 static_assert(STRIPE * 32 == BUF && STRIPE % 8 == 0 && (STRIPE / 8) % 2 == 1, "stripe geometry");
 #ifndef TSM_NL_CAP
-#define TSM_NL_CAP 1024
+#define TSM_NL_CAP 384
 #endif
-#ifndef TSM_WALK_BATCH
-#define TSM_WALK_BATCH 256
-#endif
-#ifndef TSM_BLOCKS_PER_ITER
-#define TSM_BLOCKS_PER_ITER 2
+#ifndef TSM_RW_SHIFT
+#define TSM_RW_SHIFT 2
 #endif
 #ifndef TSM_SCAN_WARPS
-#define TSM_SCAN_WARPS 4
+#define TSM_SCAN_WARPS 8
 #endif
 #ifndef TSM_SCAN_CTAS
-#define TSM_SCAN_CTAS 5
+#define TSM_SCAN_CTAS 3
 #endif
-constexpr uint32_t NL_CAP = TSM_NL_CAP;       // line-table entries per drain (>= 512 + 1)
-constexpr uint32_t WALK_BATCH = TSM_WALK_BATCH;   // lines walked (pass 2) before their balanced finalise (pass 3)
-constexpr uint32_t TAB_BYTES = (NL_CAP + 64) * 2;   // u16 per line: newline position (13 bits) | LF_* flags << 13
+constexpr uint32_t NL_CAP = TSM_NL_CAP;       // line-table entries per window
+constexpr uint32_t TAB_BYTES = (NL_CAP + 8) * 2;    // u16 per line: newline position (13 bits) | LF_* flags << 13 (NL_CAP + 1 used)
 constexpr uint32_t TAB_POS = 0x1FFFu;                // BUF < 8192
-constexpr uint32_t RAW_BYTES = WALK_BATCH * 12;     // per line: u64 Horner accumulator + u32 automaton OR
-constexpr uint32_t WARP_SMEM = ((BUF + TAB_BYTES + RAW_BYTES + 16 + 127) / 128) * 128;
+constexpr uint32_t FLAG_CAP = NL_CAP + 8;            // u32 per line of the window: OR of the automaton states (pass 2 -> pass 3)
+#ifndef TSM_Q_CAP
+#define TSM_Q_CAP 64
+#endif
+constexpr uint32_t Q_CAP = TSM_Q_CAP;                       // words whose matches need a byte-exact line (pass 2b)
+// per-warp shared memory of k_scan, offsets from the warp's base
+constexpr uint32_t OFF_TAB = BUF;                    // u16[NL_CAP + 8]   line table
+constexpr uint32_t RW_SHIFT = TSM_RW_SHIFT, RW_STRIDE = 1u << RW_SHIFT;   // hash-prefix checkpoint every RW_STRIDE words
+constexpr uint32_t RW_PER_STRIPE = 16u >> RW_SHIFT;  // (the 17th word of a stripe needs none: the next stripe starts from its base)
+constexpr uint32_t OFF_RW = OFF_TAB + TAB_BYTES;     // u64[32 * RW_PER_STRIPE]  running hash prefix behind the checkpointed words
+constexpr uint32_t OFF_FLAGS = OFF_RW + 32 * RW_PER_STRIPE * 8;         // u32[FLAG_CAP]     (pass 3 compacts the candidate list into it, u16 each)
+constexpr uint32_t OFF_MSK = OFF_FLAGS + FLAG_CAP * 4;   // u32[5][32]    newline bits of every stripe
+constexpr uint32_t OFF_BASE = OFF_MSK + 5 * 32 * 4;  // u64[33]           hash prefix at every stripe start (+ total)
+constexpr uint32_t OFF_Q = OFF_BASE + 34 * 8;        // u32[Q_CAP]
+constexpr uint32_t OFF_CTL = OFF_Q + Q_CAP * 4;      // u32 queue length, pad, u64 mbarrier
+constexpr uint32_t WARP_SMEM = ((OFF_CTL + 16 + 127) / 128) * 128;
+static_assert(NL_CAP % 4 == 0 && NL_CAP >= 64, "window size");
 static_assert(BUF <= TAB_POS + 1, "line-table positions must fit 13 bits");
-constexpr uint32_t LUT_BYTES = 3072;          // three 256-entry automaton tables (PY, C family, all-zero)
+static_assert(OFF_RW % 8 == 0 && OFF_FLAGS % 4 == 0 && OFF_MSK % 4 == 0 && OFF_BASE % 8 == 0 && OFF_CTL % 8 == 0, "alignment");
+constexpr uint32_t LUT_BYTES = 3072 + 128;    // three 256-entry automaton tables (PY, C family, all-zero) + their constants
 constexpr int SCAN_WARPS = TSM_SCAN_WARPS;    // warps per CTA of k_scan (each warp is independent)
 constexpr int SCAN_CTAS_PER_SM = TSM_SCAN_CTAS;
 constexpr uint32_t SCAN_SMEM = LUT_BYTES + SCAN_WARPS * WARP_SMEM;
@@ -129,6 +141,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy accesses of shared memory are ordered in front of later async-proxy (bulk copy) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -3,9 +3,9 @@
 //   k_plan      files -> (file, 4 KiB chunk) work units                         [tiny]
 //   k_scan      THE hot kernel: every source byte is read from HBM exactly once.  One warp per
 //               work unit, chunk staged global->shared by a 1-D TMA bulk copy (cp.async.bulk +
-//               mbarrier, double buffered), pass 1 = SWAR newline table, pass 2 = lane-per-line
-//               Shift-And automaton + Mersenne-61 line hash, then per-file counters, digest and
-//               the candidate (assertion-line) list.
+//               mbarrier), pass 1 = SWAR newline table, pass 2 = lane-per-stripe Shift-And
+//               automaton + Mersenne-61 running prefix, pass 3 = lane-per-line finalise, then
+//               per-file counters, digest and the candidate (assertion-line) list.
 //   k_classify  one thread per candidate: statement, last identifier, category (S5), events, the
 //               cross-file aggregate into a shared-memory privatised [group][category] table, and
 //               the totals of the per-file records.
@@ -51,10 +51,10 @@ __global__ void k_plan(ScanParams p) {
 // ================================================================================= k_scan
 // Work unit = (file, 4 KiB chunk).  Per warp, per unit:
 //   stage   one 1-D TMA bulk copy (cp.async.bulk + mbarrier) of [chunk-16, chunk+4096+240) into shared
-//   pass 1  SWAR newline table (16 B per lane per step, perfectly balanced)
-//   pass 2  lane-per-line walk, 2 x 8 B per iteration, lanes refill dynamically: Shift-And
-//           automaton (one LDS per byte) + Mersenne-61 Horner; raw (A, B) per line into shared
-//   pass 3  balanced finalise, one lane per line: hash finalisation, header / assertion flags
+//   pass 1  SWAR newline bits, one 136-byte stripe per lane; one warp scan orders them into the line table
+//   pass 2  stripe walk (all lanes busy whatever the line lengths): Shift-And automaton (one LDS per
+//           byte), pattern ends -> per-line flag bytes, Mersenne-61 running prefix behind every word
+//   pass 3  balanced finalise, one lane per line: hash = difference of two prefixes, header / assertion flags
 //   pass 4  ballot compaction of candidate (and header-event) lines into the global lists
 // SWAR: 16-bit mask of the bytes equal to '\n' in a 16-byte vector.
 __device__ __forceinline__ uint32_t nl_word(uint32_t w) {
@@ -154,17 +154,25 @@ struct GmemByte {                                        // byte source = the fi
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(b + i); }
 };
 
-// Finish one line from its raw (A, B): SPEC section 3 hash (trailing CR dropped) and SPEC sections 4/5 flags.
+// The four facts pass 3 needs about a line, as one nibble: bit 0 = assertion pattern, bits 1..3 = the
+// language's header patterns (PY: def, class, TEST_F gate; C family: test, one of { class void, TEST_F gate).
+__device__ __forceinline__ uint32_t flag_nibble(uint32_t A, uint32_t g1, uint32_t g2, uint32_t g3) {
+  return ((A & (AF_ASSERT | AF_EXPECT)) ? 1u : 0u) | ((A & g1) ? 2u : 0u) | ((A & g2) ? 4u : 0u) | ((A & g3) ? 8u : 0u);
+}
+__device__ __forceinline__ uint32_t flag_nibble_ext(uint32_t A, int ext) {
+  return ext == TSM_EXT_PY ? flag_nibble(A, PY_DEF, PY_CLASS, PY_STF)
+                           : flag_nibble(A, CJ_TEST, CJ_BRACE | CJ_CLASS | CJ_VOID, CJ_STF);
+}
+
+// Finish one line: h0 = Mersenne-61 value of its bytes (SPEC section 3, trailing CR still inside), nib = its
+// pattern nibble.  Adds the line to the per-file accumulators and returns its LF_* flags (SPEC sections 4/5).
 template <typename LoadByte>
-__device__ __forceinline__ uint32_t line_finish(uint32_t s, uint32_t e, uint32_t A, unsigned long long B, int ext,
-                                                LoadByte lb, Accum& ac) {
+__device__ __forceinline__ uint32_t line_finish_h(uint32_t s, uint32_t e, unsigned long long h0, uint32_t nib, int ext,
+                                                  LoadByte lb, Accum& ac) {
   uint32_t len = e - s;
   unsigned long long h = 0;
   if (len) {
-    // N * 2^(8*lead) = B * 2^(64*(m-1)), m = number of 8-byte blocks the line touches
-    const uint32_t lead = s & 7u, m = ((e - 1) >> 3) - (s >> 3) + 1;
-    uint32_t R = (3u * (m - 1) + 61u * 8u - 8u * lead) % 61u;
-    h = rotl61(canon61(B), R);
+    h = h0;
     if (lb(e - 1) == 0x0D) {                             // drop one trailing CR: subtract 0x0D * 256^(len-1)
       --len;
       const unsigned long long cr = rotl61(0x0Dull, (8u * len) % 61u);
@@ -175,20 +183,32 @@ __device__ __forceinline__ uint32_t line_finish(uint32_t s, uint32_t e, uint32_t
   ac.lines++;
   ac.digest += mix_hash(h, len);
   if (ext == 0) return 0;
-  uint32_t fl = (A & (AF_ASSERT | AF_EXPECT)) ? LF_CAND : 0;
+  uint32_t fl = (nib & 1u) ? LF_CAND : 0;
   bool hdr;
   if (ext == TSM_EXT_PY) {
-    hdr = (A & PY_DEF) != 0;
-    if (!hdr && (A & PY_CLASS)) hdr = starts_with(lb, s, e, "class", 5, true);
-    if (hdr) { fl |= LF_HDR; if ((A & PY_STF) && starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }
+    hdr = (nib & 2u) != 0;
+    if (!hdr && (nib & 4u)) hdr = starts_with(lb, s, e, "class", 5, true);
   } else {
-    hdr = (A & CJ_TEST) && (A & (CJ_BRACE | CJ_CLASS | CJ_VOID));
-    if (hdr) { fl |= LF_HDR; if ((A & CJ_STF) && starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }
+    hdr = (nib & 6u) == 6u;
   }
+  if (hdr) { fl |= LF_HDR; if ((nib & 8u) && starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }
   ac.asserts += fl & LF_CAND;
   ac.hdrs += (fl >> 1) & 1u;
   ac.fixes += (fl >> 2) & 1u;
   return fl;
+}
+
+// Same, from the raw (A, B) of a lane-per-line walk (the long-line slow path and k_hash_lines).
+template <typename LoadByte>
+__device__ __forceinline__ uint32_t line_finish(uint32_t s, uint32_t e, uint32_t A, unsigned long long B, int ext,
+                                                LoadByte lb, Accum& ac) {
+  unsigned long long h0 = 0;
+  if (e != s) {
+    // N * 2^(8*lead) = B * 2^(64*(m-1)), m = number of 8-byte blocks the line touches
+    const uint32_t lead = s & 7u, m = ((e - 1) >> 3) - (s >> 3) + 1;
+    h0 = rotl61(canon61(B), (3u * (m - 1) + 61u * 8u - 8u * lead) % 61u);
+  }
+  return line_finish_h(s, e, h0, ext ? flag_nibble_ext(A, ext) : 0u, ext, lb, ac);
 }
 
 // Append `n` list entries with one atomic; returns the base slot (broadcast from lane 0).
@@ -198,115 +218,213 @@ __device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, uint32_t n, 
   return __shfl_sync(0xffffffffu, base, 0);
 }
 
-struct WarpSmem {                                        // per-warp carve-up of the dynamic shared memory
-  uint8_t* buf; uint16_t* tab; uint32_t* rawA; unsigned long long* rawB; uint64_t* bar;
-};
-
-// Pass 2: lanes walk the lines [lo, hi) of the table, refilling dynamically; raw (A, B) per line to shared.
-// Not inlined on purpose: the hot loop gets its own register allocation (the chunk-level state of
-// the caller is saved once per call instead of competing with the loop for registers).
-__device__ __noinline__ void walk_lines(const uint8_t* buf, const uint16_t* tab, uint32_t* rawA,
-                                        unsigned long long* rawB, const uint32_t* lut, uint32_t first,
-                                        uint32_t lo, uint32_t hi, uint32_t ns, int lane) {
-  uint32_t next = lo;
-  bool active = false;
-  uint32_t myj = 0;
-  LineState L;
-  while (true) {
-    const uint32_t need = __ballot_sync(0xffffffffu, !active);
-    if (need) {
-      const uint32_t j = next + __popc(need & ((1u << lane) - 1u));
-      next += __popc(need);
-      if (!active && j < hi) {
-        line_init(L, j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns, (uint32_t)tab[j] & TAB_POS);
-        myj = j;
-        active = true;
-      }
-    }
-    if (!__any_sync(0xffffffffu, active)) break;
-    if (active) {
+// Eight automaton steps over one 8-byte word; A collects every state of the word.
+__device__ __forceinline__ void step8(unsigned long long w, const uint32_t* lut, uint32_t first, uint32_t& D, uint32_t& A) {
+  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
 #pragma unroll
-      for (int rep = 0; rep < TSM_BLOCKS_PER_ITER; ++rep)  // 8-byte blocks per refill round (tuned: profiles/)
-        if (L.pos < L.e) line_block(L, *reinterpret_cast<const unsigned long long*>(buf + L.pos), lut, first);
-      if (L.pos >= L.e) {
-        rawA[myj - lo] = L.A;
-        rawB[myj - lo] = L.B;
-        active = false;
+  for (int k = 0; k < 4; ++k) {
+    D = ((D + D) | first) & lut[__byte_perm(lo, 0, 0x4440 + k)];
+    A |= D;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    D = ((D + D) | first) & lut[__byte_perm(hi, 0, 0x4440 + k)];
+    A |= D;
+  }
+}
+
+// OR automaton states into the window's per-line flag words (lines outside the window: dropped).
+__device__ __forceinline__ void flag_or(uint8_t* wb, uint32_t rel, uint32_t A) {
+  if (rel < FLAG_CAP) atomicOr(reinterpret_cast<uint32_t*>(wb + OFF_FLAGS) + rel, A);
+}
+
+// Pass 2b: a word that holds both a pattern end and a newline - walk its bytes one at a time so that
+// every match lands on its own line.  entry = word index | line index at the word's first byte << 10.
+// The automaton state in front of the word follows from the eight bytes before it (no pattern is longer).
+__device__ __noinline__ void resolve_word(uint8_t* wb, const uint32_t* lut, uint32_t fin, uint32_t first, uint32_t wlo,
+                                          uint32_t entry) {
+  const uint32_t k = entry & 1023u, pos = 8u * k;
+  uint32_t idx = (entry >> 10) - wlo;
+  const uint32_t l = k / 17u, i = k - 17u * l;
+  uint32_t nl8 = (reinterpret_cast<const uint32_t*>(wb + OFF_MSK)[(i >> 2) * 32u + l] >> (8u * (i & 3u))) & 0xFFu;
+  uint32_t D = 0, A = 0;
+  if (pos > PRE) step8(*reinterpret_cast<const unsigned long long*>(wb + pos - 8), lut, first, D, A);
+  unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + pos);
+#pragma unroll 1
+  for (int b = 0; b < 8; ++b) {
+    D = ((D + D) | first) & lut[(uint32_t)w & 0xFFu];
+    if (D & fin) flag_or(wb, idx, D);
+    idx += nl8 & 1u;
+    nl8 >>= 1;
+    w >>= 8;
+  }
+}
+
+// Pass 2: every lane walks the 17 words of its own 136-byte stripe (all 32 lanes busy for the whole
+// pass, whatever the line lengths are; the bytes outside the chunk's staged range are zeros):
+//   automaton   8 steps per word; the OR of the word's states goes to the flag word of the line the
+//               word lies in (its index follows from the stripe's newline bits); a word with a
+//               newline AND a pattern end goes to the pass-2b queue instead
+//   hash        R_k = R_{k-1} * 2^-64 + w_k (mod 2^61-1) is stored behind every word: pass 3 gets the
+//               Mersenne value of any byte range as a difference of two such prefixes
+// then one warp scan turns the stripe totals into the absolute prefix at every stripe start.
+// Not inlined on purpose: the hot loop gets its own register allocation.
+__device__ __noinline__ void walk_stripes(uint8_t* wb, const uint32_t* lut, uint32_t fin, uint32_t first, uint32_t wlo,
+                                          uint32_t base_all, int lane) {
+  const uint32_t pos0 = (uint32_t)lane * STRIPE;
+  uint8_t* sp = wb + pos0;
+  const uint32_t* msk = reinterpret_cast<const uint32_t*>(wb + OFF_MSK) + lane;
+  uint32_t* flags = reinterpret_cast<uint32_t*>(wb + OFF_FLAGS);
+  unsigned long long* rw = reinterpret_cast<unsigned long long*>(wb + OFF_RW) + (uint32_t)lane * RW_PER_STRIPE;
+  uint32_t D = 0;
+  if (lane) {                                            // state in front of the stripe
+    uint32_t A = 0;
+    step8(*reinterpret_cast<const unsigned long long*>(sp - 8), lut, first, D, A);
+  }
+  unsigned long long R = 0;
+  uint32_t idxg = base_all - wlo;                        // window-relative line index at the group's first byte
+#pragma unroll 1
+  for (uint32_t g = 0; g < 5; ++g) {
+    const uint32_t mg = msk[g * 32u];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+      if (g == 4 && k) break;
+      const uint32_t off = 32u * g + 8u * k;
+      const unsigned long long w = *reinterpret_cast<const unsigned long long*>(sp + off);
+      uint32_t A = 0;
+      step8(w, lut, first, D, A);
+      R = (R >> 3) + ((R & 7ull) << 58) + fold61(w);      // lazily reduced: stays below 2^63
+      if ((k & (RW_STRIDE - 1u)) == RW_STRIDE - 1u && g < 4)   // checkpoint behind every RW_STRIDE-th word (not the 17th)
+        rw[(4u * g + k) >> RW_SHIFT] = R;
+      const uint32_t nl8 = (mg >> (8u * k)) & 0xFFu;
+      const uint32_t idx = idxg + __popc(mg & ((1u << (8u * k)) - 1u));
+      atomicOr(flags + min(idx, FLAG_CAP - 1u), nl8 ? 0u : A);            // entry FLAG_CAP-1 is never a line
+      if (nl8 && (A & fin)) {
+        const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(wb + OFF_CTL), 1u);
+        const uint32_t entry = ((pos0 + off) >> 3) | ((idx + wlo) << 10);
+        if (slot < Q_CAP) reinterpret_cast<uint32_t*>(wb + OFF_Q)[slot] = entry;
+        else resolve_word(wb, lut, fin, first, wlo, entry);
       }
     }
+    idxg += __popc(mg);
   }
+  // stripe totals (frame of the stripe's last word) -> absolute frame -> exclusive scan
+  unsigned long long incl = rotl61(canon61(R), (3u * (17u * (uint32_t)lane + 16u)) % 61u);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl = fold61(incl + t);
+  }
+  unsigned long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 0;
+  unsigned long long* sbase = reinterpret_cast<unsigned long long*>(wb + OFF_BASE);
+  sbase[lane] = excl;
+  if (lane == 31) sbase[32] = incl;
+  __syncwarp();
+  const uint32_t nq = min(*reinterpret_cast<const uint32_t*>(wb + OFF_CTL), Q_CAP);
+  for (uint32_t t = (uint32_t)lane; t < nq; t += 32)
+    resolve_word(wb, lut, fin, first, wlo, reinterpret_cast<const uint32_t*>(wb + OFF_Q)[t]);
   __syncwarp();
 }
 
-// Pass 3: balanced finalise, one lane per line.
-__device__ __noinline__ void finish_lines(const uint8_t* buf, uint16_t* tab, const uint32_t* rawA,
-                                          const unsigned long long* rawB, uint32_t lo, uint32_t hi, uint32_t ns,
-                                          int ext, int lane, Accum& ac) {
-  const SmemByte lb{buf};
+// Mersenne-61 value of the staged bytes [0, x), every byte weighted 256^position; lazily reduced (< 2^62 + 2).
+// x = 8k + b, r3k = 3k mod 61.  Starts from the last checkpoint in front of word k and folds the words between.
+__device__ __forceinline__ unsigned long long prefix_at(const uint8_t* wb, uint32_t k, uint32_t b, uint32_t r3k) {
+  const uint32_t l = k / 17u, i = k - 17u * l, c0 = i >> RW_SHIFT;
+  unsigned long long R = 0;                              // prefix inside the stripe behind word k-1, frame of word k-1
+  if (c0) R = *reinterpret_cast<const unsigned long long*>(wb + OFF_RW + 8u * (l * RW_PER_STRIPE + c0 - 1u));
+#pragma unroll 1
+  for (uint32_t t = c0 << RW_SHIFT; t < i; ++t)          // at most RW_STRIDE - 1 words
+    R = (R >> 3) + ((R & 7ull) << 58) + fold61(*reinterpret_cast<const unsigned long long*>(wb + 8u * (k - i + t)));
+  unsigned long long loc = (R >> 3) + ((R & 7ull) << 58);                // frame of word k
+  if (b) loc += *reinterpret_cast<const unsigned long long*>(wb + 8u * k) & ((1ull << (8u * b)) - 1ull);
+  return *reinterpret_cast<const unsigned long long*>(wb + OFF_BASE + 8u * l) + rotl61(canon61(loc), r3k);
+}
+
+// Pass 3: balanced finalise, one lane per line: hash = difference of two prefixes, flags from the
+// line's flag word; the starts of the candidate lines are compacted (u16 each) over the flag words
+// already consumed.  Returns the number of candidates.
+__device__ __noinline__ uint32_t finish_lines(uint8_t* wb, const uint32_t* lc, uint32_t j0, uint32_t cnt, uint32_t ns,
+                                              int ext, int lane, Accum& ac) {
+  uint16_t* tab = reinterpret_cast<uint16_t*>(wb + OFF_TAB);
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(wb + OFF_FLAGS);
+  uint16_t* clist = reinterpret_cast<uint16_t*>(wb + OFF_FLAGS);
+  const uint32_t g1 = lc[1], g2 = lc[2], g3 = lc[3];
+  const SmemByte lb{wb};
   Accum a = ac;
-  for (uint32_t base = lo; base < hi; base += 32) {      // uniform trip count: the warp syncs inside
-    const uint32_t j = base + lane;
-    const bool valid = j < hi;
-    uint32_t s = 0, e = 0;
-    if (valid) { s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns; e = (uint32_t)tab[j] & TAB_POS; }
-    __syncwarp();                                        // every neighbour entry is read before any is rewritten
+  uint32_t nc = 0;
+  uint32_t cs = j0 ? ((uint32_t)tab[j0 - 1] & TAB_POS) + 1u : ns;       // start of the round's first line
+  unsigned long long cP = prefix_at(wb, cs >> 3, cs & 7u, (3u * (cs >> 3)) % 61u);   // ... and the prefix in front of it
+  for (uint32_t base = j0; base < cnt; base += 32) {                     // uniform trip count
+    const uint32_t j = base + (uint32_t)lane;
+    const bool valid = j < cnt;
+    const uint32_t e = valid ? (uint32_t)tab[j] & TAB_POS : 0u;
+    const uint32_t A = valid ? flags[j] : 0u;
+    const uint32_t k = e >> 3, b = e & 7u, r3k = (3u * k) % 61u;
+    uint32_t r8e = r3k + 8u * b;                                         // (8 * e) mod 61
+    if (r8e >= 61u) r8e -= 61u;
+    const unsigned long long Pe = prefix_at(wb, k, b, r3k);
+    const unsigned long long Pn = Pe + rotl61(0x0Aull, r8e);             // prefix behind the terminator (< 2^63 - 4)
+    uint32_t s = __shfl_up_sync(0xffffffffu, e, 1) + 1u;
+    unsigned long long Ps = __shfl_up_sync(0xffffffffu, Pn, 1);
+    if (lane == 0) { s = cs; Ps = cP; }
+    cs = __shfl_sync(0xffffffffu, e, 31) + 1u;
+    cP = __shfl_sync(0xffffffffu, Pn, 31);
+    uint32_t fl = 0;
     if (valid) {
-      const uint32_t fl = line_finish(s, e, rawA[j - lo], rawB[j - lo], ext, lb, a);
+      const unsigned long long hr = canon61(Pe + 4ull * M61 - Ps);       // bytes [s, e), weighted from position 0
+      const unsigned long long h0 = rotl61(hr, (61u - (8u * s) % 61u) % 61u);
+      fl = line_finish_h(s, e, h0, flag_nibble(A, g1, g2, g3), ext, lb, a);
       tab[j] = (uint16_t)(e | (fl << 13));               // flags ride in the 3 spare bits of the entry
     }
-    __syncwarp();
+    __syncwarp();                                        // every flag word of the round is read: the list may grow over them
+    const uint32_t mc = __ballot_sync(0xffffffffu, fl & LF_CAND);
+    if (fl & LF_CAND) clist[nc + __popc(mc & ((1u << lane) - 1u))] = (uint16_t)s;
+    nc += __popc(mc);
   }
   ac = a;
   __syncwarp();
+  return nc;
 }
 
-// Passes 2-4 over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
-__device__ __forceinline__ void drain(const ScanParams& p, const uint32_t* lut, uint32_t first, const WarpSmem& ws,
-                                      uint32_t cnt, bool& skip_first, uint32_t& next_start, uint32_t f,
-                                      uint32_t cb, int ext, int lane, Accum& ac) {
+// Passes 3-4 over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
+__device__ __forceinline__ void drain(const ScanParams& p, uint8_t* wb, const uint32_t* lc, uint32_t cnt,
+                                      bool& skip_first, uint32_t& next_start, uint32_t f, uint32_t cb, int ext, int lane,
+                                      Accum& ac) {
   __syncwarp();
   if (cnt == 0) return;
-  const uint16_t* tab = ws.tab;
+  const uint16_t* tab = reinterpret_cast<const uint16_t*>(wb + OFF_TAB);
   const uint32_t j0 = skip_first ? 1u : 0u;
   const uint32_t ns = next_start;
-  for (uint32_t lo = j0; lo < cnt; lo += WALK_BATCH) {
-    const uint32_t hi = min(cnt, lo + WALK_BATCH);
-    walk_lines(ws.buf, ws.tab, ws.rawA, ws.rawB, lut, first, lo, hi, ns, lane);   // pass 2
-    finish_lines(ws.buf, ws.tab, ws.rawA, ws.rawB, lo, hi, ns, ext, lane, ac);    // pass 3
-  }
+  const uint32_t nc = finish_lines(wb, lc, j0, cnt, ns, ext, lane, ac);   // pass 3
   // ---- pass 4: candidates (always) and header events (on request) to their global lists
-  const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
-  uint32_t nc = 0, nh = 0;
-  if (ext != 0) {
-    for (uint32_t b = j0; b < cnt; b += 32) {
-      const uint32_t j = b + lane;
-      const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
-      nc += __popc(__ballot_sync(0xffffffffu, fb & LF_CAND));
-      nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
+  if (nc) {
+    const uint16_t* clist = reinterpret_cast<const uint16_t*>(wb + OFF_FLAGS);
+    const uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
+    for (uint32_t i = (uint32_t)lane; i < nc; i += 32) {
+      const uint32_t slot = cbase + i;
+      if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | (cb + (uint32_t)clist[i] - PRE);
+      else p.ctrl->overflow = 1;
     }
   }
-  if (!want_hev) nh = 0;
-  if (nc | nh) {
-    uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
-    uint32_t hbase = warp_reserve(&p.ctrl->n_hev, nh, lane);
+  if ((p.flags & TSM_SCAN_HEADER_EVENTS) && ext != 0) {
+    uint32_t nh = 0;
     for (uint32_t b = j0; b < cnt; b += 32) {
       const uint32_t j = b + lane;
       const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
-      uint32_t s = 0, e = 0;
-      if (j < cnt) { s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns; e = (uint32_t)tab[j] & TAB_POS; }
-      const uint32_t line_off = cb + s - PRE;
-      const uint32_t mc = __ballot_sync(0xffffffffu, fb & LF_CAND);
-      if (fb & LF_CAND) {
-        const uint32_t slot = cbase + __popc(mc & ((1u << lane) - 1u));
-        if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | line_off;
-        else p.ctrl->overflow = 1;
-      }
-      cbase += __popc(mc);
-      if (want_hev) {
+      nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
+    }
+    if (nh) {
+      uint32_t hbase = warp_reserve(&p.ctrl->n_hev, nh, lane);
+      for (uint32_t b = j0; b < cnt; b += 32) {
+        const uint32_t j = b + lane;
+        const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
+        uint32_t s = 0, e = 0;
+        if (j < cnt) { s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns; e = (uint32_t)tab[j] & TAB_POS; }
         const uint32_t mh = __ballot_sync(0xffffffffu, fb & LF_HDR);
         if (fb & LF_HDR) {
           const uint32_t slot = hbase + __popc(mh & ((1u << lane) - 1u));
-          if (slot < p.hev_cap) p.hev[slot] = tsm_header_event{f, line_off, e - s, (fb >> 2) & 1u};
+          if (slot < p.hev_cap) p.hev[slot] = tsm_header_event{f, cb + s - PRE, e - s, (fb >> 2) & 1u};
           else p.ctrl->overflow = 1;
         }
         hbase += __popc(mh);
@@ -345,11 +463,11 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
   }
 }
 
-__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, uint32_t first,
-                                              const WarpSmem& ws, uint32_t f, uint32_t cb, uint32_t fo,
+__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, const uint32_t* lc,
+                                              uint32_t first, uint8_t* wb, uint32_t f, uint32_t cb, uint32_t fo,
                                               uint32_t size, int ext, int lane) {
-  const uint8_t* buf = ws.buf;
-  uint16_t* tab = ws.tab;
+  const uint8_t* buf = wb;
+  uint16_t* tab = reinterpret_cast<uint16_t*>(wb + OFF_TAB);
   const uint32_t ce = min(cb + CH, size);
   const uint32_t le = min(ce + EXT, size);
   const uint32_t lim = PRE + (ce - cb);                  // buffer position just past the owned bytes
@@ -358,42 +476,49 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   uint32_t next_start = PRE;
   Accum ac{0, 0, 0, 0, 0};
   uint32_t cnt = 0;
+  __syncwarp();
+  // ---- everything outside the staged range [PRE, lim2) becomes zeros: no pass has to mask its loads
+  //      (a zero byte is no newline, matches no pattern and adds nothing to the hash prefix)
+  if (lane < 2) reinterpret_cast<unsigned long long*>(wb)[lane] = 0ull;
+  {
+    const uint32_t za = (lim2 + 7u) & ~7u;
+    if ((uint32_t)lane < za - lim2) wb[lim2 + lane] = 0;
+    for (uint32_t q = za + 8u * (uint32_t)lane; q < BUF; q += 256u) *reinterpret_cast<unsigned long long*>(wb + q) = 0ull;
+  }
+  __syncwarp();
   // ---- pass 1: every lane takes one 136-byte stripe of the 4 352 staged bytes (17 conflict-free
   //      LDS.64) and keeps the newline positions of its stripe as a 136-bit mask in registers;
   //      one warp scan then orders them into the u16 line table, NL_CAP entries per window
   const uint32_t pos0 = (uint32_t)lane * STRIPE;
+  uint32_t* msk = reinterpret_cast<uint32_t*>(wb + OFF_MSK) + lane;       // msk[g * 32]: newline bits of the stripe's bytes [32g, 32g+32)
   uint32_t own[5], extm[5];                              // newlines at positions [PRE, lim) / [lim, lim2)
   {
     uint32_t m[5] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
     for (int i = 0; i < 17; ++i) {
-      const uint32_t pos = pos0 + 8u * (uint32_t)i;
-      uint32_t nl8 = 0;
-      if (pos < lim2) {
-        const uint2 w = *reinterpret_cast<const uint2*>(buf + pos);
-        nl8 = nl_word(w.x) | (nl_word(w.y) << 4);
-      }
-      m[i >> 2] |= nl8 << (8 * (i & 3));
+      const uint2 w = *reinterpret_cast<const uint2*>(buf + pos0 + 8u * (uint32_t)i);
+      m[i >> 2] |= (nl_word(w.x) | (nl_word(w.y) << 4)) << (8 * (i & 3));
     }
+    const uint32_t rel = lim > pos0 ? lim - pos0 : 0u;   // owned bytes of this stripe (may exceed 136)
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      const uint32_t b0 = pos0 + 32u * (uint32_t)j;      // position of bit 0 of this word
-      auto below = [&](uint32_t x) -> uint32_t {         // mask of the bits whose position is < x
-        return x <= b0 ? 0u : (x - b0 >= 32u ? 0xFFFFFFFFu : (1u << (x - b0)) - 1u);
-      };
-      own[j] = m[j] & below(lim) & ~below(PRE);
-      extm[j] = m[j] & below(lim2) & ~below(lim);
+      const uint32_t below = rel >= 32u * (j + 1) ? 0xFFFFFFFFu : (rel <= 32u * j ? 0u : (1u << (rel - 32u * j)) - 1u);
+      own[j] = m[j] & below;
+      extm[j] = m[j] & ~below;
+      msk[j * 32] = m[j];                                // pass 2 reads them back
     }
   }
-  uint32_t mine = __popc(own[0]) + __popc(own[1]) + __popc(own[2]) + __popc(own[3]) + __popc(own[4]);
-  uint32_t incl = mine;
+  const uint32_t mine = __popc(own[0]) + __popc(own[1]) + __popc(own[2]) + __popc(own[3]) + __popc(own[4]);
+  const uint32_t mine_ext = __popc(extm[0]) + __popc(extm[1]) + __popc(extm[2]) + __popc(extm[3]) + __popc(extm[4]);
+  uint32_t incl = mine | (mine_ext << 16);               // both counts in one scan (each < 2^13)
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += t;
   }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t base_idx = incl - mine;
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31) & 0xFFFFu;
+  const uint32_t base_idx = (incl & 0xFFFFu) - mine;
+  const uint32_t base_all = base_idx + (incl >> 16) - mine_ext;          // newlines (of either kind) in front of the stripe
   uint32_t ext_first = 0xFFFFu;                          // first newline behind the owned bytes
 #pragma unroll
   for (int j = 4; j >= 0; --j)
@@ -401,21 +526,24 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
   ext_first = __reduce_min_sync(0xffffffffu, ext_first);
   for (uint32_t wstart = 0;; wstart += NL_CAP) {
     cnt = min(total - wstart, NL_CAP);
-    uint32_t idx = base_idx;
+    uint32_t idx = base_idx - wstart;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       uint32_t b = own[j];
       while (b) {
-        if (idx - wstart < cnt) tab[idx - wstart] = (uint16_t)(pos0 + 32u * (uint32_t)j + (uint32_t)(__ffs(b) - 1));
+        if (idx < cnt) tab[idx] = (uint16_t)(pos0 + 32u * (uint32_t)j + (uint32_t)(__ffs(b) - 1));
         ++idx;
         b &= b - 1;
       }
     }
+    for (uint32_t i = (uint32_t)lane; i < cnt + 2u; i += 32) reinterpret_cast<uint32_t*>(wb + OFF_FLAGS)[i] = 0u;
+    if (lane == 0) *reinterpret_cast<uint32_t*>(wb + OFF_CTL) = 0u;
     __syncwarp();
+    walk_stripes(wb, lut, lc[0], first, wstart, base_all, lane);         // pass 2 (the window's flag words)
     if (wstart + cnt >= total) break;                    // last window: the tail line joins it below
-    drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+    drain(p, wb, lc, cnt, skip_first, next_start, f, cb, ext, lane, ac);
   }
-  // ---- the last owned line: starts in the chunk, may end behind it
+  // ---- the last owned line: starts in the chunk, may end behind it (its line index = total)
   const uint32_t tail_start = cnt ? ((uint32_t)tab[cnt - 1] & TAB_POS) + 1u : next_start;
   const bool owned = !(skip_first && cnt == 0);
   bool have_tail = false, tail_long = false;
@@ -426,24 +554,24 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
     else if (le == size) { tail_end = lim2; have_tail = true; }        // file ends inside the staged bytes
     else tail_long = true;
   }
-  if (have_tail) {
-    if (cnt == NL_CAP) {
-      drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-      cnt = 0;
-    }
+  if (have_tail) {                                       // the table has room for NL_CAP + 1 entries
     if (lane == 0) tab[cnt] = (uint16_t)tail_end;
     ++cnt;
   }
-  drain(p, lut, first, ws, cnt, skip_first, next_start, f, cb, ext, lane, ac);
+  drain(p, wb, lc, cnt, skip_first, next_start, f, cb, ext, lane, ac);
   if (tail_long && lane == 0) long_line(p, lut, first, f, fo, size, ext, cb + tail_start - PRE, ac);
-  // ---- per-file counters: warp reduce, then one store (single-chunk file) or one atomic per counter
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    ac.lines += __shfl_xor_sync(0xffffffffu, ac.lines, d);
-    ac.asserts += __shfl_xor_sync(0xffffffffu, ac.asserts, d);
-    ac.hdrs += __shfl_xor_sync(0xffffffffu, ac.hdrs, d);
-    ac.fixes += __shfl_xor_sync(0xffffffffu, ac.fixes, d);
-    ac.digest += __shfl_xor_sync(0xffffffffu, ac.digest, d);
+  // ---- per-file counters: warp reduce (the digest as three partial sums: low halves keep their carries),
+  //      then one store (single-chunk file) or one atomic per counter
+  ac.lines = __reduce_add_sync(0xffffffffu, ac.lines);
+  ac.asserts = __reduce_add_sync(0xffffffffu, ac.asserts);
+  ac.hdrs = __reduce_add_sync(0xffffffffu, ac.hdrs);
+  ac.fixes = __reduce_add_sync(0xffffffffu, ac.fixes);
+  {
+    const uint32_t dlo = (uint32_t)ac.digest, dhi = (uint32_t)(ac.digest >> 32);
+    const unsigned long long s0 = __reduce_add_sync(0xffffffffu, dlo & 0xFFFFu);
+    const unsigned long long s1 = __reduce_add_sync(0xffffffffu, dlo >> 16);
+    const unsigned long long s2 = __reduce_add_sync(0xffffffffu, dhi);
+    ac.digest = s0 + (s1 << 16) + (s2 << 32);
   }
   if (lane == 0) {
     tsm_file_stat* st = p.stats + f;
@@ -489,32 +617,35 @@ __device__ __forceinline__ Unit claim_unit(const ScanParams& p, uint32_t n_units
 
 __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t* lut_py = reinterpret_cast<uint32_t*>(smem);
-  uint32_t* lut_cj = lut_py + 256;
-  uint32_t* lut_zero = lut_py + 512;
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_py[i] = i < 512 ? c_lut[i] : 0u;
+  uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) PY, [256,512) C family, [512,768) zero, then 3 x 4 constants
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_all[i] = i < 512 ? c_lut[i] : 0u;
+  if (threadIdx.x < 12) {                                // per language: all pattern ends, then the three header groups
+    const uint32_t py[4] = {AF_ASSERT | AF_EXPECT | PY_DEF | PY_CLASS | PY_STF, PY_DEF, PY_CLASS, PY_STF};
+    const uint32_t cj[4] = {AF_ASSERT | AF_EXPECT | CJ_TEST | CJ_CLASS | CJ_VOID | CJ_BRACE | CJ_STF, CJ_TEST,
+                            CJ_BRACE | CJ_CLASS | CJ_VOID, CJ_STF};
+    const int t = threadIdx.x;
+    lut_all[768 + t] = t < 4 ? py[t] : (t < 8 ? cj[t - 4] : 0u);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wb = smem + LUT_BYTES + warp * WARP_SMEM;
-  WarpSmem ws;
-  ws.buf = wb;
-  ws.tab = reinterpret_cast<uint16_t*>(wb + BUF);
-  ws.rawB = reinterpret_cast<unsigned long long*>(wb + BUF + TAB_BYTES);
-  ws.rawA = reinterpret_cast<uint32_t*>(wb + BUF + TAB_BYTES + 8 * WALK_BATCH);
-  ws.bar = reinterpret_cast<uint64_t*>(wb + BUF + TAB_BYTES + 12 * WALK_BATCH);
-  if (lane == 0) { mbar_init(ws.bar, 1); fence_mbar_init(); }
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wb + OFF_CTL + 8);
+  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   __syncwarp();
   const uint32_t n_units = p.slab->n_units;
   uint32_t phase = 0;
   Unit cur = claim_unit(p, n_units, lane);
   while (cur.u < n_units) {
-    if (lane == 0) issue_load(p, ws.buf, ws.bar, cur.fo, cur.size, cur.cb);
+    fence_proxy_async();                                 // this warp's zero fill and reads of the last chunk come first
+    __syncwarp();
+    if (lane == 0) issue_load(p, wb, bar, cur.fo, cur.size, cur.cb);
     const Unit nxt = claim_unit(p, n_units, lane);       // metadata of the next unit arrives during this chunk
-    while (!mbar_try_wait(ws.bar, phase)) {}
+    while (!mbar_try_wait(bar, phase)) {}
     phase ^= 1;
-    const uint32_t* lut = cur.ext == 0 ? lut_zero : (cur.ext == TSM_EXT_PY ? lut_py : lut_cj);
+    const uint32_t lang = cur.ext == 0 ? 2u : (cur.ext == TSM_EXT_PY ? 0u : 1u);
     const uint32_t first = cur.ext == 0 ? 0u : (cur.ext == TSM_EXT_PY ? PY_FIRST : CJ_FIRST);
-    process_chunk(p, lut, first, ws, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
+    process_chunk(p, lut_all + 256u * lang, lut_all + 768u + 4u * lang, first, wb, cur.f, cur.cb, cur.fo, cur.size,
+                  cur.ext, lane);
     __syncwarp();
     cur = nxt;
   }
