@@ -25,6 +25,9 @@ static_assert(STRIPE * 32 == BUF && STRIPE % 8 == 0 && (STRIPE / 8) % 2 == 1, "s
 #ifndef TSM_NL_CAP
 #define TSM_NL_CAP 384
 #endif
+#ifndef TSM_LOCKSTEP
+#define TSM_LOCKSTEP 1
+#endif
 #ifndef TSM_RW_SHIFT
 #define TSM_RW_SHIFT 2
 #endif

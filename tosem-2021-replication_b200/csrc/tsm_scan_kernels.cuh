@@ -635,7 +635,15 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(Scan
   const uint32_t n_units = p.slab->n_units;
   uint32_t phase = 0;
   Unit cur = claim_unit(p, n_units, lane);
+#if TSM_LOCKSTEP
+  // the warps of a CTA start every chunk together: they then run the same pass at about the same time and
+  // share its instructions in the SM's instruction caches (the hot code is larger than the 32 KB L1.5;
+  // measured -6 % kernel time, profiles/README.md)
+  while (__syncthreads_or(cur.u < n_units)) {
+    if (cur.u >= n_units) continue;
+#else
   while (cur.u < n_units) {
+#endif
     fence_proxy_async();                                 // this warp's zero fill and reads of the last chunk come first
     __syncwarp();
     if (lane == 0) issue_load(p, wb, bar, cur.fo, cur.size, cur.cb);
