@@ -61,7 +61,7 @@ __device__ __forceinline__ uint32_t nl_word(uint32_t w) {
   const uint32_t y = w ^ 0x0A0A0A0Au;
   const uint32_t t = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
   const uint32_t z = ~(t | y | 0x7F7F7F7Fu);            // 0x80 in every byte that was '\n'
-  return ((z >> 7) * 0x00204081u) >> 21 & 0xFu;         // gather the four flag bits
+  return (z * 0x00204081u) >> 28;                        // gather the four flag bits: 7+21, 15+14, 23+7, 31+0 -> 28..31
 }
 __device__ __forceinline__ uint32_t nl16(const uint4& v) {
   return nl_word(v.x) | (nl_word(v.y) << 4) | (nl_word(v.z) << 8) | (nl_word(v.w) << 12);
