@@ -89,9 +89,25 @@ def test_chunk_edge_alignment_sweep(scanner):
 
 
 def test_newline_storms(scanner):
-    """More lines per chunk than the 1024-entry line table holds (mid-chunk drains)."""
+    """More lines per chunk than one window of the line table holds (several windows per chunk)."""
     files = [b"\n" * 20000, b"a\n" * 9000, (b"assert x\n" + b"\n" * 700) * 9, b"\n" * 4096 + b"assert y", b"\r\n" * 5000]
     check_against_oracle(scanner, ts.pack(files, [1, 2, 1, 4, 3]))
+
+
+def test_pattern_ends_next_to_newlines(scanner):
+    """Every word holds a newline AND a pattern end (pass 2b: queue overflow, several line windows per chunk),
+    patterns straddling stripe and word borders at every alignment, flags of lines that span stripes."""
+    files, exts = [], []
+    for body, ext in [(b"{\n", 3), (b"test{\n}\n", 3), (b"void test(){\n", 3), (b"TEST_F(A, b) {\n", 3),
+                      (b"def\n", 1), (b"def f():\n assert x\n", 1), (b"class A:\n  class B :\n", 1),
+                      (b"EXPECT_EQ(a, b);\r\n", 3), (b"\tassert(x);{\n", 6), (b"x = 1\n", 1)]:
+        for pad in (0, 1, 3, 7, 129, 135, 4090):
+            files.append(b"#" * pad + b"\n" + body * (20000 // len(body)))
+            exts.append(ext)
+    long_line = b"// " + b"y" * 700 + b" assert_that(x) test { void class " + b"z" * 300 + b"\n"   # spans 8 stripes
+    files.append((long_line + b"int test_it() {\n") * 40)
+    exts.append(3)
+    check_against_oracle(scanner, ts.pack(files, exts))
 
 
 def test_synthetic_c2_shape(scanner):
