@@ -97,23 +97,17 @@ extern "C" const char* tsm_category_name(int id) {
   return kNames[id];
 }
 
-static void build_lut(uint32_t* lut) {                   // lut[0..256) = PY table, lut[256..512) = C-family table
+static void build_lut(uint32_t* lut) {                   // the one automaton table of tsm_device.cuh
   struct Pat { const char* s; int first; bool ci; };
-  static const Pat py[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"def", 13, false}, {"class", 16, false},
-                           {"ST_F", 21, false}};
-  static const Pat cj[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"test", 13, true}, {"class", 17, false},
-                           {"void", 22, false}, {"{", 26, false}, {"ST_F", 27, false}};
-  memset(lut, 0, 512 * sizeof(uint32_t));
-  auto fill = [](uint32_t* t, const Pat* pats, int n) {
-    for (int i = 0; i < n; ++i)
-      for (int k = 0; pats[i].s[k]; ++k) {
-        const unsigned char c = (unsigned char)pats[i].s[k];
-        t[c] |= 1u << (pats[i].first + k);
-        if (pats[i].ci && c >= 'a' && c <= 'z') t[c - 32] |= 1u << (pats[i].first + k);
-      }
-  };
-  fill(lut, py, 5);
-  fill(lut + 256, cj, 7);
+  static const Pat pats[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"class", 13, false}, {"def", 18, false},
+                             {"test", 21, true}, {"void", 25, false}, {"{", 29, false}, {"_F", 30, false}};
+  memset(lut, 0, 256 * sizeof(uint32_t));
+  for (const Pat& p : pats)
+    for (int k = 0; p.s[k]; ++k) {
+      const unsigned char c = (unsigned char)p.s[k];
+      lut[c] |= 1u << (p.first + k);
+      if (p.ci && c >= 'a' && c <= 'z') lut[c - 32] |= 1u << (p.first + k);
+    }
 }
 
 static void build_elut(uint32_t* lut) {                  // operator patterns of SPEC section 6 rule 2
@@ -183,7 +177,7 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   if (rc == TSM_OK && cudaHostAlloc((void**)&c->h_ctrl, sizeof(Ctrl) + 64, cudaHostAllocDefault) != cudaSuccess) rc = TSM_E_CUDA;
   for (auto& set : c->ev) for (cudaEvent_t& e : set) if (rc == TSM_OK && cudaEventCreate(&e) != cudaSuccess) rc = TSM_E_CUDA;
   if (rc == TSM_OK) {
-    uint32_t lut[512];
+    uint32_t lut[256];
     build_lut(lut);
     static const uint8_t slot[TSM_CAT_SLOTS] = TSM_CAT_SLOT_INIT;
     static const uint16_t offs[TSM_CAT_NAMED + 1] = TSM_CAT_OFF_INIT;

@@ -59,22 +59,22 @@ constexpr uint32_t WARP_SMEM = ((OFF_CTL + 16 + 127) / 128) * 128;
 static_assert(NL_CAP % 4 == 0 && NL_CAP >= 64, "window size");
 static_assert(BUF <= TAB_POS + 1, "line-table positions must fit 13 bits");
 static_assert(OFF_RW % 8 == 0 && OFF_FLAGS % 4 == 0 && OFF_MSK % 4 == 0 && OFF_BASE % 8 == 0 && OFF_CTL % 8 == 0, "alignment");
-constexpr uint32_t LUT_BYTES = 3072 + 128;    // three 256-entry automaton tables (PY, C family, all-zero) + their constants
+constexpr uint32_t LUT_BYTES = 1024 + 128;    // the 256-entry automaton table + the per-language pattern-end masks
 constexpr int SCAN_WARPS = TSM_SCAN_WARPS;    // warps per CTA of k_scan (each warp is independent)
 constexpr int SCAN_CTAS_PER_SM = TSM_SCAN_CTAS;
 constexpr uint32_t SCAN_SMEM = LUT_BYTES + SCAN_WARPS * WARP_SMEM;
 
-// ---- multi-pattern Shift-And automata (SPEC sections 4, 5) -----------------------------------------
-// One state bit per pattern byte; D' = ((D << 1) | FIRST) & LUT[c]; a line's OR of all D tells
-// which patterns ended somewhere inside it.  One table per language family (the header rules differ):
-//   both  bits  0.. 5  assert (ci)   bits  6..12  EXPECT_ (cs)
-//   PY    bits 13..15  def           bits 16..20  class        bits 21..24  ST_F (gate of the TEST_F check)
-//   CJ    bits 13..16  test (ci)     bits 17..21  class        bits 22..25  void   bit 26  {   bits 27..30  ST_F
-constexpr uint32_t AF_ASSERT = 1u << 5, AF_EXPECT = 1u << 12;
-constexpr uint32_t PY_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 16) | (1u << 21);
-constexpr uint32_t PY_DEF = 1u << 15, PY_CLASS = 1u << 20, PY_STF = 1u << 24;
-constexpr uint32_t CJ_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 17) | (1u << 22) | (1u << 26) | (1u << 27);
-constexpr uint32_t CJ_TEST = 1u << 16, CJ_CLASS = 1u << 21, CJ_VOID = 1u << 25, CJ_BRACE = 1u << 26, CJ_STF = 1u << 30;
+// ---- multi-pattern Shift-And automaton (SPEC sections 4, 5) ------------------------------------------
+// One state bit per pattern byte; D' = ((D << 1) | FIRST) & LUT[c]; a line's OR of all D tells which
+// patterns ended somewhere inside it.  ONE table for all languages (its address is a compile-time
+// constant: the lookups are LDS [byte * 4 + const]); the language only decides which pattern ends count:
+//   bits  0.. 5  assert (ci)    bits  6..12  EXPECT_ (cs)   bits 13..17  class     bits 18..20  def
+//   bits 21..24  test (ci)      bits 25..28  void           bit  29      {         bits 30..31  _F (gate of the TEST_F check)
+constexpr uint32_t A_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 18) | (1u << 21) | (1u << 25) | (1u << 29) | (1u << 30);
+constexpr uint32_t AF_ASSERT = 1u << 5, AF_EXPECT = 1u << 12, A_CLASS = 1u << 17, A_DEF = 1u << 20, A_TEST = 1u << 24,
+                   A_VOID = 1u << 28, A_BRACE = 1u << 29, A_STF = 1u << 31;
+// header patterns per language family: group 1, group 2, TEST_F gate (SPEC section 5)
+constexpr uint32_t PY_G1 = A_DEF, PY_G2 = A_CLASS, CJ_G1 = A_TEST, CJ_G2 = A_BRACE | A_CLASS | A_VOID;
 
 // per-line flag byte written by k_scan's pass 3
 constexpr uint8_t LF_CAND = 1, LF_HDR = 2, LF_FIX = 4;

@@ -68,10 +68,10 @@ __global__ void k_mark_lines(DiffSide d, int32_t n) {
 }
 
 __global__ void k_hash_lines(DiffSide d, int32_t n, unsigned long long total) {
-  __shared__ uint32_t lut[768];                          // PY, C-family and all-zero automaton tables
+  __shared__ uint32_t lut[256];                          // the automaton table
   const bool want_flags = d.line_flag != nullptr;
   if (want_flags) {
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = i < 512 ? c_lut[i] : 0u;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_lut[i];
     __syncthreads();
   }
   const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -87,10 +87,8 @@ __global__ void k_hash_lines(DiffSide d, int32_t n, unsigned long long total) {
   line_init(L, s, e);
   if (want_flags) {
     const int ext = d.ext ? d.ext[f] : 0;
-    const uint32_t* t = ext == 0 ? lut + 512 : (ext == TSM_EXT_PY ? lut : lut + 256);
-    const uint32_t first = ext == 0 ? 0u : (ext == TSM_EXT_PY ? PY_FIRST : CJ_FIRST);
-    while (L.pos < L.e) line_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), t, first);
-    d.line_flag[i] = (L.A & (AF_ASSERT | AF_EXPECT)) ? 1 : 0;
+    while (L.pos < L.e) line_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), lut, A_FIRST);
+    d.line_flag[i] = (ext != 0 && (L.A & (AF_ASSERT | AF_EXPECT))) ? 1 : 0;
   } else {
     while (L.pos < L.e) hash_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)));
   }

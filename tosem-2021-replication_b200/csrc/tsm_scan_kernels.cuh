@@ -17,7 +17,7 @@
 
 namespace tsm {
 
-__constant__ uint32_t c_lut[512];                       // automaton byte classes: [0,256) PY, [256,512) C/C++/Java
+__constant__ uint32_t c_lut[256];                       // automaton byte classes (one table, tsm_device.cuh)
 __constant__ uint32_t c_elut[256];                      // bare-assert operator automaton (k_classify)
 __constant__ uint8_t c_cat_slot[TSM_CAT_SLOTS];         // perfect hash slot -> category id
 __constant__ uint16_t c_cat_off[TSM_CAT_NAMED + 1];
@@ -80,8 +80,8 @@ __device__ __forceinline__ void line_init(LineState& L, uint32_t s, uint32_t e) 
   L.pos = (s == e) ? e : (s & ~7u);
 }
 
-// One 8-byte block.  Files without a scannable extension run the same code on an all-zero table
-// (nothing ever matches): one instantiation keeps the kernel small enough for the instruction cache.
+// One 8-byte block of a lane-per-line walk (long-line slow path, k_hash_lines).  Files without a scannable
+// extension run the same code: their pattern ends are simply never looked at.
 __device__ __forceinline__ void line_block(LineState& L, unsigned long long w, const uint32_t* lut, uint32_t first) {
   const uint32_t pos = L.pos;
   if (pos < L.s || pos + 8 > L.e) {                      // first / last block: zero the bytes outside the line
@@ -160,8 +160,7 @@ __device__ __forceinline__ uint32_t flag_nibble(uint32_t A, uint32_t g1, uint32_
   return ((A & (AF_ASSERT | AF_EXPECT)) ? 1u : 0u) | ((A & g1) ? 2u : 0u) | ((A & g2) ? 4u : 0u) | ((A & g3) ? 8u : 0u);
 }
 __device__ __forceinline__ uint32_t flag_nibble_ext(uint32_t A, int ext) {
-  return ext == TSM_EXT_PY ? flag_nibble(A, PY_DEF, PY_CLASS, PY_STF)
-                           : flag_nibble(A, CJ_TEST, CJ_BRACE | CJ_CLASS | CJ_VOID, CJ_STF);
+  return ext == TSM_EXT_PY ? flag_nibble(A, PY_G1, PY_G2, A_STF) : flag_nibble(A, CJ_G1, CJ_G2, A_STF);
 }
 
 // Finish one line: h0 = Mersenne-61 value of its bytes (SPEC section 3, trailing CR still inside), nib = its
@@ -177,8 +176,7 @@ __device__ __forceinline__ uint32_t line_finish_h(uint32_t s, uint32_t e, unsign
       --len;
       const unsigned long long cr = rotl61(0x0Dull, (8u * len) % 61u);
       h = h >= cr ? h - cr : h + M61 - cr;
-    }
-    h = canon61(h);
+    }                                                    // h0 is canonical (< 2^61 - 1) and the CR step keeps it so
   }
   ac.lines++;
   ac.digest += mix_hash(h, len);
@@ -218,17 +216,24 @@ __device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, uint32_t n, 
   return __shfl_sync(0xffffffffu, base, 0);
 }
 
+// The automaton table of k_scan sits at the start of the dynamic shared memory: a compile-time address.
+__device__ __forceinline__ const uint32_t* scan_lut() {
+  extern __shared__ __align__(128) uint8_t smem[];
+  return reinterpret_cast<const uint32_t*>(smem);
+}
+
 // Eight automaton steps over one 8-byte word; A collects every state of the word.
-__device__ __forceinline__ void step8(unsigned long long w, const uint32_t* lut, uint32_t first, uint32_t& D, uint32_t& A) {
+__device__ __forceinline__ void step8(unsigned long long w, uint32_t& D, uint32_t& A) {
+  const uint32_t* lut = scan_lut();
   const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | first) & lut[__byte_perm(lo, 0, 0x4440 + k)];
+    D = ((D + D) | A_FIRST) & lut[__byte_perm(lo, 0, 0x4440 + k)];
     A |= D;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | first) & lut[__byte_perm(hi, 0, 0x4440 + k)];
+    D = ((D + D) | A_FIRST) & lut[__byte_perm(hi, 0, 0x4440 + k)];
     A |= D;
   }
 }
@@ -241,18 +246,18 @@ __device__ __forceinline__ void flag_or(uint8_t* wb, uint32_t rel, uint32_t A) {
 // Pass 2b: a word that holds both a pattern end and a newline - walk its bytes one at a time so that
 // every match lands on its own line.  entry = word index | line index at the word's first byte << 10.
 // The automaton state in front of the word follows from the eight bytes before it (no pattern is longer).
-__device__ __noinline__ void resolve_word(uint8_t* wb, const uint32_t* lut, uint32_t fin, uint32_t first, uint32_t wlo,
-                                          uint32_t entry) {
+__device__ __noinline__ void resolve_word(uint8_t* wb, uint32_t fin, uint32_t wlo, uint32_t entry) {
   const uint32_t k = entry & 1023u, pos = 8u * k;
   uint32_t idx = (entry >> 10) - wlo;
   const uint32_t l = k / 17u, i = k - 17u * l;
   uint32_t nl8 = (reinterpret_cast<const uint32_t*>(wb + OFF_MSK)[(i >> 2) * 32u + l] >> (8u * (i & 3u))) & 0xFFu;
   uint32_t D = 0, A = 0;
-  if (pos > PRE) step8(*reinterpret_cast<const unsigned long long*>(wb + pos - 8), lut, first, D, A);
+  if (pos > PRE) step8(*reinterpret_cast<const unsigned long long*>(wb + pos - 8), D, A);
   unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + pos);
+  const uint32_t* lut = scan_lut();
 #pragma unroll 1
   for (int b = 0; b < 8; ++b) {
-    D = ((D + D) | first) & lut[(uint32_t)w & 0xFFu];
+    D = ((D + D) | A_FIRST) & lut[(uint32_t)w & 0xFFu];
     if (D & fin) flag_or(wb, idx, D);
     idx += nl8 & 1u;
     nl8 >>= 1;
@@ -269,8 +274,7 @@ __device__ __noinline__ void resolve_word(uint8_t* wb, const uint32_t* lut, uint
 //               Mersenne value of any byte range as a difference of two such prefixes
 // then one warp scan turns the stripe totals into the absolute prefix at every stripe start.
 // Not inlined on purpose: the hot loop gets its own register allocation.
-__device__ __noinline__ void walk_stripes(uint8_t* wb, const uint32_t* lut, uint32_t fin, uint32_t first, uint32_t wlo,
-                                          uint32_t base_all, int lane) {
+__device__ __noinline__ void walk_stripes(uint8_t* wb, uint32_t fin, uint32_t wlo, uint32_t base_all, int lane) {
   const uint32_t pos0 = (uint32_t)lane * STRIPE;
   uint8_t* sp = wb + pos0;
   const uint32_t* msk = reinterpret_cast<const uint32_t*>(wb + OFF_MSK) + lane;
@@ -279,7 +283,7 @@ __device__ __noinline__ void walk_stripes(uint8_t* wb, const uint32_t* lut, uint
   uint32_t D = 0;
   if (lane) {                                            // state in front of the stripe
     uint32_t A = 0;
-    step8(*reinterpret_cast<const unsigned long long*>(sp - 8), lut, first, D, A);
+    step8(*reinterpret_cast<const unsigned long long*>(sp - 8), D, A);
   }
   unsigned long long R = 0;
   uint32_t idxg = base_all - wlo;                        // window-relative line index at the group's first byte
@@ -292,7 +296,7 @@ __device__ __noinline__ void walk_stripes(uint8_t* wb, const uint32_t* lut, uint
       const uint32_t off = 32u * g + 8u * k;
       const unsigned long long w = *reinterpret_cast<const unsigned long long*>(sp + off);
       uint32_t A = 0;
-      step8(w, lut, first, D, A);
+      step8(w, D, A);
       R = (R >> 3) + ((R & 7ull) << 58) + fold61(w);      // lazily reduced: stays below 2^63
       if ((k & (RW_STRIDE - 1u)) == RW_STRIDE - 1u && g < 4)   // checkpoint behind every RW_STRIDE-th word (not the 17th)
         rw[(4u * g + k) >> RW_SHIFT] = R;
@@ -303,7 +307,7 @@ __device__ __noinline__ void walk_stripes(uint8_t* wb, const uint32_t* lut, uint
         const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(wb + OFF_CTL), 1u);
         const uint32_t entry = ((pos0 + off) >> 3) | ((idx + wlo) << 10);
         if (slot < Q_CAP) reinterpret_cast<uint32_t*>(wb + OFF_Q)[slot] = entry;
-        else resolve_word(wb, lut, fin, first, wlo, entry);
+        else resolve_word(wb, fin, wlo, entry);
       }
     }
     idxg += __popc(mg);
@@ -323,7 +327,7 @@ __device__ __noinline__ void walk_stripes(uint8_t* wb, const uint32_t* lut, uint
   __syncwarp();
   const uint32_t nq = min(*reinterpret_cast<const uint32_t*>(wb + OFF_CTL), Q_CAP);
   for (uint32_t t = (uint32_t)lane; t < nq; t += 32)
-    resolve_word(wb, lut, fin, first, wlo, reinterpret_cast<const uint32_t*>(wb + OFF_Q)[t]);
+    resolve_word(wb, fin, wlo, reinterpret_cast<const uint32_t*>(wb + OFF_Q)[t]);
   __syncwarp();
 }
 
@@ -338,7 +342,7 @@ __device__ __forceinline__ unsigned long long prefix_at(const uint8_t* wb, uint3
     R = (R >> 3) + ((R & 7ull) << 58) + fold61(*reinterpret_cast<const unsigned long long*>(wb + 8u * (k - i + t)));
   unsigned long long loc = (R >> 3) + ((R & 7ull) << 58);                // frame of word k
   if (b) loc += *reinterpret_cast<const unsigned long long*>(wb + 8u * k) & ((1ull << (8u * b)) - 1ull);
-  return *reinterpret_cast<const unsigned long long*>(wb + OFF_BASE + 8u * l) + rotl61(canon61(loc), r3k);
+  return *reinterpret_cast<const unsigned long long*>(wb + OFF_BASE + 8u * l) + rotl61(fold61(fold61(loc)), r3k);
 }
 
 // Pass 3: balanced finalise, one lane per line: hash = difference of two prefixes, flags from the
@@ -463,9 +467,8 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
   }
 }
 
-__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lut, const uint32_t* lc,
-                                              uint32_t first, uint8_t* wb, uint32_t f, uint32_t cb, uint32_t fo,
-                                              uint32_t size, int ext, int lane) {
+__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t f,
+                                              uint32_t cb, uint32_t fo, uint32_t size, int ext, int lane) {
   const uint8_t* buf = wb;
   uint16_t* tab = reinterpret_cast<uint16_t*>(wb + OFF_TAB);
   const uint32_t ce = min(cb + CH, size);
@@ -539,7 +542,7 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
     for (uint32_t i = (uint32_t)lane; i < cnt + 2u; i += 32) reinterpret_cast<uint32_t*>(wb + OFF_FLAGS)[i] = 0u;
     if (lane == 0) *reinterpret_cast<uint32_t*>(wb + OFF_CTL) = 0u;
     __syncwarp();
-    walk_stripes(wb, lut, lc[0], first, wstart, base_all, lane);         // pass 2 (the window's flag words)
+    walk_stripes(wb, lc[0], wstart, base_all, lane);         // pass 2 (the window's flag words)
     if (wstart + cnt >= total) break;                    // last window: the tail line joins it below
     drain(p, wb, lc, cnt, skip_first, next_start, f, cb, ext, lane, ac);
   }
@@ -559,7 +562,7 @@ __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_
     ++cnt;
   }
   drain(p, wb, lc, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-  if (tail_long && lane == 0) long_line(p, lut, first, f, fo, size, ext, cb + tail_start - PRE, ac);
+  if (tail_long && lane == 0) long_line(p, scan_lut(), A_FIRST, f, fo, size, ext, cb + tail_start - PRE, ac);
   // ---- per-file counters: warp reduce (the digest as three partial sums: low halves keep their carries),
   //      then one store (single-chunk file) or one atomic per counter
   ac.lines = __reduce_add_sync(0xffffffffu, ac.lines);
@@ -617,14 +620,13 @@ __device__ __forceinline__ Unit claim_unit(const ScanParams& p, uint32_t n_units
 
 __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) PY, [256,512) C family, [512,768) zero, then 3 x 4 constants
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_all[i] = i < 512 ? c_lut[i] : 0u;
-  if (threadIdx.x < 12) {                                // per language: all pattern ends, then the three header groups
-    const uint32_t py[4] = {AF_ASSERT | AF_EXPECT | PY_DEF | PY_CLASS | PY_STF, PY_DEF, PY_CLASS, PY_STF};
-    const uint32_t cj[4] = {AF_ASSERT | AF_EXPECT | CJ_TEST | CJ_CLASS | CJ_VOID | CJ_BRACE | CJ_STF, CJ_TEST,
-                            CJ_BRACE | CJ_CLASS | CJ_VOID, CJ_STF};
-    const int t = threadIdx.x;
-    lut_all[768 + t] = t < 4 ? py[t] : (t < 8 ? cj[t - 4] : 0u);
+  uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) the automaton table, then 3 x 4 per-language masks
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[i] = c_lut[i];
+  if (threadIdx.x < 12) {                                // per language (PY, C family, none): all pattern ends that count, then the header groups
+    const int t = threadIdx.x, lang = t >> 2, q = t & 3;
+    const uint32_t g1 = lang == 0 ? PY_G1 : CJ_G1, g2 = lang == 0 ? PY_G2 : CJ_G2;
+    const uint32_t v = q == 0 ? (AF_ASSERT | AF_EXPECT | g1 | g2 | A_STF) : (q == 1 ? g1 : (q == 2 ? g2 : A_STF));
+    lut_all[256 + t] = lang == 2 ? 0u : v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -651,9 +653,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(Scan
     while (!mbar_try_wait(bar, phase)) {}
     phase ^= 1;
     const uint32_t lang = cur.ext == 0 ? 2u : (cur.ext == TSM_EXT_PY ? 0u : 1u);
-    const uint32_t first = cur.ext == 0 ? 0u : (cur.ext == TSM_EXT_PY ? PY_FIRST : CJ_FIRST);
-    process_chunk(p, lut_all + 256u * lang, lut_all + 768u + 4u * lang, first, wb, cur.f, cur.cb, cur.fo, cur.size,
-                  cur.ext, lane);
+    process_chunk(p, lut_all + 256u + 4u * lang, wb, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
     __syncwarp();
     cur = nxt;
   }
