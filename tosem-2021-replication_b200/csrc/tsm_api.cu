@@ -315,7 +315,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     }
     if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);
-    const size_t hist = sizeof(uint32_t) * (512 + (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0));
+    const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
     k_classify<<<c->sms * 8, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
     cudaEventRecord(ev[4], st);                           // (slot of the former k_totals, now fused into k_classify)

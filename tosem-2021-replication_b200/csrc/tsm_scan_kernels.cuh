@@ -19,9 +19,10 @@ namespace tsm {
 
 __constant__ uint32_t c_lut[256];                       // automaton byte classes (one table, tsm_device.cuh)
 __constant__ uint32_t c_elut[256];                      // bare-assert operator automaton (k_classify)
-__constant__ uint8_t c_cat_slot[TSM_CAT_SLOTS];         // perfect hash slot -> category id
-__constant__ uint16_t c_cat_off[TSM_CAT_NAMED + 1];
-__constant__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
+// category tables: read once per block of k_classify into shared memory (coalesced, hence plain device memory)
+__device__ uint8_t c_cat_slot[TSM_CAT_SLOTS];            // perfect hash slot -> category id
+__device__ uint16_t c_cat_off[TSM_CAT_NAMED + 1];
+__device__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
 
 // ================================================================================= k_plan
 // One lane per file: units = ceil(len / CH); the warp reserves a contiguous range of the unit
@@ -665,6 +666,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(Scan
 // stripped start, the right-stripped end and the last identifier L; everything else (gtest stem,
 // bare-assert operators, table lookup of L, statement hash) touches only the few bytes it needs.
 constexpr uint32_t CC_W = 1, CC_IDENT = 2, CC_STOP = 4;  // byte classes: blank, [A-Za-z0-9_], '(' or LF
+constexpr uint32_t CLS_CAT_OFF_N = (TSM_CAT_NAMED + 2) & ~1u;            // u16 entries (even count keeps the blob 4-byte aligned)
+constexpr uint32_t CLS_CAT_WORDS = ((TSM_CAT_SLOTS + 2 * CLS_CAT_OFF_N + TSM_CAT_BLOB_LEN + 15) / 16) * 4;   // (keeps the queue 16-byte aligned)
+constexpr uint32_t CLS_SMEM_BASE = 4 * (512 + CLS_CAT_WORDS + 4 * 1024 + 4);   // bytes in front of the histogram (tables + BQ_CAP queue)
 constexpr uint32_t E_FIRST = (1u << 0) | (1u << 5) | (1u << 9) | (1u << 17) | (1u << 21) | (1u << 23) | (1u << 25) |
                              (1u << 27) | (1u << 29) | (1u << 30);
 
@@ -718,19 +722,65 @@ __device__ __forceinline__ int stem_lookup(FileBytes& rd, uint32_t s, uint32_t n
   }
 }
 
+// SPEC section 6 rule 2 on e = T[7:] of a bare "assert <expr>": one Shift-And pass over e for the ten
+// operator patterns (table built in tsm_api.cu), 8 bytes per step:
+//  " not " 0-4 | " in " 5-8 | " is not " 9-16 | "True" 17-20 | "==" 21-22 | "!=" 23-24 | "<=" 25-26 |
+//  ">=" 27-28 | "<" 29 | ">" 30   (final bits 4, 8, 16, 20, 22, 24, 26, 28, 29, 30)
+__device__ __forceinline__ int bare_assert_category(FileBytes& rd, uint32_t e0, uint32_t en, const uint32_t* elut) {
+  if (en >= 4 && (uint32_t)rd.get8(e0) == 0x20746F6Eu) return 2;        // "not "
+  uint32_t D = 0, A = 0;
+  for (uint32_t a = 0; a < en; a += 8) {                 // bytes behind the end become zeros (match nothing)
+    unsigned long long w = rd.get8(e0 + a);
+    if (en - a < 8) w &= (1ull << (8u * (en - a))) - 1ull;
+    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { D = ((D + D) | E_FIRST) & elut[__byte_perm(lo, 0, 0x4440 + k)]; A |= D; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { D = ((D + D) | E_FIRST) & elut[__byte_perm(hi, 0, 0x4440 + k)]; A |= D; }
+  }
+  if (((A & (1u << 4)) && (A & (1u << 8))) || (A & (1u << 16))) return 4;   // not ... in / is not
+  if (A & (1u << 20)) return 3;                          // True
+  if (A & (1u << 22)) return 1;                          // ==
+  if (A & (1u << 24)) return 2;                          // !=
+  if (A & (1u << 26)) return 8;                          // <=
+  if (A & (1u << 28)) return 6;                          // >=
+  if (A & (1u << 29)) return 7;                          // <
+  if (A & (1u << 30)) return 5;                          // >
+  return 3;
+}
+
+constexpr uint32_t BQ_CAP = 1024;                        // bare-assert expressions a block of k_classify defers (16 B each)
+
 __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
-  extern __shared__ uint32_t csm[];                      // [256] byte classes, then [n_groups][K] histogram
+  extern __shared__ __align__(16) uint32_t csm[];        // byte classes, operator table, category tables, deferral queue, [n_groups][K] histogram
   uint32_t* cls = csm;
   uint32_t* elut = csm + 256;
-  uint32_t* hist = csm + 512;
+  uint8_t* cat_slot = reinterpret_cast<uint8_t*>(csm + 512);             // copies of the constant tables: the lanes of a
+  uint16_t* cat_off = reinterpret_cast<uint16_t*>(cat_slot + TSM_CAT_SLOTS);   // warp look up different names (divergent
+  uint8_t* cat_blob = reinterpret_cast<uint8_t*>(cat_off + CLS_CAT_OFF_N);     // constant-memory reads would serialise)
+  uint4* bq = reinterpret_cast<uint4*>(csm + 512 + CLS_CAT_WORDS);       // deferred bare asserts: file, e0, en, event slot
+  uint32_t* bqn = csm + 512 + CLS_CAT_WORDS + 4 * BQ_CAP;
+  uint32_t* hist = bqn + 4;
   const bool use_smem = p.n_groups <= 16;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const uint32_t c = (uint32_t)i;
     cls[i] = (is_w(c) ? CC_W : 0u) | (is_ident(c) ? CC_IDENT : 0u) | ((c == '(' || c == '\n') ? CC_STOP : 0u);
     elut[i] = c_elut[i];
   }
+  for (int i = threadIdx.x; i < TSM_CAT_SLOTS; i += blockDim.x) cat_slot[i] = c_cat_slot[i];
+  for (int i = threadIdx.x; i < TSM_CAT_NAMED + 1; i += blockDim.x) cat_off[i] = c_cat_off[i];
+  for (int i = threadIdx.x; i < TSM_CAT_BLOB_LEN; i += blockDim.x) cat_blob[i] = (uint8_t)c_cat_blob[i];
   if (use_smem) for (int i = threadIdx.x; i < p.n_groups * TSM_K; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x == 0) *bqn = 0;
   __syncthreads();
+  auto count = [&](uint32_t f, int cat) {                // cross-file aggregate: [group][category]
+    const uint32_t g = p.grp ? p.grp[f] : 0u;
+    if (use_smem) atomicAdd(&hist[g * TSM_K + cat], 1u);
+    else {
+      atomicAdd(&p.counts[(size_t)g * TSM_K + cat], 1ull);
+      atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + cat], 1ull);
+    }
+  };
   const uint32_t n = min(p.ctrl->n_cand, p.cand_cap);
   const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -761,6 +811,7 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     // ---- category (SPEC section 6), first match wins
     int cat = 0;
     bool done = false;
+    uint32_t def_e0 = 0, def_en = 0;                     // def_en != 0: category decided by the deferred operator pass
     if (Ln >= 7) {                                       // rule 1: EXPECT_x / ASSERT_x
       const unsigned long long h7 = low_bytes(rd.get8(Ls), 7);
       if (h7 == 0x5F544345505845ull || h7 == 0x5F545245535341ull) { cat = stem_lookup(rd, Ls + 7, Ln - 7); done = true; }
@@ -771,29 +822,7 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
       if (a6 && tlen == 6) { cat = 3; done = true; }
       else if (a6 && tlen >= 8 && ((h >> 48) & 0xFF) == 0x20) {
         done = true;
-        const uint32_t e0 = t0 + 7, en = tlen - 7;       // e = T[7:]
-        // one Shift-And pass over e for the ten operator patterns of rule 2 (table built in tsm_api.cu):
-        //  " not " 0-4 | " in " 5-8 | " is not " 9-16 | "True" 17-20 | "==" 21-22 | "!=" 23-24 | "<=" 25-26 |
-        //  ">=" 27-28 | "<" 29 | ">" 30   (final bits 4, 8, 16, 20, 22, 24, 26, 28, 29, 30)
-        const bool f_pre = en >= 4 && (uint32_t)rd.get8(e0) == 0x20746F6Eu;          // "not "
-        uint32_t D = 0, A = 0;
-        for (uint32_t a = 0; a < en; ++a) {
-          D = ((D + D) | E_FIRST) & elut[rd.get(e0 + a)];
-          A |= D;
-        }
-        const bool f_not = A & (1u << 4), f_in = A & (1u << 8), f_isnot = A & (1u << 16), f_true = A & (1u << 20);
-        const bool eq = A & (1u << 22), ne = A & (1u << 24), le = A & (1u << 26), ge = A & (1u << 28);
-        const bool lt = A & (1u << 29), gt = A & (1u << 30);
-        if (f_pre) cat = 2;
-        else if ((f_not && f_in) || f_isnot) cat = 4;
-        else if (f_true) cat = 3;
-        else if (eq) cat = 1;
-        else if (ne) cat = 2;
-        else if (le) cat = 8;
-        else if (ge) cat = 6;
-        else if (lt) cat = 7;
-        else if (gt) cat = 5;
-        else cat = 3;
+        def_e0 = t0 + 7; def_en = tlen - 7;              // e = T[7:]: the operator pass runs later, with every lane busy
       }
     }
     if (!done && Ln >= 6) {                              // rules 3-5 on L
@@ -802,24 +831,32 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
         if (Ln == 7 && ((h >> 48) & 0xFF) == '_') cat = 3;
         else {
           cat = TSM_CAT_OTHER;
-          uint32_t hh = 0x811C9DC5u;
-          for (uint32_t j = 0; j < Ln; ++j) hh = (hh ^ rd.get(Ls + j)) * 0x01000193u;
-          const int id = c_cat_slot[(hh * TSM_CAT_HASH_MULT) >> 23];
-          if (id && (uint32_t)(c_cat_off[id + 1] - c_cat_off[id]) == Ln) {
+          uint32_t hh = 0x811C9DC5u;                       // FNV-1a of L, 8 bytes per load
+          for (uint32_t j = 0; j < Ln; j += 8) {
+            unsigned long long w = rd.get8(Ls + j);
+            const uint32_t nb = min(8u, Ln - j);
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+              if (k < nb) hh = (hh ^ ((uint32_t)w & 0xFFu)) * 0x01000193u;
+              w >>= 8;
+            }
+          }
+          const int id = cat_slot[(hh * TSM_CAT_HASH_MULT) >> 23];
+          if (id && (uint32_t)(cat_off[id + 1] - cat_off[id]) == Ln) {
+            const uint8_t* name = cat_blob + cat_off[id];
             bool ok = true;
-            for (uint32_t j = 0; j < Ln; ++j) ok &= (rd.get(Ls + j) == (uint32_t)(uint8_t)c_cat_blob[c_cat_off[id] + j]);
+            for (uint32_t j = 0; j < Ln; j += 8) {
+              unsigned long long w = rd.get8(Ls + j);
+              const uint32_t nb = min(8u, Ln - j);
+              for (uint32_t k = 0; k < nb; ++k) { ok &= ((uint32_t)w & 0xFFu) == (uint32_t)name[j + k]; w >>= 8; }
+            }
             if (ok) cat = id;
           }
         }
       }
     }
-    // ---- aggregate + event
-    const uint32_t g = p.grp ? p.grp[f] : 0u;
-    if (use_smem) atomicAdd(&hist[g * TSM_K + cat], 1u);
-    else {
-      atomicAdd(&p.counts[(size_t)g * TSM_K + cat], 1ull);
-      atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + cat], 1ull);
-    }
+    // ---- event, then aggregate (or defer)
+    uint32_t ev_slot = 0xFFFFFFFFu;
     if (want_ev) {
       unsigned long long hacc = 0; uint32_t hr = 0;     // Mersenne-61 of T (SPEC section 3)
       for (uint32_t j = 0; j < tlen; ++j) {
@@ -830,11 +867,32 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
       if (slot < p.aev_cap) {
         tsm_assert_event ev;
         ev.file = f; ev.line_off = line_off; ev.stmt_off = t0;
-        ev.stmt_len = (uint16_t)min(tlen, 65535u); ev.cat = (uint16_t)cat;
+        ev.stmt_len = (uint16_t)min(tlen, 65535u); ev.cat = (uint16_t)cat;      // (patched by the deferred pass)
         ev.ident_off = Ls; ev.ident_len = (uint16_t)min(Ln, 65535u); ev.pad = 0;
         ev.stmt_hash = mix_hash(canon61(hacc), tlen);
         p.aev[slot] = ev;
+        ev_slot = slot;
       } else p.ctrl->overflow = 1;
+    }
+    if (def_en) {
+      const uint32_t slot = atomicAdd(bqn, 1u);
+      if (slot < BQ_CAP) { bq[slot] = make_uint4(f, def_e0, def_en, ev_slot); continue; }
+      cat = bare_assert_category(rd, def_e0, def_en, elut);              // queue full: decide here
+      if (ev_slot != 0xFFFFFFFFu) p.aev[ev_slot].cat = (uint16_t)cat;
+    }
+    count(f, cat);
+  }
+  // ---- deferred bare asserts: the block's queue, one expression per thread (the inline version kept 3 of 32
+  //      lanes busy for ~50 bytes of serial automaton each)
+  __syncthreads();
+  {
+    const uint32_t nq = min(*bqn, BQ_CAP);
+    for (uint32_t t = threadIdx.x; t < nq; t += blockDim.x) {
+      const uint4 e = bq[t];
+      FileBytes rd(p.arena + (size_t)(uint32_t)p.off[e.x]);
+      const int cat = bare_assert_category(rd, e.y, e.z, elut);
+      if (e.w != 0xFFFFFFFFu) p.aev[e.w].cat = (uint16_t)cat;
+      count(e.x, cat);
     }
   }
   // ---- totals of the per-file records (lines, assertion lines, headers, fixture headers) behind the table
