@@ -32,6 +32,7 @@ struct tsm_ctx {
   uint32_t* d_unit_file = nullptr;
   uint32_t* d_unit_begin = nullptr;
   uint32_t unit_cap = 0;
+  uint8_t* d_zero = nullptr;                // one allocation, zeroed by one memset per scan: ctrl | slab | counts
   Ctrl* d_ctrl = nullptr;
   SlabCtl* d_slab = nullptr;                // [kMaxSlabs]
   cudaStream_t copy_stream = nullptr;       // H2D of arena slabs, overlapped with the scan of earlier slabs
@@ -123,12 +124,11 @@ extern "C" void tsm_destroy(tsm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_arena); cudaFree(c->d_off); cudaFree(c->d_len); cudaFree(c->d_ext); cudaFree(c->d_grp);
-  cudaFree(c->d_unit_file); cudaFree(c->d_unit_begin); cudaFree(c->d_ctrl); cudaFree(c->d_stats);
-  cudaFree(c->d_slab);
+  cudaFree(c->d_unit_file); cudaFree(c->d_unit_begin); cudaFree(c->d_zero); cudaFree(c->d_stats);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (cudaEvent_t e : c->slab_ev) if (e) cudaEventDestroy(e);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);
-  cudaFree(c->d_cand); cudaFree(c->d_hev); cudaFree(c->d_aev); cudaFree(c->d_counts);
+  cudaFree(c->d_cand); cudaFree(c->d_hev); cudaFree(c->d_aev);
   if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
   for (auto& set : c->ev) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
   delete c;
@@ -166,14 +166,18 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   A((void**)&c->d_grp, sizeof(uint16_t) * (size_t)max_files);
   A((void**)&c->d_unit_file, sizeof(uint32_t) * (size_t)c->unit_cap);
   A((void**)&c->d_unit_begin, sizeof(uint32_t) * (size_t)c->unit_cap);
-  A((void**)&c->d_ctrl, sizeof(Ctrl));
-  A((void**)&c->d_slab, sizeof(SlabCtl) * tsm_ctx::kMaxSlabs);
+  {
+    const size_t slab_off = 256, counts_off = slab_off + (sizeof(SlabCtl) * tsm_ctx::kMaxSlabs + 255) / 256 * 256;
+    A((void**)&c->d_zero, counts_off + sizeof(unsigned long long) * ((size_t)(max_groups + 1) * TSM_K + 4));
+    c->d_ctrl = reinterpret_cast<Ctrl*>(c->d_zero);
+    c->d_slab = reinterpret_cast<SlabCtl*>(c->d_zero + slab_off);
+    c->d_counts = reinterpret_cast<unsigned long long*>(c->d_zero + counts_off);
+  }
   if (rc == TSM_OK && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = TSM_E_CUDA;
   for (cudaEvent_t& e : c->slab_ev) if (rc == TSM_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = TSM_E_CUDA;
   if (rc == TSM_OK && cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming) != cudaSuccess) rc = TSM_E_CUDA;
   A((void**)&c->d_stats, sizeof(tsm_file_stat) * (size_t)max_files);
   A((void**)&c->d_cand, sizeof(unsigned long long) * (size_t)c->max_events);
-  A((void**)&c->d_counts, sizeof(unsigned long long) * ((size_t)(max_groups + 1) * TSM_K + 4));
   if (rc == TSM_OK && cudaHostAlloc((void**)&c->h_ctrl, sizeof(Ctrl) + 64, cudaHostAllocDefault) != cudaSuccess) rc = TSM_E_CUDA;
   for (auto& set : c->ev) for (cudaEvent_t& e : set) if (rc == TSM_OK && cudaEventCreate(&e) != cudaSuccess) rc = TSM_E_CUDA;
   if (rc == TSM_OK) {
@@ -275,11 +279,9 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
   ScanParams p = make_params(c, flags);
   const int n = c->n_files;
   c->launches = 0;
-  CU(cudaMemsetAsync(c->d_ctrl, 0, sizeof(Ctrl), st));
-  CU(cudaMemsetAsync(c->d_slab, 0, sizeof(SlabCtl) * tsm_ctx::kMaxSlabs, st));
-  CU(cudaMemsetAsync(c->d_counts, 0, sizeof(unsigned long long) * ((size_t)(c->n_groups + 1) * TSM_K + 4), st));
-  if (n) {
-    CU(cudaMemsetAsync(c->d_stats, 0, sizeof(tsm_file_stat) * (size_t)n, st));
+  CU(cudaMemsetAsync(c->d_zero, 0, (size_t)(reinterpret_cast<uint8_t*>(c->d_counts) - c->d_zero) +
+                     sizeof(unsigned long long) * ((size_t)(c->n_groups + 1) * TSM_K + 4), st));   // ctrl | slab | counts
+  if (n) {                                               // (k_plan zeroes the per-file records that k_scan adds into)
     // slab boundaries (file indices): one slab when resident, ~32 MiB of arena each when streaming
     std::vector<int32_t> cut{0};
     if (host) {

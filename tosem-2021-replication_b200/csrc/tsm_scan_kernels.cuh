@@ -31,7 +31,10 @@ __global__ void k_plan(ScanParams p) {
   const int f = p.f_begin + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t nu = 0;
-  if (f < p.f_end) nu = ((uint32_t)p.len[f] + CH - 1) / CH;
+  if (f < p.f_end) {
+    nu = ((uint32_t)p.len[f] + CH - 1) / CH;
+    if (nu != 1) p.stats[f] = tsm_file_stat{0, 0, 0, 0, 0};   // several chunks add into it (one chunk: k_scan stores), none leave it zero
+  }
   uint32_t incl = nu;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
