@@ -57,7 +57,8 @@ __global__ void k_plan(ScanParams p) {
 //   stage   one 1-D TMA bulk copy (cp.async.bulk + mbarrier) of [chunk-16, chunk+4096+240) into shared
 //   pass 1  SWAR newline bits, one 136-byte stripe per lane; one warp scan orders them into the line table
 //   pass 2  stripe walk (all lanes busy whatever the line lengths): Shift-And automaton (one LDS per
-//           byte), pattern ends -> per-line flag bytes, Mersenne-61 running prefix behind every word
+//           byte), pattern ends -> per-line flag words, Mersenne-61 running prefix (checkpoint every 4 words)
+//   pass 2b words with a newline AND a pattern end, byte by byte, one lane per word
 //   pass 3  balanced finalise, one lane per line: hash = difference of two prefixes, header / assertion flags
 //   pass 4  ballot compaction of candidate (and header-event) lines into the global lists
 // SWAR: 16-bit mask of the bytes equal to '\n' in a 16-byte vector.
