@@ -17,8 +17,39 @@ using namespace tsm;
 
 static const char* const kNames[TSM_K] = TSM_CAT_NAMES_INIT;
 
+// Scratch memory of the diff / statements calls: grow-only, kept by the ctx between calls (a cudaMalloc +
+// cudaFree pair per buffer and call costs more than the kernels of a C5-sized batch).
+struct ScratchPool {
+  struct Slot { void* p; size_t cap; bool used; };
+  std::vector<Slot> slots;
+  void* take(size_t bytes) {
+    int best = -1;
+    for (int i = 0; i < (int)slots.size(); ++i)
+      if (!slots[(size_t)i].used && slots[(size_t)i].cap >= bytes && (best < 0 || slots[(size_t)i].cap < slots[(size_t)best].cap)) best = i;
+    if (best < 0) {
+      for (size_t i = 0; i < slots.size(); ++i)           // replace a free slot that is too small rather than pile up
+        if (!slots[i].used) { cudaFree(slots[i].p); slots.erase(slots.begin() + (long)i); break; }
+      void* q = nullptr;
+      const size_t cap = bytes + bytes / 8 + 256;
+      if (cudaMalloc(&q, cap) != cudaSuccess) return nullptr;
+      slots.push_back(Slot{q, cap, true});
+      return q;
+    }
+    slots[(size_t)best].used = true;
+    return slots[(size_t)best].p;
+  }
+  void give(void* p) { for (Slot& s : slots) if (s.p == p) s.used = false; }
+  void clear() { for (Slot& s : slots) cudaFree(s.p); slots.clear(); }
+};
+static thread_local ScratchPool* t_pool = nullptr;        // pool of the ctx whose call runs on this thread
+struct PoolScope {
+  explicit PoolScope(ScratchPool* p) { t_pool = p; }
+  ~PoolScope() { t_pool = nullptr; }
+};
+
 struct tsm_ctx {
   int device = 0;
+  ScratchPool pool;
   int sms = 0;
   int64_t max_arena = 0;
   int32_t max_files = 0, max_groups = 0;
@@ -125,6 +156,7 @@ extern "C" void tsm_destroy(tsm_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_arena); cudaFree(c->d_off); cudaFree(c->d_len); cudaFree(c->d_ext); cudaFree(c->d_grp);
   cudaFree(c->d_unit_file); cudaFree(c->d_unit_begin); cudaFree(c->d_zero); cudaFree(c->d_stats);
+  c->pool.clear();
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (cudaEvent_t e : c->slab_ev) if (e) cudaEventDestroy(e);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);
@@ -437,6 +469,7 @@ extern "C" int tsm_reduce(tsm_ctx* c, const uint8_t* flags, const int32_t* repo,
   for (int32_t i = 0; i < n_rows; ++i)
     if (repo[i] < 0 || repo[i] >= n_repos || case_id[i] < 0 || case_id[i] >= n_cases) return TSM_E_ARG;
   CU(cudaSetDevice(c->device));
+  PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t words = ((size_t)n_cases + 31) / 32;
   const size_t nbits = (size_t)(n_flags + 1) * n_repos * words;
@@ -483,11 +516,11 @@ extern "C" void tsm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------- S8 diff
 namespace {
-struct DevBuf {                                           // cudaMalloc'd scratch, freed on scope exit
+struct DevBuf {                                           // device scratch from the ctx's pool, returned on scope exit
   void* p = nullptr;
   ~DevBuf() { reset(); }
-  void reset() { if (p) cudaFree(p); p = nullptr; }
-  bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
+  void reset() { if (p && t_pool) t_pool->give(p); p = nullptr; }
+  bool alloc(size_t bytes) { reset(); p = t_pool ? t_pool->take(bytes ? bytes : 16) : nullptr; return p != nullptr; }
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
@@ -550,6 +583,7 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
         return TSM_E_LAYOUT;
   }
   CU(cudaSetDevice(c->device));
+  PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   HostSide A, B;
   int rc = side_lines(olds, A, st, detail != nullptr);
@@ -628,6 +662,7 @@ extern "C" int tsm_statements(tsm_ctx* c, const tsm_corpus* k, int64_t* line_bas
     if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1])
       return TSM_E_LAYOUT;
   CU(cudaSetDevice(c->device));
+  PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   HostSide S;
   int rc = side_lines(k, S, st, false);                   // newline count, ordered line ends (and hashes)
