@@ -21,12 +21,14 @@
 //   tosem-scan body   <project-root>... [--out F]
 //   tosem-scan releases <snapshot-root>=<tag>... [--out F]
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <unistd.h>
 #include <filesystem>
 #include <fstream>
@@ -202,11 +204,27 @@ static void load_batch(const std::vector<FileEntry>& files, Batch& b) {
   b.arena = (uint8_t*)tsm_host_alloc(std::max<int64_t>(b.bytes, 128));
   if (!b.arena) die("pinned arena allocation failed (no CUDA device? there is no CPU fallback)");
   memset(b.arena, 0, (size_t)std::max<int64_t>(b.bytes, 128));
-  for (size_t i = 0; i < b.count; ++i) {
-    std::ifstream in(files[b.first + i].abs, std::ios::binary);
-    in.read((char*)b.arena + b.off[i], b.len[i]);
-    if (in.gcount() != b.len[i]) die("short read: " + files[b.first + i].abs);
-  }
+  // the reads of a batch run on a few host threads (a source tree is many small files: latency-bound)
+  const unsigned nt = std::max(1u, std::min({std::thread::hardware_concurrency(), 32u, (unsigned)((b.count + 63) / 64)}));
+  std::atomic<long> bad{-1};
+  auto reader = [&](unsigned t) {
+    for (size_t i = t; i < b.count && bad.load(std::memory_order_relaxed) < 0; i += nt) {
+      const int fd = open(files[b.first + i].abs.c_str(), O_RDONLY);
+      int64_t got = 0;
+      while (fd >= 0 && got < b.len[i]) {
+        const ssize_t r = read(fd, b.arena + b.off[i] + got, (size_t)(b.len[i] - got));
+        if (r <= 0) break;
+        got += r;
+      }
+      if (fd >= 0) close(fd);
+      if (got != b.len[i]) bad.store((long)i);
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back(reader, t);
+  reader(0);
+  for (std::thread& x : th) x.join();
+  if (bad.load() >= 0) die("short read: " + files[b.first + (size_t)bad.load()].abs);
 }
 
 struct ScanOut {
