@@ -260,7 +260,7 @@ __device__ __noinline__ void resolve_word(uint8_t* wb, uint32_t fin, uint32_t wl
   if (pos > PRE) step8(*reinterpret_cast<const unsigned long long*>(wb + pos - 8), D, A);
   unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + pos);
   const uint32_t* lut = scan_lut();
-#pragma unroll 1
+#pragma unroll
   for (int b = 0; b < 8; ++b) {
     D = ((D + D) | A_FIRST) & lut[(uint32_t)w & 0xFFu];
     if (D & fin) flag_or(wb, idx, D);
@@ -292,7 +292,11 @@ __device__ __noinline__ void walk_stripes(uint8_t* wb, uint32_t fin, uint32_t wl
   }
   unsigned long long R = 0;
   uint32_t idxg = base_all - wlo;                        // window-relative line index at the group's first byte
+#if TSM_WALK_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (uint32_t g = 0; g < 5; ++g) {
     const uint32_t mg = msk[g * 32u];
 #pragma unroll
