@@ -13,6 +13,7 @@
 // There is no reference kernel: the reference ships data only.  Rules cite
 // docs/SPEC.md, which cites the artefacts.
 #pragma once
+#include <type_traits>
 #include "tsm_device.cuh"
 
 namespace tsm {
@@ -132,8 +133,31 @@ __device__ __forceinline__ void hash_block(LineState& L, unsigned long long w) {
   L.pos = pos + 8;
 }
 
+struct SmemByte {                                        // byte source = the staged chunk
+  const uint8_t* b;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return b[i]; }
+  // number of leading 0x20 bytes among the 8 bytes at i (any alignment; the buffer is readable 8 bytes past any line)
+  __device__ __forceinline__ uint32_t spaces8(uint32_t i) const {
+    const uint32_t a = i & ~7u, sh = 8u * (i & 7u);
+    const unsigned long long lo = *reinterpret_cast<const unsigned long long*>(b + a);
+    const unsigned long long hi = *reinterpret_cast<const unsigned long long*>(b + a + 8);
+    const unsigned long long w = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    const unsigned long long x = w ^ 0x2020202020202020ull, k7 = 0x7F7F7F7F7F7F7F7Full;
+    const unsigned long long nz = (((x & k7) + k7) | x) & ~k7;           // 0x80 in every byte that is not a space
+    return nz ? ((uint32_t)__ffsll((long long)nz) - 1u) >> 3 : 8u;
+  }
+};
+struct GmemByte {                                        // byte source = the file in HBM (slow path)
+  const uint8_t* b;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(b + i); }
+};
+
 template <typename LoadByte>
 __device__ __forceinline__ bool starts_with(LoadByte lb, uint32_t s, uint32_t e, const char* pat, int n, bool need_ws) {
+  if constexpr (std::is_same<LoadByte, SmemByte>::value) {  // staged bytes: runs of spaces eight at a time
+    uint32_t r;
+    while (s + 8 <= e && (r = lb.spaces8(s)) != 0) { s += r; if (r < 8) break; }
+  }
   while (s < e && is_w(lb(s))) ++s;
   if (s + n + (need_ws ? 1 : 0) > e) return false;
   for (int k = 0; k < n; ++k)
@@ -150,14 +174,6 @@ __device__ __forceinline__ bool starts_with(LoadByte lb, uint32_t s, uint32_t e,
 
 struct Accum { uint32_t lines, asserts, hdrs, fixes; unsigned long long digest; };
 
-struct SmemByte {                                        // byte source = the staged chunk
-  const uint8_t* b;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return b[i]; }
-};
-struct GmemByte {                                        // byte source = the file in HBM (slow path)
-  const uint8_t* b;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(b + i); }
-};
 
 // The four facts pass 3 needs about a line, as one nibble: bit 0 = assertion pattern, bits 1..3 = the
 // language's header patterns (PY: def, class, TEST_F gate; C family: test, one of { class void, TEST_F gate).
@@ -292,11 +308,7 @@ __device__ __noinline__ void walk_stripes(uint8_t* wb, uint32_t fin, uint32_t wl
   }
   unsigned long long R = 0;
   uint32_t idxg = base_all - wlo;                        // window-relative line index at the group's first byte
-#if TSM_WALK_UNROLL
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
   for (uint32_t g = 0; g < 5; ++g) {
     const uint32_t mg = msk[g * 32u];
 #pragma unroll
