@@ -136,12 +136,16 @@ __device__ __forceinline__ void hash_block(LineState& L, unsigned long long w) {
 struct SmemByte {                                        // byte source = the staged chunk
   const uint8_t* b;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return b[i]; }
-  // number of leading 0x20 bytes among the 8 bytes at i (any alignment; the buffer is readable 8 bytes past any line)
-  __device__ __forceinline__ uint32_t spaces8(uint32_t i) const {
+  // the 8 bytes at i, any alignment (shared memory is readable 8 bytes past any line of the buffer)
+  __device__ __forceinline__ unsigned long long load8(uint32_t i) const {
     const uint32_t a = i & ~7u, sh = 8u * (i & 7u);
     const unsigned long long lo = *reinterpret_cast<const unsigned long long*>(b + a);
     const unsigned long long hi = *reinterpret_cast<const unsigned long long*>(b + a + 8);
-    const unsigned long long w = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+  }
+  // number of leading 0x20 bytes among the 8 bytes at i
+  __device__ __forceinline__ uint32_t spaces8(uint32_t i) const {
+    const unsigned long long w = load8(i);
     const unsigned long long x = w ^ 0x2020202020202020ull, k7 = 0x7F7F7F7F7F7F7F7Full;
     const unsigned long long nz = (((x & k7) + k7) | x) & ~k7;           // 0x80 in every byte that is not a space
     return nz ? ((uint32_t)__ffsll((long long)nz) - 1u) >> 3 : 8u;
