@@ -698,19 +698,29 @@ constexpr uint32_t E_FIRST = (1u << 0) | (1u << 5) | (1u << 9) | (1u << 17) | (1
 
 struct FileBytes {                                       // 8-byte buffered reader over one file in HBM
   const unsigned long long* base; uint32_t cur_blk; unsigned long long w;
-  __device__ __forceinline__ explicit FileBytes(const uint8_t* b)
-      : base(reinterpret_cast<const unsigned long long*>(b)), cur_blk(0xFFFFFFFFu), w(0) {}
+  // the first words of the candidate line, fetched by independent loads up front: one HBM / L2 latency per
+  // candidate instead of one per step of the parse
+  uint32_t blk0; unsigned long long w0, w1, w2, w3;
+  __device__ __forceinline__ FileBytes(const uint8_t* b, uint32_t first_byte)
+      : base(reinterpret_cast<const unsigned long long*>(b)), cur_blk(0xFFFFFFFFu), w(0), blk0(first_byte >> 3) {
+    w0 = __ldg(base + blk0); w1 = __ldg(base + blk0 + 1); w2 = __ldg(base + blk0 + 2); w3 = __ldg(base + blk0 + 3);
+  }
+  __device__ __forceinline__ unsigned long long word(uint32_t blk) const {
+    const uint32_t d = blk - blk0;
+    if (d < 4u) return d < 2u ? (d == 0u ? w0 : w1) : (d == 2u ? w2 : w3);
+    return __ldg(base + blk);
+  }
   __device__ __forceinline__ uint32_t get(uint32_t i) {
     const uint32_t blk = i >> 3;
-    if (blk != cur_blk) { w = __ldg(base + blk); cur_blk = blk; }
+    if (blk != cur_blk) { w = word(blk); cur_blk = blk; }
     return (uint32_t)(w >> (8u * (i & 7u))) & 0xFFu;
   }
-  // the 8 bytes at file offset i (unaligned), little-endian; bytes past the word pair are garbage-free
-  __device__ __forceinline__ unsigned long long get8(uint32_t i) {
+  // the 8 bytes at file offset i (unaligned), little-endian
+  __device__ __forceinline__ unsigned long long get8(uint32_t i) const {
     const uint32_t blk = i >> 3, sh = 8u * (i & 7u);
-    const unsigned long long lo = __ldg(base + blk);
+    const unsigned long long lo = word(blk);
     if (sh == 0) return lo;
-    return (lo >> sh) | (__ldg(base + blk + 1) << (64u - sh));
+    return (lo >> sh) | (word(blk + 1) << (64u - sh));
   }
 };
 
@@ -811,7 +821,7 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     const unsigned long long cd = p.cand[i];
     const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
     const uint32_t size = (uint32_t)p.len[f];
-    FileBytes rd(p.arena + (size_t)(uint32_t)p.off[f]);
+    FileBytes rd(p.arena + (size_t)(uint32_t)p.off[f], line_off);
     // ---- T = [t0, last): skip the indentation, find the first '(' / LF a word at a time (SWAR),
     //      strip blanks backwards; L = the identifier run that ends at `last`
     uint32_t q = line_off;
@@ -819,7 +829,7 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     const uint32_t t0 = q;
     uint32_t stop = size;
     for (uint32_t wb = t0 & ~7u; wb < size; wb += 8) {
-      unsigned long long w = __ldg(rd.base + (wb >> 3));
+      unsigned long long w = rd.word(wb >> 3);
       const unsigned long long x1 = w ^ 0x2828282828282828ull, x2 = w ^ 0x0A0A0A0A0A0A0A0Aull;
       const unsigned long long k7 = 0x7F7F7F7F7F7F7F7Full;
       unsigned long long z = (~(((x1 & k7) + k7) | x1 | k7)) | (~(((x2 & k7) + k7) | x2 | k7));   // 0x80 per '(' or LF
@@ -913,7 +923,7 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     const uint32_t nq = min(*bqn, BQ_CAP);
     for (uint32_t t = threadIdx.x; t < nq; t += blockDim.x) {
       const uint4 e = bq[t];
-      FileBytes rd(p.arena + (size_t)(uint32_t)p.off[e.x]);
+      FileBytes rd(p.arena + (size_t)(uint32_t)p.off[e.x], e.y);
       const int cat = bare_assert_category(rd, e.y, e.z, elut);
       if (e.w != 0xFFFFFFFFu) p.aev[e.w].cat = (uint16_t)cat;
       count(e.x, cat);
