@@ -212,6 +212,27 @@ def test_scan_two_gpus_matches_one(tmp_path):
     assert outs[0][2].replace("on 1 GPU(s)", "") == outs[1][2].replace("on 2 GPU(s)", "")
 
 
+@pytest.mark.gpu
+def test_scan_many_batches_match_one(tmp_path):
+    """`--batch-bytes` small: dozens of batches per GPU, each loaded by the background task while the previous
+    one is scanned; rows, summary and the aggregate table must not depend on the batching."""
+    import tosemscan as ts
+    root = tmp_path / "proj_tests"
+    os.makedirs(root)
+    c = ts.gen_corpus(33, 300, 1, n_groups=1, pinned=False)
+    for i in range(c.n_files):
+        ext = {1: "py", 2: "cc", 4: "java"}[int(c.ext[i])]
+        (root / ("f%04d_test.%s" % (i, ext))).write_bytes(c.file_bytes(i))
+    outs = []
+    for extra in ([], ["--batch-bytes", "65536"]):
+        tag = "b" if extra else "a"
+        rows_p, sum_p = str(tmp_path / ("rows_%s.csv" % tag)), str(tmp_path / ("sum_%s.csv" % tag))
+        out = subprocess.run([CLI, "scan", str(root), "--rows", rows_p, "--summary", sum_p] + extra, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        outs.append((out.stdout, open(rows_p, "rb").read(), open(sum_p, "rb").read()))
+    assert outs[0] == outs[1]
+
+
 def py_case_name(ext, line):
     s = line.strip(b" \t\r\x0b\x0c").decode("latin-1")
     if ext == 1:

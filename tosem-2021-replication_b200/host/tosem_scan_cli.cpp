@@ -15,7 +15,7 @@
 // into the pinned byte arena, method strings (S3, host side of SPEC section 5), CSV.  Every byte of the scan
 // itself goes through libtosemscan.so (sm_100a kernels); there is no CPU fallback.
 //
-//   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files]
+//   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]
 //   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
@@ -32,6 +32,7 @@
 #include <unistd.h>
 #include <filesystem>
 #include <fstream>
+#include <future>
 #include <map>
 #include <string>
 #include <thread>
@@ -235,19 +236,19 @@ struct ScanOut {
 };
 
 static int cmd_scan(const std::vector<std::string>& roots, const std::string& rows_path, const std::string& summary_path,
-                    int gpus, bool all_files) {
+                    int gpus, bool all_files, int64_t batch_bytes) {
   std::vector<FileEntry> files;
   for (size_t g = 0; g < roots.size(); ++g) walk(roots[g], (int)g, all_files, files);
   const int n_groups = (int)std::max<size_t>(roots.size(), 1);
   fprintf(stderr, "tosem-scan: %zu files selected under %zu root(s)\n", files.size(), roots.size());
-  // batches of consecutive files, each at most ~1 GiB of arena and 1M files
+  // batches of consecutive files, each at most ~1 GiB of arena (--batch-bytes) and 1M files
   std::vector<Batch> batches;
   {
     int64_t cur = 0; size_t first = 0;
     for (size_t i = 0; i < files.size(); ++i) {
       if (files[i].size >= (1ll << 30)) die("file larger than 1 GiB: " + files[i].abs);
       const int64_t padded = (files[i].size + 127) / 128 * 128;
-      if (i > first && (cur + padded > (1ll << 30) || i - first >= (1u << 20))) {
+      if (i > first && (cur + padded > batch_bytes || i - first >= (1u << 20))) {
         batches.emplace_back(first, i - first); first = i; cur = 0;
       }
       cur += padded;
@@ -292,9 +293,15 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
     int64_t* d_acc = nullptr;                               // running sum of the count tables of this GPU's batches
     cudaMalloc((void**)&d_acc, table * sizeof(int64_t));
     cudaMemsetAsync(d_acc, 0, table * sizeof(int64_t), st);
+    // host pipeline: while the GPU scans batch b (tsm_scan overlaps its H2D slabs with the kernels), a
+    // background task already reads the files of this GPU's next batch into its pinned arena
+    std::future<void> next_load;
+    if ((size_t)g < batches.size()) next_load = std::async(std::launch::async, [&files, &batches, g] { cudaSetDevice(g); load_batch(files, batches[(size_t)g]); });
     for (size_t b = g; b < batches.size(); b += gpus) {
       Batch& B = batches[b];
-      load_batch(files, B);
+      next_load.get();
+      if (b + gpus < batches.size())
+        next_load = std::async(std::launch::async, [&files, &batches, b, gpus, g] { cudaSetDevice(g); load_batch(files, batches[b + (size_t)gpus]); });
       tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, n_groups};
       ScanOut& o = outs[b];
       o.stats.resize(B.count);
@@ -770,7 +777,7 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
 
 static void usage() {
   fprintf(stderr,
-          "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files]\n"
+          "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]\n"
           "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
@@ -790,7 +797,8 @@ int main(int argc, char** argv) {
     else if (a.rfind("--", 0) == 0) { if (i + 1 >= argc) die("missing value for " + a); opt[a] = argv[++i]; }
     else pos.push_back(a);
   }
-  if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files); }
+  if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
+                                        opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30)); }
   if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"]); }
   if (cmd == "releases") { if (pos.empty()) die("releases needs <root>=<tag>..."); return cmd_releases(pos, opt["--out"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
