@@ -136,7 +136,8 @@ def test_reduce_tables(tmp_path):
     for i in range(600):
         repo = repos[int(rng.integers(0, 9))]
         rec = {"Index": str(i), "Labels": 'a "quoted", label\nwith a newline' if i % 50 == 0 else "x", "Cases": str(int(rng.integers(0, 120))) + repo[:2],
-               "Repo": repo, "status_test": str(int(rng.random() < 0.3)), "Error_Type": ["", "ValueError", "RuntimeError"][int(rng.integers(0, 3))],
+               "Repo": repo, "status_test": str(int(rng.random() < 0.3)), "Error_Type": ["", "ValueError", "RuntimeError", "Exception", "nullptr", "SyntaxError", "SchemaError", "FileError",
+                              "AssertionError", "Timeout", "DataError"][int(rng.integers(0, 11))],
                "negative_test": str(int(rng.random() < 0.2)), "logical_statement": "0", "logical_expression": str(int(rng.random() < 0.1)),
                "null_pointer": "0", "value_range": str(int(rng.random() < 0.4)), "Approximation_Type": ["", "rounding_tolence"][int(rng.integers(0, 2))],
                "checks_type": ["", "instance_check"][int(rng.integers(0, 2))], "regression": "0", "Integration": str(int(rng.random() < 0.05)),
@@ -154,6 +155,9 @@ def test_reduce_tables(tmp_path):
     cases = {r: {x["Cases"] for x in recs if x["Repo"] == r} for r in repos}
     row = {x[0]: x for x in s[1:]}
     for name, pred in [("status_analysis", lambda x: x["status_test"] == "1"), ("value_error", lambda x: x["Error_Type"] == "ValueError"),
+                       ("runtime_error", lambda x: x["Error_Type"] in ("RuntimeError", "Exception", "nullptr", "Timeout")),   # merged rows (SPEC section 9)
+                       ("AssertionError", lambda x: x["Error_Type"] in ("AssertionError", "SyntaxError")),
+                       ("FileError", lambda x: x["Error_Type"] in ("FileError", "SchemaError")),
                        ("logical_condition", lambda x: x["logical_statement"] == "1" or x["logical_expression"] == "1"),
                        ("rounding_tolence", lambda x: x["Approximation_Type"] == "rounding_tolence")]:
         for k, r in enumerate(repos):
