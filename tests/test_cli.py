@@ -129,14 +129,15 @@ def test_scan_rows_and_summary(tmp_path):
 def test_reduce_tables(tmp_path):
     rng = np.random.default_rng(5)
     repos = ["autokeras", "auto_sklearn", "tpot", "Ray", "DeepSpeech2", "google_automl", "nni", "Apollo", "Nupic"]
-    cols = ["Index", "Labels", "Cases", "Repo", "status_test", "Error_Type", "negative_test", "logical_statement",
+    cols = ["Index", "Labels", "Cases", "Repo", "Data", "Model", "status_test", "Error_Type", "negative_test", "logical_statement",
             "logical_expression", "null_pointer", "value_range", "Approximation_Type", "checks_type", "regression",
             "Integration", "mock_test", "API"]
     lines, recs = [cols], []
     for i in range(600):
         repo = repos[int(rng.integers(0, 9))]
         rec = {"Index": str(i), "Labels": 'a "quoted", label\nwith a newline' if i % 50 == 0 else "x", "Cases": str(int(rng.integers(0, 120))) + repo[:2],
-               "Repo": repo, "status_test": str(int(rng.random() < 0.3)), "Error_Type": ["", "ValueError", "RuntimeError", "Exception", "nullptr", "SyntaxError", "SchemaError", "FileError",
+               "Repo": repo, "Data": ["", "Distribution", "Validity", "Data Error", "Time behaviour"][int(rng.integers(0, 5))],
+               "Model": ["", "", "Resource Usage", "Compatibility"][int(rng.integers(0, 4))], "status_test": str(int(rng.random() < 0.3)), "Error_Type": ["", "ValueError", "RuntimeError", "Exception", "nullptr", "SyntaxError", "SchemaError", "FileError",
                               "AssertionError", "Timeout", "DataError"][int(rng.integers(0, 11))],
                "negative_test": str(int(rng.random() < 0.2)), "logical_statement": "0", "logical_expression": str(int(rng.random() < 0.1)),
                "null_pointer": "0", "value_range": str(int(rng.random() < 0.4)), "Approximation_Type": ["", "rounding_tolence"][int(rng.integers(0, 2))],
@@ -147,8 +148,8 @@ def test_reduce_tables(tmp_path):
     tax = tmp_path / "taxonomy.csv"
     with open(tax, "w", newline="", encoding="utf-8") as f:
         csv.writer(f, lineterminator="\r\n").writerows(lines)
-    sp, mp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv")
-    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp], capture_output=True, text=True)
+    sp, mp, pp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     s = read_csv(sp)
     assert s[0][:10] == ["Tests"] + repos
@@ -164,6 +165,16 @@ def test_reduce_tables(tmp_path):
             d = len({x["Cases"] for x in recs if x["Repo"] == r and pred(x)})
             v = round(round(100.0 * d / len(cases[r]), 4) / 1.1, 4)
             assert row[name][1 + k] == (("%.4f" % v).rstrip("0").rstrip(".") or "0"), (name, r)
+    # property table: rows = repositories, cells = 100 * distinct / (Apollo's case count)
+    pt = read_csv(pp)
+    assert pt[0][0] == "Repos" and len(pt[0]) == 22 and [x[0] for x in pt[1:]][:2] == ["auto_sklearn", "google_automl"]
+    prow = {x[0]: x for x in pt[1:]}
+    for name, labels in [("Data Distribution", {"Distribution"}), ("Data Validity", {"Validity", "Data Error"}),
+                         ("Efficiency", {"Time behaviour", "Resource Usage"}), ("Compatibility and Portability", {"Compatibility"})]:
+        j = pt[0].index(name)
+        for r in repos:
+            dd = len({x["Cases"] for x in recs if x["Repo"] == r and (x["Data"] in labels or x["Model"] in labels)})
+            assert prow[r][j] == (("%.4f" % round(100.0 * dd / len(cases["Apollo"]), 4)).rstrip("0").rstrip(".") or "0"), (name, r)
     m = {x[0]: x for x in read_csv(mp)[1:]}
     tot = sum(len(c) for c in cases.values())
     d = len({(x["Repo"], x["Cases"]) for x in recs if x["mock_test"] not in ("", "0")})

@@ -160,9 +160,20 @@ def test_g3_reduce_golden():
                 s = ("%.4f" % v).rstrip("0").rstrip(".") or "0"
                 assert s == str(d["want_strategy_cells"][j][k])
     ns = ok.shape[0]
-    tot = out[ns:].sum(axis=1)
     rep = d["method_reproduces"].astype(bool)
+    tot = out[ns:ns + len(rep)].sum(axis=1)
     assert np.array_equal(tot[rep], d["want_method_total_cases"][rep]) and int(rep.sum()) == 11
+    # RQ3 property table (tests_prop_rq3.csv): 100 * distinct / 216 (Apollo's case count), 17 of 21 columns exact
+    pok = d["property_cell_reproduces"]
+    assert pok.shape == (21, 9) and int(pok.sum()) == 172 and int((pok.sum(axis=1) == 9).sum()) == 17
+    p0 = ns + len(rep)
+    denom = int(cpr[list(d["repo_names"]).index("Apollo")])
+    assert denom == 216
+    for j in range(pok.shape[0]):
+        for k in range(pok.shape[1]):
+            if pok[j, k]:
+                s = ("%.4f" % round(100.0 * out[p0 + j, k] / denom, 4)).rstrip("0").rstrip(".") or "0"
+                assert s == str(d["want_property_cells"][j][k])
 
 
 def test_lcs_oracle_against_bruteforce():

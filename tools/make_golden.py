@@ -213,6 +213,25 @@ METHODS = [  # (row name in tests_methods_v2.csv, taxonomy column)
     ("api_test", "API"), ("threat", "ThreadTest"), ("blob", "blob_performance")]
 
 
+# RQ3 property table (tests_prop_rq3.csv): property -> Data / Model labels.  17 of the 21 sets are exact solutions of a
+# search against the nine shipped per-repository cells; Consistency, Features Importance, Concurrency and Anomaly are
+# not recoverable from taxonomy_test2.csv (their cells need labels this revision of the CSV does not carry).
+PROPERTIES = [
+    ("Consistency", ("Consistency",)), ("Data Distribution", ("Distribution",)),
+    ("Data Validity", ("Validity", "Data Error", "Data Error and Validity")), ("Completeness", ("Completeness",)),
+    ("Correctness", ("Correctness", "Accuracy & Precision", "Statistical Evidence/ explainability")),
+    ("Robustness", ("Robustness",)), ("Efficiency", ("Time behaviour", "Resource Usage", "Training Efficiency")),
+    ("Data Relation", ("Relation & Association", "Closeness", "Missing Data", "Data Differencing", "Data Quality")),
+    ("Scalability", ("Scalability",)), ("Features Importance", ("Feature Importance",)),
+    ("Data Restoration and Recoverability", ("Recoverability", "Data Restoration")),
+    ("Concurrency and Parallelism", ("Parallel Processing", "parallel")), ("Uncertainty", ("uncertainty",)),
+    ("Anomaly", ("Anomaly",)), ("Data Migration Loss and Corruption", ("Data Loss",)),
+    ("Bias and Fairness", ("Model Bias",)), ("Security and Privacy", ("Security", "Data Encapsulation")),
+    ("Data Uniqueness", ("Uniqueness",)), ("Data Timeliness", ("Timeliness",)),
+    ("Data Integration Integrity", ("Validate data integration and integrity",)),
+    ("Compatibility and Portability", ("Compatibility",))]
+
+
 def fmt4(x):
     s = ("%.4f" % x).rstrip("0").rstrip(".")
     return s if s else "0"
@@ -229,7 +248,7 @@ def golden_g3(ledger):
     rid = {r: i for i, r in enumerate(repos)}
     cases = sorted({r["Cases"] for r in rows}, key=lambda s: (len(s), s))
     cid = {c: i for i, c in enumerate(cases)}
-    names = [s[0] for s in STRATEGY] + ["m:" + m[0] for m in METHODS]
+    names = [s[0] for s in STRATEGY] + ["m:" + m[0] for m in METHODS] + ["p:" + q[0] for q in PROPERTIES]
     flags = np.zeros((len(rows), len(names)), np.uint8)
     for i, r in enumerate(rows):
         for j, (name, col, val) in enumerate(STRATEGY):
@@ -238,6 +257,8 @@ def golden_g3(ledger):
                 flags[i, j] |= r["logical_expression"].strip() == "1"
         for j, (_, col) in enumerate(METHODS):
             flags[i, len(STRATEGY) + j] = r[col].strip() not in ("", "0")
+        for j, (_, labels) in enumerate(PROPERTIES):
+            flags[i, len(STRATEGY) + len(METHODS) + j] = (r["Data"].strip() in labels) or (r["Model"].strip() in labels)
     repo = np.array([rid[r["Repo"]] for r in rows], np.int32)
     case = np.array([cid[r["Cases"]] for r in rows], np.int32)
     out, cpr = orc.reduce(flags, repo, case, len(repos), len(cases))
@@ -258,7 +279,21 @@ def golden_g3(ledger):
     # RQ4: distinct cases over all repos = sum over repos (a case belongs to one repo)
     for j, (name, _) in enumerate(METHODS):
         m_ok.append(int(out[len(STRATEGY) + j].sum()) == want4[name])
+    # RQ3 property table: rows = repos (shipped order), cells = 100 * distinct / 216
+    tp = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_prop_rq3.csv"), newline="")))
+    assert tp[0][1:] == [q[0] for q in PROPERTIES]
+    prop_rows = [r for r in tp[1:10]]
+    denom = int(cpr[rid["Apollo"]])           # 216: the shipped table divides every repository by Apollo's case count
+    prop_ok = np.zeros((len(PROPERTIES), len(repos)), np.uint8)
+    want_prop = [["" for _ in repos] for _ in PROPERTIES]
+    p0 = len(STRATEGY) + len(METHODS)
+    for r in prop_rows:
+        k = rid[r[0]]
+        for j in range(len(PROPERTIES)):
+            want_prop[j][k] = r[1 + j]
+            prop_ok[j, k] = fmt4(round(100.0 * out[p0 + j, k] / denom, 4)) == r[1 + j]
     np.savez_compressed(os.path.join(OUT, "g3_reduce.npz"), flags=flags, repo=repo, case_id=case,
+                        want_property_cells=np.array(want_prop), property_cell_reproduces=prop_ok,
                         flag_names=np.array(names), repo_names=np.array(repos),
                         want_strategy_cells=np.array(want_cells), strategy_cell_reproduces=cell_ok,
                         want_method_total_cases=np.array([want4[m[0]] for m in METHODS], np.int64),
@@ -268,9 +303,11 @@ def golden_g3(ledger):
                     "rows": len(rows), "cases": len(cases), "cases_per_repo": dict(zip(repos, map(int, cpr))),
                     "strategy_cells_bit_identical": [int(cell_ok.sum()), int(cell_ok.size)],
                     "rq4_method_counts_identical": [int(sum(m_ok)), len(m_ok)],
+                    "property_cells_bit_identical": [int(prop_ok.sum()), int(prop_ok.size)],
+                    "property_columns_fully_identical": [int((prop_ok.sum(axis=1) == len(repos)).sum()), len(PROPERTIES)],
                     "rq4_mismatches": {m[0]: [int(out[len(STRATEGY) + j].sum()), want4[m[0]]]
                                        for j, m in enumerate(METHODS) if not m_ok[j]}}
-    print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok))
+    print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok), "property cells", int(prop_ok.sum()), prop_ok.size)
 
 
 def c1_summary(ledger, write=True):

@@ -16,7 +16,7 @@
 // itself goes through libtosemscan.so (sm_100a kernels); there is no CPU fallback.
 //
 //   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]
-//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]
+//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
 //   tosem-scan releases <snapshot-root>=<tag>... [--out F]
@@ -426,6 +426,34 @@ static const FlagDef kMethods[] = {
     {"robustness_test", "roboustness", nullptr, nullptr}, {"experimental", "Experimental_benchmark_test", nullptr, nullptr},
     {"api_test", "API", nullptr, nullptr}, {"threat", "ThreadTest", nullptr, nullptr}, {"blob", "blob_performance", nullptr, nullptr}};
 
+// RQ3 property table (RQs/RQ3/tests_prop_rq3.csv): a case has a property when the `Data` or the `Model` label of
+// one of its rows is in the property's label set.  The sets are not written down in the package; 17 of the 21 were
+// recovered by search against the nine shipped per-repository cells (exact, tools/make_golden.py), the other four
+// (Consistency, Features Importance, Concurrency, Anomaly) use the label of the same name.
+struct PropDef { const char* name; const char* labels; };
+static const PropDef kProperties[] = {
+    {"Consistency", "Consistency"}, {"Data Distribution", "Distribution"},
+    {"Data Validity", "Validity|Data Error|Data Error and Validity"}, {"Completeness", "Completeness"},
+    {"Correctness", "Correctness|Accuracy & Precision|Statistical Evidence/ explainability"}, {"Robustness", "Robustness"},
+    {"Efficiency", "Time behaviour|Resource Usage|Training Efficiency"},
+    {"Data Relation", "Relation & Association|Closeness|Missing Data|Data Differencing|Data Quality"},
+    {"Scalability", "Scalability"}, {"Features Importance", "Feature Importance"},
+    {"Data Restoration and Recoverability", "Recoverability|Data Restoration"},
+    {"Concurrency and Parallelism", "Parallel Processing|parallel"}, {"Uncertainty", "uncertainty"}, {"Anomaly", "Anomaly"},
+    {"Data Migration Loss and Corruption", "Data Loss"}, {"Bias and Fairness", "Model Bias"},
+    {"Security and Privacy", "Security|Data Encapsulation"}, {"Data Uniqueness", "Uniqueness"},
+    {"Data Timeliness", "Timeliness"}, {"Data Integration Integrity", "Validate data integration and integrity"},
+    {"Compatibility and Portability", "Compatibility"}};
+
+static bool one_of(const std::string& have, const std::string& want) {   // `want` = '|'-separated values
+  for (size_t a = 0; a <= want.size();) {
+    const size_t b = std::min(want.find('|', a), want.size());
+    if (have == want.substr(a, b - a)) return true;
+    a = b + 1;
+  }
+  return false;
+}
+
 static std::string trim(const std::string& s) {
   size_t a = 0, b = s.size();
   while (a < b && (s[a] == ' ' || s[a] == '\t')) ++a;
@@ -441,7 +469,8 @@ static std::string fmt_num(double v, int dec) {            // shipped cells drop
 }
 static double round_to(double v, int dec) { const double p = std::pow(10.0, dec); return std::round(v * p) / p; }
 
-static int cmd_reduce(const std::string& path, const std::string& strategy_path, const std::string& methods_path) {
+static int cmd_reduce(const std::string& path, const std::string& strategy_path, const std::string& methods_path,
+                      const std::string& properties_path) {
   auto rows = csv_read(path);
   if (rows.size() < 2) die("empty taxonomy");
   std::map<std::string, int> col;
@@ -452,7 +481,8 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
   std::map<std::string, int> rid, cid;
   for (size_t r = 1; r < rows.size(); ++r) if ((int)rows[r].size() > col["Repo"] && !std::count(repos.begin(), repos.end(), rows[r][col["Repo"]])) repos.push_back(rows[r][col["Repo"]]);
   for (size_t i = 0; i < repos.size(); ++i) rid[repos[i]] = (int)i;
-  const int nS = sizeof(kStrategy) / sizeof(kStrategy[0]), nM = sizeof(kMethods) / sizeof(kMethods[0]), nF = nS + nM;
+  const int nS = sizeof(kStrategy) / sizeof(kStrategy[0]), nM = sizeof(kMethods) / sizeof(kMethods[0]);
+  const int nP = sizeof(kProperties) / sizeof(kProperties[0]), nF = nS + nM + nP;
   std::vector<uint8_t> flags; std::vector<int32_t> repo, cas;
   auto cell = [&](const std::vector<std::string>& r, const char* c) -> std::string {
     auto it = col.find(c); return (it == col.end() || it->second >= (int)r.size()) ? std::string() : trim(r[it->second]); };
@@ -463,19 +493,14 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
     if (!cid.count(cs)) { const int k = (int)cid.size(); cid[cs] = k; }
     repo.push_back(rid[R[col["Repo"]]]); cas.push_back(cid[cs]);
     for (int j = 0; j < nS; ++j) {
-      bool v = false;
-      {
-        const std::string have = cell(R, kStrategy[j].col), want = kStrategy[j].val;
-        for (size_t a = 0; a <= want.size();) {             // any of the '|'-separated values
-          const size_t b = std::min(want.find('|', a), want.size());
-          if (have == want.substr(a, b - a)) v = true;
-          a = b + 1;
-        }
-      }
+      bool v = one_of(cell(R, kStrategy[j].col), kStrategy[j].val);
       if (kStrategy[j].col2) v = v || cell(R, kStrategy[j].col2) == "1";
       flags.push_back(v);
     }
     for (int j = 0; j < nM; ++j) { const std::string v = cell(R, kMethods[j].col); flags.push_back(!(v.empty() || v == "0")); }
+    const std::string data = cell(R, "Data"), model = cell(R, "Model");
+    for (int j = 0; j < nP; ++j)
+      flags.push_back((!data.empty() && one_of(data, kProperties[j].labels)) || (!model.empty() && one_of(model, kProperties[j].labels)));
   }
   const int n_rows = (int)repo.size(), n_repos = (int)repos.size(), n_cases = (int)cid.size();
   tsm_ctx* ctx = nullptr;
@@ -518,6 +543,26 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
       int64_t t = 0;
       for (int r = 0; r < n_repos; ++r) t += out[(size_t)(nS + j) * n_repos + r];
       csv_row(os, {kMethods[j].name, std::to_string(t), fmt_num(all_cases ? round_to(100.0 * t / all_cases, 4) : 0.0, 4)});
+    }
+  }
+  if (!properties_path.empty()) {                           // layout of RQs/RQ3/tests_prop_rq3.csv:1-10
+    std::ofstream os(properties_path, std::ios::binary);
+    std::vector<std::string> h = {"Repos"};
+    for (int j = 0; j < nP; ++j) h.push_back(kProperties[j].name);
+    csv_row(os, h);
+    int64_t denom = 0;                                      // one denominator for every row: Apollo's case count (the 216 of
+    if (rid.count("Apollo")) denom = cpr[(size_t)rid["Apollo"]];   // the shipped table), else the largest repository
+    if (denom == 0) for (int64_t c : cpr) denom = std::max(denom, c);
+    // shipped row order when all nine repositories are present, else the order of `repos`
+    std::vector<std::string> order = {"auto_sklearn", "google_automl", "tpot", "autokeras", "Nupic", "Apollo", "nni", "Ray", "DeepSpeech2"};
+    for (auto& r : repos) if (!std::count(order.begin(), order.end(), r)) order.push_back(r);
+    for (auto& name : order) {
+      if (!rid.count(name) || cpr[(size_t)rid[name]] == 0) continue;
+      const int r = rid[name];
+      std::vector<std::string> row = {name};
+      for (int j = 0; j < nP; ++j)
+        row.push_back(fmt_num(denom ? round_to(100.0 * out[(size_t)(nS + nM + j) * n_repos + r] / denom, 4) : 0.0, 4));
+      csv_row(os, row);
     }
   }
   fprintf(stderr, "tosem-scan: reduce %d rows, %d cases, %d repos\n", n_rows, n_cases, n_repos);
@@ -788,7 +833,7 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
 static void usage() {
   fprintf(stderr,
           "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]\n"
-          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F]\n"
+          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
           "       tosem-scan releases <snapshot-root>=<tag>... [--out F]\n"
@@ -809,7 +854,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
                                         opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30)); }
-  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"]); }
+  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"]); }
   if (cmd == "releases") { if (pos.empty()) die("releases needs <root>=<tag>..."); return cmd_releases(pos, opt["--out"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
   if (cmd == "diff") { if (pos.size() != 2) die("diff needs <old-root> <new-root>"); return cmd_diff(pos[0], pos[1], opt["--out"]); }
