@@ -182,6 +182,51 @@ def test_reduce_tables(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reduce_reproduces_the_shipped_tables(tmp_path):
+    """The CLI on the package's own taxonomy (the columns it reads, tests/golden/taxonomy_min.csv.gz): every cell the
+    ledger marks reproducible must come out bit-identical to RQs/RQ3/tests_strategy_rq32.csv, tests_prop_rq3.csv and
+    RQs/RQ4/tests_methods_v2.csv (shipped cells kept in tests/golden/g3_reduce.npz)."""
+    import gzip
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    tax = tmp_path / "taxonomy.csv"
+    tax.write_bytes(gzip.open(os.path.join(gold, "taxonomy_min.csv.gz"), "rb").read())
+    sp, mp, pp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    d = np.load(os.path.join(gold, "g3_reduce.npz"))
+    repos = [str(x) for x in d["repo_names"]]
+    names = [str(x) for x in d["flag_names"]]
+    s = read_csv(sp)
+    assert s[0][1:10] == repos
+    srow = {x[0]: x for x in s[1:]}
+    ok, want = d["strategy_cell_reproduces"], d["want_strategy_cells"]
+    n_ok = 0
+    for j in range(ok.shape[0]):
+        for k in range(ok.shape[1]):
+            if ok[j, k]:
+                assert srow[names[j]][1 + k] == str(want[j][k]), (names[j], repos[k])
+                n_ok += 1
+    assert n_ok == 171
+    m = {x[0]: x for x in read_csv(mp)[1:]}
+    mnames = [n[2:] for n in names if n.startswith("m:")]
+    for j, name in enumerate(mnames):
+        if d["method_reproduces"][j]:
+            assert int(m[name][1]) == int(d["want_method_total_cases"][j]), name
+    pt = read_csv(pp)
+    prow = {x[0]: x for x in pt[1:]}
+    pnames = [n[2:] for n in names if n.startswith("p:")]
+    assert pt[0][1:] == pnames
+    pok, pwant = d["property_cell_reproduces"], d["want_property_cells"]
+    n_ok = 0
+    for j in range(pok.shape[0]):
+        for k in range(pok.shape[1]):
+            if pok[j, k]:
+                assert prow[repos[k]][1 + j] == str(pwant[j][k]), (pnames[j], repos[k])
+                n_ok += 1
+    assert n_ok == 172
+
+
+@pytest.mark.gpu
 def test_diff_trees(tmp_path):
     old, new = tmp_path / "old", tmp_path / "new"
     os.makedirs(old / "a")

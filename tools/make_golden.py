@@ -279,6 +279,14 @@ def golden_g3(ledger):
     # RQ4: distinct cases over all repos = sum over repos (a case belongs to one repo)
     for j, (name, _) in enumerate(METHODS):
         m_ok.append(int(out[len(STRATEGY) + j].sum()) == want4[name])
+    # the columns `tosem-scan reduce` reads, as a compact fixture for the CLI's own golden test (tests/test_cli.py)
+    import gzip
+    keep = ["Cases", "Repo", "Data", "Model"] + sorted({c for _, c, _ in STRATEGY} | {"logical_expression"} | {c for _, c in METHODS})
+    with gzip.open(os.path.join(OUT, "taxonomy_min.csv.gz"), "wt", newline="", encoding="utf-8", compresslevel=9) as f:
+        w = csv.writer(f, lineterminator="\r\n")
+        w.writerow(keep)
+        for r in rows:
+            w.writerow([r[c] for c in keep])
     # RQ3 property table: rows = repos (shipped order), cells = 100 * distinct / 216
     tp = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_prop_rq3.csv"), newline="")))
     assert tp[0][1:] == [q[0] for q in PROPERTIES]
