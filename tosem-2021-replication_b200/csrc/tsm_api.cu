@@ -8,6 +8,9 @@
 
 #include "tsm_device.cuh"
 
+#ifndef TSM_CLS_GRID
+#define TSM_CLS_GRID 8
+#endif
 #include "tsm_scan_kernels.cuh"
 #include "tsm_reduce_kernels.cuh"
 #include "tsm_diff_kernels.cuh"
@@ -350,7 +353,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);
     const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
-    k_classify<<<c->sms * 8, 256, hist, st>>>(p);
+    k_classify<<<c->sms * TSM_CLS_GRID, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
     cudaEventRecord(ev[4], st);                           // (slot of the former k_totals, now fused into k_classify)
     c->ev_used[es] = (n_slabs == 1);
