@@ -8,9 +8,6 @@
 
 #include "tsm_device.cuh"
 
-#ifndef TSM_CLS_GRID
-#define TSM_CLS_GRID 8
-#endif
 #include "tsm_scan_kernels.cuh"
 #include "tsm_reduce_kernels.cuh"
 #include "tsm_diff_kernels.cuh"
@@ -53,6 +50,7 @@ struct PoolScope {
 struct tsm_ctx {
   int device = 0;
   ScratchPool pool;
+  int cls_grid = 0; size_t cls_smem = (size_t)-1;        // launch shape of k_classify for the current histogram size
   int sms = 0;
   int64_t max_arena = 0;
   int32_t max_files = 0, max_groups = 0;
@@ -353,7 +351,13 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);
     const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
-    k_classify<<<c->sms * TSM_CLS_GRID, 256, hist, st>>>(p);
+    if (c->cls_smem != hist) {                           // one resident wave of k_classify (grid-stride inside): measured
+      int per_sm = 0;                                    // -7 % on C2 against 8 blocks per SM, equal on C4
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify, 256, hist) != cudaSuccess || per_sm < 1) per_sm = 4;
+      c->cls_grid = c->sms * per_sm;
+      c->cls_smem = hist;
+    }
+    k_classify<<<c->cls_grid, 256, hist, st>>>(p);
     cudaEventRecord(ev[3], st);
     cudaEventRecord(ev[4], st);                           // (slot of the former k_totals, now fused into k_classify)
     c->ev_used[es] = (n_slabs == 1);
