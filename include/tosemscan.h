@@ -163,6 +163,15 @@ int tsm_gen_fill(uint64_t seed, int32_t n_files, int size_law, int32_t first_ind
 int64_t tsm_gen_edit(uint64_t seed, const uint8_t* src, int32_t src_len, double lambda,
                      uint8_t* dst, int64_t cap);
 
+/* BASELINE config C5: n (old, new) revision pairs; old ~ the size law 1 with the target clamped to cap bytes,
+ * new = old with Poisson(lambda) line edits.  Slot i holds logical pair first_index + i*index_stride.
+ * tsm_gen_pair_sizes -> tsm_layout (twice) -> tsm_gen_pair_fill. */
+int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
+                       double lambda, int32_t* len_old, int32_t* len_new, uint8_t* ext);
+int tsm_gen_pair_fill(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
+                      double lambda, const uint8_t* ext, const int32_t* off_old, const int32_t* len_old,
+                      uint8_t* arena_old, const int32_t* off_new, const int32_t* len_new, uint8_t* arena_new);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,15 @@ int orc_reduce(const uint8_t* flags, const int32_t* repo, const int32_t* case_id
                int32_t n_flags, int32_t n_repos, int32_t n_cases, int64_t* out,
                int64_t* cases_per_repo);
 
+/* orc_mt.c: orc_scan over a pool of persistent POSIX threads, files partitioned statically by bytes (the
+ * host-cores baseline bench.py times).  n_threads <= 0: one per CPU of the calling thread's affinity mask.
+ * orc_mt_create returns the thread count; orc_mt_scan returns 0 / -1 (corpus) / -2 (no pool). */
+int orc_mt_affinity_cpus(void);
+int orc_mt_create(int n_threads, int32_t max_groups);
+void orc_mt_destroy(void);
+int orc_mt_scan(const uint8_t* arena, const int32_t* off, const int32_t* len, const uint8_t* ext, const uint16_t* grp,
+                int32_t n_files, int32_t n_groups, orc_file_stat* stats, int64_t* group_counts, int64_t* global_counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ _lib = None
 
 def build():
     so = os.path.join(ORC_DIR, "liborc.so")
-    srcs = [os.path.join(ORC_DIR, f) for f in ("orc.c", "orc.h", "orc_categories.inc")]
+    srcs = [os.path.join(ORC_DIR, f) for f in ("orc.c", "orc_mt.c", "orc.h", "orc_categories.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORC_DIR, "-s"])
     return so
@@ -69,6 +69,12 @@ def lib():
         L.orc_statements.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_reduce.restype = C.c_int
         L.orc_reduce.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+        L.orc_mt_affinity_cpus.restype = C.c_int
+        L.orc_mt_create.restype = C.c_int
+        L.orc_mt_create.argtypes = [C.c_int, C.c_int32]
+        L.orc_mt_destroy.restype = None
+        L.orc_mt_scan.restype = C.c_int
+        L.orc_mt_scan.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 3
         _lib = L
     return _lib
 
@@ -163,6 +169,30 @@ def scan(arena, off, length, ext, grp, n_groups=1, events=True, line_hashes=Fals
             out["line_hash"] = lh[:nl]
             out["line_base"] = lb
     return out
+
+
+class MtScanner:
+    """orc_scan over a pool of persistent POSIX threads (oracle/orc_mt.c): the host-cores baseline.  Buffers
+    are allocated once; scan() is one C call with no Python work per file or per thread."""
+
+    def __init__(self, threads=0, max_groups=16):
+        self.threads = int(lib().orc_mt_create(int(threads), int(max_groups)))
+        if self.threads < 1:
+            raise RuntimeError("orc_mt_create failed")
+        self._bufs = None
+
+    def scan(self, arena, off, length, ext, grp, n_groups=1):
+        n = len(length)
+        if self._bufs is None or self._bufs[0].size != n or self._bufs[1].shape[0] != n_groups:
+            self._bufs = (np.zeros(n, FILE_STAT), np.zeros((n_groups, K), np.int64), np.zeros(K, np.int64))
+        stats, gc, glob = self._bufs
+        rc = lib().orc_mt_scan(_p(arena), _p(off), _p(length), _p(ext), _p(grp), n, n_groups, _p(stats), _p(gc), _p(glob))
+        if rc != 0:
+            raise ValueError("orc_mt_scan failed (%d)" % rc)
+        return {"stats": stats, "group_counts": gc, "global_counts": glob}
+
+    def close(self):
+        lib().orc_mt_destroy()
 
 
 def lcs(a, b) -> int:

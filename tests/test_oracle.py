@@ -281,3 +281,27 @@ def test_c1_bundled_corpus_summary_is_stable():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "make_golden.py"), "--check-c1"],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+def test_mt_harness_equals_single_thread_scan():
+    """oracle/orc_mt.c (the host-cores baseline of bench.py): same records and tables as orc_scan, for any
+    thread count, including more threads than files and empty files."""
+    files, exts, grps = cu.fuzz_corpus(77, 300, 9000)
+    files += [b""] * 40
+    exts = np.concatenate([exts, np.ones(40, np.uint8)])
+    grps = np.concatenate([grps, np.zeros(40, np.uint16)])
+    arena, off, ln = orc.pack(files)
+    want = orc.scan(arena, off, ln, exts, grps, 5, events=False)
+    assert orc.lib().orc_mt_affinity_cpus() >= 1
+    for threads in (1, 3, 8, 500):
+        mt = orc.MtScanner(threads, max_groups=5)
+        assert mt.threads == threads
+        for _ in range(2):                                  # the pool is reused across calls
+            got = mt.scan(arena, off, ln, exts, grps, 5)
+            assert np.array_equal(got["stats"], want["stats"])
+            assert np.array_equal(got["group_counts"], want["group_counts"])
+            assert np.array_equal(got["global_counts"], want["global_counts"])
+        mt.close()
+    mt = orc.MtScanner(0)
+    assert mt.threads == orc.lib().orc_mt_affinity_cpus()
+    mt.close()

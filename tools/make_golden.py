@@ -11,6 +11,8 @@ Outputs (all committed, all small):
   tests/golden/g3_reduce.npz                G3: RQs/taxonomy_test2.csv reduced to integer arrays
                                             + the shipped RQ3/RQ4 table cells it must reproduce
   tests/golden/c1_summary.json              oracle totals over the bundled corpus src/ (config C1)
+  tests/golden/c1_testfiles.npz             the C1 test files themselves (real bytes for the GPU box)
+  tests/golden/c1_hazard_files.npz          the hazard files of SURVEY.md section 8d outside that subset
   tests/golden/ledger.json                  reproduction rates of every golden (the parity ledger)
 
 xlsx files are read with zipfile + ElementTree (no openpyxl in the image).
@@ -282,11 +284,15 @@ def golden_g3(ledger):
     # the columns `tosem-scan reduce` reads, as a compact fixture for the CLI's own golden test (tests/test_cli.py)
     import gzip
     keep = ["Cases", "Repo", "Data", "Model"] + sorted({c for _, c, _ in STRATEGY} | {"logical_expression"} | {c for _, c in METHODS})
-    with gzip.open(os.path.join(OUT, "taxonomy_min.csv.gz"), "wt", newline="", encoding="utf-8", compresslevel=9) as f:
-        w = csv.writer(f, lineterminator="\r\n")
-        w.writerow(keep)
-        for r in rows:
-            w.writerow([r[c] for c in keep])
+    import io
+    txt = io.StringIO(newline="")
+    w = csv.writer(txt, lineterminator="\r\n")
+    w.writerow(keep)
+    for r in rows:
+        w.writerow([r[c] for c in keep])
+    with open(os.path.join(OUT, "taxonomy_min.csv.gz"), "wb") as raw:      # mtime 0, no file name: the bytes do not
+        with gzip.GzipFile(filename="", mode="wb", fileobj=raw, compresslevel=9, mtime=0) as f:   # depend on when it is made
+            f.write(txt.getvalue().encode("utf-8"))
     # RQ3 property table: rows = repos (shipped order), cells = 100 * distinct / 216
     tp = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_prop_rq3.csv"), newline="")))
     assert tp[0][1:] == [q[0] for q in PROPERTIES]
@@ -318,8 +324,8 @@ def golden_g3(ledger):
     print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok), "property cells", int(prop_ok.sum()), prop_ok.size)
 
 
-def c1_summary(ledger, write=True):
-    """Config C1: the oracle over the bundled corpus (test files with a scannable extension)."""
+def c1_collect():
+    """The test files of the bundled corpus with a scannable extension (S0 + S1), in walk order."""
     root = os.path.join(REF, "src")
     projects = sorted(os.listdir(root))
     projects = [p for p in projects if os.path.isdir(os.path.join(root, p))]
@@ -339,6 +345,70 @@ def c1_summary(ledger, write=True):
                 ext.append(EXT_TAG[e])
                 grp.append(g)
                 names.append(proj + "/" + rel)
+    return projects, files, ext, grp, names
+
+
+def c1_fixture():
+    """tests/golden/c1_testfiles.npz: the C1 test files themselves (1 779 files, 10.55 MB of the study's corpus),
+    so that the GPU box - which has no /root/reference - can put real bytes through the CUDA path.  Deflated."""
+    projects, files, ext, grp, names = c1_collect()
+    blob = np.frombuffer(b"".join(files), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "c1_testfiles.npz"), blob=blob, size=np.array([len(f) for f in files], np.int32),
+                        ext=np.array(ext, np.uint8), grp=np.array(grp, np.uint16),
+                        names=np.frombuffer("\n".join(names).encode(), np.uint8),
+                        projects=np.frombuffer("\n".join(projects).encode(), np.uint8))
+    hz = {"files": len(files), "bytes": int(blob.size), "empty": sum(1 for f in files if not f),
+          "crlf_files": sum(1 for f in files if b"\r\n" in f), "no_trailing_newline": sum(1 for f in files if f and not f.endswith(b"\n")),
+          "with_bytes_over_127": sum(1 for f in files if any(b > 127 for b in f)), "largest": max(len(f) for f in files),
+          "longest_line": max(max((len(l) for l in f.split(b"\n")), default=0) for f in files)}
+    print("C1 fixture", hz)
+    return hz
+
+
+def c1_hazards():
+    """tests/golden/c1_hazard_files.npz: the hazard files SURVEY.md section 8d lists for config C1 that lie outside the
+    test-file subset: the one non-UTF-8 file, every CRLF file, the 2.5 MB file with the 2 061-byte lines, and every
+    scannable file without a trailing newline."""
+    root = os.path.join(REF, "src")
+    picked = []
+    for dp, dn, fn in os.walk(root):
+        dn.sort()
+        for f in sorted(fn):
+            e = f.rsplit(".", 1)[-1] if "." in f else ""
+            if e not in EXT_TAG:
+                continue
+            b = open(os.path.join(dp, f), "rb").read()
+            try:
+                b.decode("utf-8")
+                utf8 = True
+            except UnicodeDecodeError:
+                utf8 = False
+            if (not utf8) or b"\r\n" in b or len(b) > 2500000 or (b and not b.endswith(b"\n")):
+                picked.append((os.path.relpath(os.path.join(dp, f), root), b, EXT_TAG[e]))
+    blob = np.frombuffer(b"".join(b for _, b, _ in picked), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "c1_hazard_files.npz"), blob=blob, size=np.array([len(b) for _, b, _ in picked], np.int32),
+                        ext=np.array([e for _, _, e in picked], np.uint8), grp=np.zeros(len(picked), np.uint16),
+                        names=np.frombuffer("\n".join(n for n, _, _ in picked).encode(), np.uint8))
+    hz = {"files": len(picked), "bytes": int(blob.size), "non_utf8": sum(1 for _, b, _ in picked if not _is_utf8(b)),
+          "crlf_files": sum(1 for _, b, _ in picked if b"\r\n" in b),
+          "no_trailing_newline": sum(1 for _, b, _ in picked if b and not b.endswith(b"\n")),
+          "largest": max(len(b) for _, b, _ in picked),
+          "longest_line": max(max((len(l) for l in b.split(b"\n")), default=0) for _, b, _ in picked)}
+    print("C1 hazards", hz)
+    return hz
+
+
+def _is_utf8(b):
+    try:
+        b.decode("utf-8")
+        return True
+    except UnicodeDecodeError:
+        return False
+
+
+def c1_summary(ledger, write=True):
+    """Config C1: the oracle over the bundled corpus (test files with a scannable extension)."""
+    projects, files, ext, grp, names = c1_collect()
     arena, off, length = orc.pack(files)
     res = orc.scan(arena, off, length, np.array(ext, np.uint8), np.array(grp, np.uint16), len(projects), events=False)
     st = res["stats"]
@@ -446,6 +516,8 @@ def main():
     golden_g3(ledger)
     ledger_g2(ledger)
     c1_summary(ledger)
+    ledger["C1"]["fixture"] = c1_fixture()
+    ledger["C1"]["hazard_fixture"] = c1_hazards()
     json.dump(ledger, open(os.path.join(OUT, "ledger.json"), "w"), indent=1)
 
 

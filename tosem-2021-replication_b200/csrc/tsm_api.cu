@@ -2,6 +2,7 @@
 // memory, H2D/D2H staging and kernel launches.  No torch types, no CPU fallback.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -9,6 +10,7 @@
 #include "tsm_device.cuh"
 
 #include "tsm_scan_kernels.cuh"
+#include "tsm_scan2_kernels.cuh"
 #include "tsm_reduce_kernels.cuh"
 #include "tsm_diff_kernels.cuh"
 #include "tsm_stmt_kernels.cuh"
@@ -52,6 +54,7 @@ struct tsm_ctx {
   ScratchPool pool;
   int cls_grid = 0; size_t cls_smem = (size_t)-1;        // launch shape of k_classify for the current histogram size
   int sms = 0;
+  bool scan_v1 = false;
   int64_t max_arena = 0;
   int32_t max_files = 0, max_groups = 0;
   int64_t max_events = 0;
@@ -143,6 +146,19 @@ static void build_lut(uint32_t* lut) {                   // the one automaton ta
     }
 }
 
+static void build_lut2(uint32_t* lut) {                  // table of k_scan2: no `_F` gate, bit 31 = newline
+  struct Pat { const char* s; int first; bool ci; };
+  static const Pat pats[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"class", 13, false}, {"def", 18, false},
+                             {"test", 21, true}, {"void", 25, false}, {"{", 29, false}, {"\n", 31, false}};
+  memset(lut, 0, 256 * sizeof(uint32_t));
+  for (const Pat& p : pats)
+    for (int k = 0; p.s[k]; ++k) {
+      const unsigned char c = (unsigned char)p.s[k];
+      lut[c] |= 1u << (p.first + k);
+      if (p.ci && c >= 'a' && c <= 'z') lut[c - 32] |= 1u << (p.first + k);
+    }
+}
+
 static void build_elut(uint32_t* lut) {                  // operator patterns of SPEC section 6 rule 2
   struct Pat { const char* s; int first; };
   static const Pat pats[] = {{" not ", 0}, {" in ", 5}, {" is not ", 9}, {"True", 17}, {"==", 21}, {"!=", 23},
@@ -219,9 +235,14 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
     static const uint8_t slot[TSM_CAT_SLOTS] = TSM_CAT_SLOT_INIT;
     static const uint16_t offs[TSM_CAT_NAMED + 1] = TSM_CAT_OFF_INIT;
     static const char blob[] = TSM_CAT_BLOB_INIT;
-    uint32_t elut[256];
+    uint32_t elut[256], lut2[256];
     build_elut(elut);
+    build_lut2(lut2);
+    const char* impl = getenv("TSM_SCAN_IMPL");          // A/B knob of the round-2 rewrite: 1 = the first-generation k_scan
+    c->scan_v1 = impl && impl[0] == '1';
     if (cudaMemcpyToSymbol(c_lut, lut, sizeof lut) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_lut2, lut2, sizeof lut2) != cudaSuccess ||
+        cudaFuncSetAttribute(k_scan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess ||
         cudaMemcpyToSymbol(c_elut, elut, sizeof elut) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_slot, slot, sizeof slot) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_off, offs, sizeof offs) != cudaSuccess ||
@@ -346,7 +367,8 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       p.unit_base = (uint32_t)((host ? (int64_t)host->off[f0] : 0) / CH + f0);
       k_plan<<<(f1 - f0 + 255) / 256, 256, 0, st>>>(p);
       if (s == 0 && n_slabs == 1) cudaEventRecord(ev[1], st);
-      k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
+      if (c->scan_v1) k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
+      else k_scan2<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN2_SMEM, st>>>(p);
     }
     if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);

@@ -214,7 +214,7 @@ __device__ __forceinline__ uint32_t line_finish_h(uint32_t s, uint32_t e, unsign
   } else {
     hdr = (nib & 6u) == 6u;
   }
-  if (hdr) { fl |= LF_HDR; if ((nib & 8u) && starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }
+  if (hdr) { fl |= LF_HDR; if (starts_with(lb, s, e, "TEST_F", 6, false)) fl |= LF_FIX; }   // (headers are ~2 % of the lines)
   ac.asserts += fl & LF_CAND;
   ac.hdrs += (fl >> 1) & 1u;
   ac.fixes += (fl >> 2) & 1u;

@@ -208,9 +208,22 @@ extern "C" int tsm_gen_fill(uint64_t seed, int32_t n_files, int size_law, int32_
   return TSM_OK;
 }
 
+namespace {
+int64_t edit_lines(uint64_t seed, const uint8_t* src, int32_t src_len, double lambda, std::string* out);
+}
+
 extern "C" int64_t tsm_gen_edit(uint64_t seed, const uint8_t* src, int32_t src_len, double lambda,
                                 uint8_t* dst, int64_t cap) {
   if (!src || src_len < 0 || !dst || cap < 0) return -1;
+  std::string out;
+  const int64_t n = edit_lines(seed, src, src_len, lambda, &out);
+  if (n > cap) return -1;
+  memcpy(dst, out.data(), (size_t)n);
+  return n;
+}
+
+namespace {
+int64_t edit_lines(uint64_t seed, const uint8_t* src, int32_t src_len, double lambda, std::string* out) {
   Rng r(file_seed(seed, 0xD1FFull));
   std::vector<std::string> lines;
   for (int32_t p = 0; p < src_len;) {
@@ -244,9 +257,56 @@ extern "C" int64_t tsm_gen_edit(uint64_t seed, const uint8_t* src, int32_t src_l
   }
   int64_t n = 0;
   for (const std::string& s : lines) {
-    if (n + (int64_t)s.size() > cap) return -1;
-    memcpy(dst + n, s.data(), s.size());
+    if (out) out->append(s);
     n += (int64_t)s.size();
   }
   return n;
+}
+
+// BASELINE config C5: pair `index` = (old, new); old follows the C4 size law with the target
+// clamped to `cap` bytes (whole lines), new = old with Poisson(lambda) line edits.
+void gen_pair(uint64_t seed, int64_t index, int32_t cap, double lambda, int ext, std::string& old_s, std::string& new_s) {
+  Rng r(file_seed(seed, (uint64_t)index));
+  const double a = 1.0 / std::sqrt(128.0), b = 1.0 / std::sqrt(1048576.0);
+  const double t = a - r.unit() * (a - b);
+  int64_t target = (int64_t)(1.0 / (t * t));
+  if (target < 128) target = 128;
+  if (target > cap) target = cap;
+  old_s.clear();
+  std::string line;
+  while ((int64_t)old_s.size() < target) { make_line(r, ext, line); line += '\n'; old_s += line; }
+  new_s.clear();
+  edit_lines(seed ^ (0xC5ull << 56) ^ (uint64_t)index, (const uint8_t*)old_s.data(), (int32_t)old_s.size(), lambda, &new_s);
+}
+}  // namespace
+
+extern "C" int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
+                                  double lambda, int32_t* len_old, int32_t* len_new, uint8_t* ext) {
+  if (n_pairs < 0 || !len_old || !len_new || !ext || first_index < 0 || index_stride < 1 || cap < 128 || lambda < 0) return TSM_E_ARG;
+  std::string o, n;
+  for (int32_t i = 0; i < n_pairs; ++i) {
+    const int64_t logical = (int64_t)first_index + (int64_t)i * index_stride;
+    ext[i] = (uint8_t)gen_ext(seed, logical);
+    gen_pair(seed, logical, cap, lambda, ext[i], o, n);
+    len_old[i] = (int32_t)o.size();
+    len_new[i] = (int32_t)n.size();
+  }
+  return TSM_OK;
+}
+
+extern "C" int tsm_gen_pair_fill(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
+                                 double lambda, const uint8_t* ext, const int32_t* off_old, const int32_t* len_old,
+                                 uint8_t* arena_old, const int32_t* off_new, const int32_t* len_new, uint8_t* arena_new) {
+  if (n_pairs < 0 || !ext || !off_old || !len_old || !arena_old || !off_new || !len_new || !arena_new || first_index < 0 ||
+      index_stride < 1 || cap < 128)
+    return TSM_E_ARG;
+  std::string o, n;
+  for (int32_t i = 0; i < n_pairs; ++i) {
+    const int64_t logical = (int64_t)first_index + (int64_t)i * index_stride;
+    gen_pair(seed, logical, cap, lambda, ext[i], o, n);
+    if ((int64_t)o.size() != len_old[i] || (int64_t)n.size() != len_new[i]) return TSM_E_ARG;   // sizes must come from tsm_gen_pair_sizes
+    memcpy(arena_old + off_old[i], o.data(), o.size());
+    memcpy(arena_new + off_new[i], n.data(), n.size());
+  }
+  return TSM_OK;
 }

@@ -32,7 +32,7 @@ DIFF_DETAIL = np.dtype([("hunks_add", "<i8"), ("hunks_del", "<i8"), ("hunks_mod"
 SYMBOLS = ["tsm_abi_version", "tsm_strerror", "tsm_category_name", "tsm_create", "tsm_destroy", "tsm_scan",
            "tsm_upload", "tsm_scan_resident", "tsm_download", "tsm_device_counts", "tsm_last_launch_count", "tsm_last_kernel_ms", "tsm_kernel_ms_stats",
            "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_statements", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
-           "tsm_gen_fill", "tsm_gen_edit"]
+           "tsm_gen_fill", "tsm_gen_edit", "tsm_gen_pair_sizes", "tsm_gen_pair_fill"]
 
 
 class TsmError(RuntimeError):
@@ -113,6 +113,11 @@ def lib():
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsm_gen_edit.restype = C.c_int64
         L.tsm_gen_edit.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int64]
+        L.tsm_gen_pair_sizes.restype = C.c_int
+        L.tsm_gen_pair_sizes.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tsm_gen_pair_fill.restype = C.c_int
+        L.tsm_gen_pair_fill.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 7
         _lib = L
     return _lib
 
@@ -238,6 +243,44 @@ def gen_corpus(seed, n_files, size_law=0, fixed_size=4096, first_index=0, index_
     if any(rcs):
         raise TsmError([r for r in rcs if r][0], "tsm_gen_fill")
     return Corpus(arena, off, length, ext, grp, n_groups, keep)
+
+
+def gen_pairs(seed, n_pairs, cap=65536, lam=6.0, first_index=0, index_stride=1, pinned=True, threads=None):
+    """BASELINE config C5: (olds, news) corpora of n_pairs revision pairs, generated in C++."""
+    L = lib()
+    lo, ln = np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.int32)
+    ext = np.zeros(n_pairs, np.uint8)
+    nthr = max(1, min(threads or (os.cpu_count() or 1), 64, (n_pairs + 255) // 256))
+    bounds = [n_pairs * t // nthr for t in range(nthr + 1)]
+
+    def run(fn):
+        if nthr == 1:
+            rcs = [fn(0)]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(nthr) as ex:
+                rcs = list(ex.map(fn, range(nthr)))
+        if any(rcs):
+            raise TsmError([r for r in rcs if r][0], "tsm_gen_pair_*")
+
+    def sizes(t):
+        a, b = bounds[t], bounds[t + 1]
+        return 0 if a == b else L.tsm_gen_pair_sizes(seed, b - a, first_index + a * index_stride, index_stride, cap, float(lam),
+                                                     _p(lo[a:b]), _p(ln[a:b]), _p(ext[a:b]))
+    run(sizes)
+    oo, on = np.zeros(n_pairs + 1, np.int32), np.zeros(n_pairs + 1, np.int32)
+    to, tn = L.tsm_layout(_p(lo), n_pairs, _p(oo)), L.tsm_layout(_p(ln), n_pairs, _p(on))
+    if to < 0 or tn < 0:
+        raise ValueError("pairs do not fit an int32-indexed arena")
+    ao, ko = host_buffer(to, pinned)
+    an, kn = host_buffer(tn, pinned)
+
+    def fill(t):
+        a, b = bounds[t], bounds[t + 1]
+        return 0 if a == b else L.tsm_gen_pair_fill(seed, b - a, first_index + a * index_stride, index_stride, cap, float(lam),
+                                                    _p(ext[a:b]), _p(oo[a:b + 1]), _p(lo[a:b]), _p(ao), _p(on[a:b + 1]), _p(ln[a:b]), _p(an))
+    run(fill)
+    return Corpus(ao, oo, lo, ext, None, 1, ko), Corpus(an, on, ln, ext.copy(), None, 1, kn)
 
 
 def gen_edit(seed, src: bytes, lam=6.0) -> bytes:
