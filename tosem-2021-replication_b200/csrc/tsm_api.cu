@@ -146,10 +146,10 @@ static void build_lut(uint32_t* lut) {                   // the one automaton ta
     }
 }
 
-static void build_lut2(uint32_t* lut) {                  // table of k_scan2: no `_F` gate, bit 31 = newline
+static void build_lut2(uint32_t* lut) {                  // table of k_scan2: bit 30 = 'F' (gate of the TEST_F check), bit 31 = newline
   struct Pat { const char* s; int first; bool ci; };
   static const Pat pats[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"class", 13, false}, {"def", 18, false},
-                             {"test", 21, true}, {"void", 25, false}, {"{", 29, false}, {"\n", 31, false}};
+                             {"test", 21, true}, {"void", 25, false}, {"{", 29, false}, {"F", 30, false}, {"\n", 31, false}};
   memset(lut, 0, 256 * sizeof(uint32_t));
   for (const Pat& p : pats)
     for (int k = 0; p.s[k]; ++k) {
@@ -319,7 +319,7 @@ static ScanParams make_params(const tsm_ctx* c, uint32_t flags) {
   p.cand = c->d_cand; p.cand_cap = (uint32_t)c->max_events;
   p.hev = c->d_hev; p.hev_cap = (uint32_t)c->max_events;
   p.aev = c->d_aev; p.aev_cap = (uint32_t)c->max_events;
-  p.counts = c->d_counts; p.flags = flags;
+  p.counts = c->d_counts; p.flags = flags; p.four = 4;
   return p;
 }
 
@@ -368,7 +368,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       k_plan<<<(f1 - f0 + 255) / 256, 256, 0, st>>>(p);
       if (s == 0 && n_slabs == 1) cudaEventRecord(ev[1], st);
       if (c->scan_v1) k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
-      else k_scan2<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN2_SMEM, st>>>(p);
+      else k_scan2<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
     }
     if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
     cudaEventRecord(ev[2], st);

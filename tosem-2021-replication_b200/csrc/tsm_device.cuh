@@ -112,6 +112,7 @@ struct ScanParams {
   uint32_t aev_cap;
   unsigned long long* counts;     // [n_groups + 1][K]
   uint32_t flags;
+  uint32_t four;                  // 4 (a multiplier the compiler must not see: tsm_scan2_kernels.cuh, lut_at)
 };
 
 // ---- hashing (SPEC section 3) -------------------------------------------------------------------------

@@ -4,15 +4,17 @@
 // (file, 4 KiB chunk) work unit, chunk staged global -> shared by one 1-D TMA bulk copy, every source byte
 // read from HBM exactly once.  What changed is how the per-line facts are produced:
 //
-//   * '\n' is a ninth pattern of the Shift-And automaton (state bit 31), so the OR of a word's eight
-//     states says for free whether the word holds a newline: no SWAR newline pass, no line table up front;
-//   * the walk keeps the OR of the states since the last newline word in a REGISTER and stores it behind
-//     every word (one STS): no per-word shared-memory atomicOr, no per-word line index arithmetic;
-//   * lines are finished per NEWLINE WORD (one lane per word that holds a newline, balanced over the warp
-//     through a small entry table): the line that ends at the word's first newline gets the stored OR,
-//     lines that lie inside the word (at most 6 bytes) are walked in place;
+//   * '\n' is one more pattern of the Shift-And automaton (state bit 31), so the OR of a word's eight
+//     states says for free whether the word holds a newline: no SWAR newline pass over every byte;
+//   * the walk keeps the OR of the states since the last newline word in a REGISTER and stores it in front
+//     of every word (one STS): no per-word shared-memory atomicOr, no per-word line index arithmetic;
+//   * only the words that hold a newline (~ 1 in 5) are looked at again: a dense pass turns them into one
+//     16-bit record per LINE, and the finish pass takes one line per lane with no inner loops: one hash
+//     prefix per line (the prefix behind its newline; the one in front of the line is the neighbour lane's);
 //   * a word that holds a newline AND a pattern end ("mixed", a few per chunk) is re-walked byte by byte
-//     by a dense pass that splits its states between the line that ends in it and the line that starts.
+//     by a dense pass that splits its states between the line that ends in it and the line that starts;
+//   * table addresses are formed by IMAD (FMA pipe) instead of LEA (ALU pipe): the kernel is bound by the ALU
+//     pipe, the FMA pipe is mostly idle (profiles/).
 //
 // The hash prefix machinery (Mersenne-61 running prefix, checkpoints, warp scan of the stripe totals) is
 // the first generation's.  There is no reference kernel; rules cite docs/SPEC.md.
@@ -21,39 +23,81 @@
 
 namespace tsm {
 
-__constant__ uint32_t c_lut2[256];                       // automaton table of this kernel (bit 31 = '\n')
+__constant__ uint32_t c_lut2[256];                       // automaton table of this kernel (bit 30 = 'F', bit 31 = '\n')
 
-// Pattern layout: the first generation's (tsm_device.cuh) without the `_F` gate, plus the newline bit.
-constexpr uint32_t B_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 18) | (1u << 21) | (1u << 25) | (1u << 29) | (1u << 31);
+// Pattern layout: the first generation's (tsm_device.cuh), with the `_F` gate reduced to one bit ('F' occurs in
+// the line) and the newline bit.
+constexpr uint32_t B_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 18) | (1u << 21) | (1u << 25) | (1u << 29) | (1u << 30) | (1u << 31);
+constexpr uint32_t B_F = 1u << 30;                       // gate of the TEST_F check
+
+#ifndef TSM_SCAN2_WARPS
+#define TSM_SCAN2_WARPS 11
+#endif
+#ifndef TSM_SCAN2_CTAS
+#define TSM_SCAN2_CTAS 2
+#endif
+#ifndef TSM_RW2_SHIFT
+#define TSM_RW2_SHIFT 2
+#endif
+#ifndef TSM_WALK_UNROLL
+#define TSM_WALK_UNROLL 1
+#endif
+constexpr int SCAN2_WARPS = TSM_SCAN2_WARPS, SCAN2_CTAS_PER_SM = TSM_SCAN2_CTAS, WALK_UNROLL = TSM_WALK_UNROLL;
 
 // ---- per-warp shared memory --------------------------------------------------------------------
 constexpr uint32_t NWORD = BUF / 8;                      // 544 words of 8 bytes, 17 per stripe
 constexpr uint32_t O2_ARUN = BUF;                        // u32[NWORD + 1]  OR of the states since the last newline word, in front of every word
 constexpr uint32_t SLOT_TAIL = NWORD;                    //                 (+ one slot: the line that ends with the data)
-constexpr uint32_t O2_RW = O2_ARUN + ((NWORD + 1) * 4 + 7) / 8 * 8;   // u64[32 * 4]   hash prefix behind words 3, 7, 11, 15 of every stripe
-constexpr uint32_t O2_ENT = O2_RW + 32 * 4 * 8;          // u16[ENT_CAP]    newline words in order (bit 15: mixed); later the candidate list
-constexpr uint32_t ENT_CAP = NWORD + 8;
-constexpr uint32_t ENT_VIRTUAL = 0x7FFFu;                // entry of the unterminated last line of a file
-constexpr uint32_t O2_BASE = O2_ENT + ENT_CAP * 2;       // u64[33]         hash prefix at every stripe start (+ total)
+constexpr uint32_t RW2_SHIFT = TSM_RW2_SHIFT, RW2_PER_STRIPE = 16u >> RW2_SHIFT;   // hash-prefix checkpoint behind every 2^RW2_SHIFT-th word
+constexpr uint32_t O2_RW = O2_ARUN + ((NWORD + 1) * 4 + 7) / 8 * 8;   // u64[32 * RW2_PER_STRIPE]
+constexpr uint32_t O2_WENT = O2_RW + 32 * RW2_PER_STRIPE * 8;         // u16[WENT_CAP]   newline words in order (bit 15: mixed)
+constexpr uint32_t WENT_CAP = NWORD + 8;
+constexpr uint32_t LCAP = 512;                           // line records per window
+constexpr uint32_t O2_LTAB = O2_WENT + WENT_CAP * 2;     // u16[LCAP]       line records; consumed ones are reused for the candidate list
+constexpr uint32_t O2_BASE = O2_LTAB + (LCAP + 8) * 2;   // u64[33]         hash prefix at every stripe start (+ total)
 constexpr uint32_t Q2_CAP = 64;
 constexpr uint32_t O2_Q = O2_BASE + 34 * 8;              // u16[Q2_CAP]     mixed words
 constexpr uint32_t O2_CTL = O2_Q + Q2_CAP * 2;           // u32 queue length, pad, u64 mbarrier
 constexpr uint32_t WARP_SMEM2 = ((O2_CTL + 16 + 127) / 128) * 128;
-constexpr uint32_t SCAN2_SMEM = LUT_BYTES + SCAN_WARPS * WARP_SMEM2;
-static_assert(O2_RW % 8 == 0 && O2_ENT % 8 == 0 && O2_BASE % 8 == 0 && O2_Q % 4 == 0 && O2_CTL % 8 == 0, "alignment");
+// per CTA in front of the warps: automaton table (1 KB), per-language masks + the opaque 4 (128 B), rotations of '\n' (61 x 8 B)
+constexpr uint32_t O2_T0A = LUT_BYTES;
+constexpr uint32_t CTA_BYTES2 = LUT_BYTES + 512;
+constexpr uint32_t SCAN2_SMEM = CTA_BYTES2 + SCAN2_WARPS * WARP_SMEM2;
+static_assert(O2_RW % 8 == 0 && O2_WENT % 8 == 0 && O2_LTAB % 2 == 0 && O2_BASE % 8 == 0 && O2_Q % 4 == 0 && O2_CTL % 8 == 0, "alignment");
+static_assert(SCAN2_CTAS_PER_SM * SCAN2_SMEM <= 232448, "shared memory per SM");
+// line record: bits 0..12 position of the line's end in the buffer, 13 = first newline of its word (the word's stored
+// OR is the line's), 14 = the word is mixed, 15 = no newline: the unterminated last line of a file
+constexpr uint32_t LR_POS = 0x1FFFu, LR_FIRST = 0x2000u, LR_MIXED = 0x4000u, LR_VIRT = 0x8000u;
+
+// Table entry of byte `idx`.  The address is formed by an integer multiply-add whose factor (4) the compiler
+// cannot see: IMAD runs on the FMA pipe, the LEA it replaces on the ALU pipe.
+#ifndef TSM_PIPE_BALANCE
+#define TSM_PIPE_BALANCE 1
+#endif
+__device__ __forceinline__ uint32_t lut_at(uint32_t idx, uint32_t four) {
+#if TSM_PIPE_BALANCE
+  uint32_t addr, v;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(idx), "r"(four), "r"(smem_u32(scan_lut())));
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+#else
+  (void)four;
+  return scan_lut()[idx];
+#endif
+}
+__device__ __forceinline__ uint32_t opaque_four() { return scan_lut()[256 + 12]; }   // written by the kernel prologue from a launch parameter
 
 // Eight automaton steps over one 8-byte word; A collects every state of the word.
-__device__ __forceinline__ void step8b(unsigned long long w, uint32_t& D, uint32_t& A) {
-  const uint32_t* lut = scan_lut();
+__device__ __forceinline__ void step8b(unsigned long long w, uint32_t& D, uint32_t& A, uint32_t four) {
   const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | B_FIRST) & lut[__byte_perm(lo, 0, 0x4440 + k)];
+    D = ((D + D) | B_FIRST) & lut_at(__byte_perm(lo, 0, 0x4440 + k), four);
     A |= D;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | B_FIRST) & lut[__byte_perm(hi, 0, 0x4440 + k)];
+    D = ((D + D) | B_FIRST) & lut_at(__byte_perm(hi, 0, 0x4440 + k), four);
     A |= D;
   }
 }
@@ -76,24 +120,25 @@ __device__ __noinline__ WalkOut walk2(uint8_t* wb, uint32_t fin, int lane) {
   const uint32_t pos0 = (uint32_t)lane * STRIPE;
   const uint8_t* sp = wb + pos0;
   uint32_t* ar = reinterpret_cast<uint32_t*>(wb + O2_ARUN) + (uint32_t)lane * 17u;
-  unsigned long long* rw = reinterpret_cast<unsigned long long*>(wb + O2_RW) + (uint32_t)lane * 4u;
+  unsigned long long* rw = reinterpret_cast<unsigned long long*>(wb + O2_RW) + (uint32_t)lane * RW2_PER_STRIPE;
+  const uint32_t four = opaque_four();
   uint32_t D = 0;
   if (lane) {                                            // state in front of the stripe (no pattern is longer than 7 bytes)
     uint32_t A = 0;
-    step8b(*reinterpret_cast<const unsigned long long*>(sp - 8), D, A);
+    step8b(*reinterpret_cast<const unsigned long long*>(sp - 8), D, A, four);
   }
   unsigned long long R = 0;
   uint32_t run = 0, nlr = 0;                             // nlr: newline-word bits, the newest word in bit 0
 #pragma unroll 1
   for (uint32_t g = 0; g < 5; ++g) {
-#pragma unroll
+#pragma unroll WALK_UNROLL
     for (uint32_t k = 0; k < 4; ++k) {
       if (g == 4 && k) break;
       const unsigned long long w = *reinterpret_cast<const unsigned long long*>(sp + 32u * g + 8u * k);
       uint32_t A = 0;
-      step8b(w, D, A);
+      step8b(w, D, A, four);
       R = ror3_61(R) + fold61(w);                        // lazily reduced: stays below 2^63
-      if (k == 3) rw[g] = R;
+      if (((k + 1u) & ((1u << RW2_SHIFT) - 1u)) == 0u && g < 4u) rw[(4u * g + k) >> RW2_SHIFT] = R;   // (not behind the 17th word)
       ar[4u * g + k] = run;
       nlr = __funnelshift_l(A, nlr, 1);                  // bit 31 of A: the word holds a newline
       const bool nl = (int32_t)A < 0;
@@ -120,12 +165,12 @@ __device__ __noinline__ WalkOut walk2(uint8_t* wb, uint32_t fin, int lane) {
 }
 
 // A mixed word (newline + pattern end), byte by byte: the states in front of its first newline belong to the
-// line that ends there (entry i), the states behind its last newline to the line that ends at the next entry.
-// Lines inside the word are walked by the finish pass itself (the entry's bit 15 asks for it).
-__device__ __forceinline__ void resolve_mixed(uint8_t* wb, uint32_t g, uint32_t i, uint32_t n_real) {
+// line that ends there (word entry i), the states behind its last newline to the line that ends at the next
+// entry.  Lines inside the word are walked by the finish pass itself (LR_MIXED asks for it).
+__device__ __noinline__ void resolve_mixed(uint8_t* wb, uint32_t g, uint32_t i, uint32_t n_went) {
   const uint32_t* lut = scan_lut();
   uint32_t D = 0, A = 0;
-  step8b(*reinterpret_cast<const unsigned long long*>(wb + 8u * g - 8u), D, A);   // g >= 2: the first 16 bytes are zeros
+  step8b(*reinterpret_cast<const unsigned long long*>(wb + 8u * g - 8u), D, A, opaque_four());   // g >= 2: the first 16 bytes are zeros
   unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + 8u * g);
   uint32_t pre = 0, post = 0, seen = 0;
 #pragma unroll
@@ -138,28 +183,10 @@ __device__ __forceinline__ void resolve_mixed(uint8_t* wb, uint32_t g, uint32_t 
     w >>= 8;
   }
   uint32_t* arun = reinterpret_cast<uint32_t*>(wb + O2_ARUN);
-  const uint16_t* ent = reinterpret_cast<const uint16_t*>(wb + O2_ENT);
+  const uint16_t* went = reinterpret_cast<const uint16_t*>(wb + O2_WENT);
   atomicOr(arun + g, pre);
-  const uint32_t tgt = i + 1u < n_real ? ((uint32_t)ent[i + 1u] & 0x3FFu) : SLOT_TAIL;
+  const uint32_t tgt = i + 1u < n_went ? ((uint32_t)went[i + 1u] & 0x3FFu) : SLOT_TAIL;
   atomicOr(arun + tgt, post);
-}
-
-// Hash prefixes (SPEC section 3) of the staged bytes [0, 8g + b1) and [0, 8g + b2), every byte weighted
-// 256^position, lazily reduced (< 2^62 + 2).  w = word g.
-__device__ __forceinline__ void prefix_pair(const uint8_t* wb, uint32_t g, unsigned long long w, uint32_t b1, uint32_t b2,
-                                            unsigned long long& P1, unsigned long long& P2) {
-  const uint32_t l = g / 17u, i = g - 17u * l, c0 = i >> 2, ns = i & 3u;
-  unsigned long long R = 0;
-  if (c0) R = *reinterpret_cast<const unsigned long long*>(wb + O2_RW + 8u * (l * 4u + c0 - 1u));
-  const unsigned long long* wp = reinterpret_cast<const unsigned long long*>(wb) + (g - ns);   // words since the checkpoint
-  if (ns > 0u) R = ror3_61(R) + fold61(wp[0]);
-  if (ns > 1u) R = ror3_61(R) + fold61(wp[1]);
-  if (ns > 2u) R = ror3_61(R) + fold61(wp[2]);
-  const unsigned long long Q = ror3_61(R);               // frame of word g
-  const uint32_t r3g = (3u * g) % 61u;
-  const unsigned long long sb = *reinterpret_cast<const unsigned long long*>(wb + O2_BASE + 8u * l);
-  P1 = sb + rotl61(fold61(fold61(Q + fold61(w & low_mask(b1)))), r3g);
-  P2 = sb + rotl61(fold61(fold61(Q + fold61(w & low_mask(b2)))), r3g);
 }
 
 __device__ __forceinline__ void emit_header(const ScanParams& p, uint32_t f, uint32_t line_off, uint32_t len, uint32_t fl) {
@@ -168,86 +195,136 @@ __device__ __forceinline__ void emit_header(const ScanParams& p, uint32_t f, uin
   else p.ctrl->overflow = 1;
 }
 
-// Finish pass: one lane per newline word (entry).  Line "A" of an entry ends at the word's first newline and
-// starts behind the last newline of the entry in front of it; its hash is the difference of two prefixes, its
-// pattern flags are the word's stored OR.  The other newlines of the word end lines of at most 6 bytes that lie
-// inside the word.  A line belongs to the chunk its first byte lies in (start < lim).  The starts of the
-// assertion lines are compacted (u16 each) over the entries already consumed.  Returns their number.
-__device__ __noinline__ uint32_t finish_entries(const ScanParams& p, uint8_t* wb, const uint32_t* lc, uint32_t n_real, uint32_t n_tot,
-                                                uint32_t X, uint32_t lim, bool skip_first, uint32_t f, uint32_t cb, int ext,
-                                                int lane, Accum& ac) {
-  uint16_t* ent = reinterpret_cast<uint16_t*>(wb + O2_ENT);
+// Does the stripped line [s, e) start with the n <= 7 bytes of `pat` (little-endian in a u64)?  With need_ws the
+// byte behind them must be a blank that lies inside the stripped line (SPEC section 5, `class`).  Staged bytes only.
+__device__ __noinline__ bool starts_with8(SmemByte lb, uint32_t s, uint32_t e, unsigned long long pat, uint32_t n, bool need_ws) {
+  uint32_t r;
+  while (s + 8 <= e && (r = lb.spaces8(s)) != 0) { s += r; if (r < 8) break; }
+  while (s < e && is_w(lb(s))) ++s;
+  if (s + n + (need_ws ? 1u : 0u) > e) return false;
+  const unsigned long long v = lb.load8(s);              // readable 8 bytes past any line of the buffer
+  if ((v & low_mask(n)) != pat) return false;
+  if (need_ws) {
+    const uint32_t c = (uint32_t)(v >> (8u * n)) & 0xFFu;
+    if (c != 0x20 && c != 0x09) return false;
+    for (uint32_t q = s + n + 1; q < e; ++q)
+      if (!is_w(lb(q))) return true;
+    return false;
+  }
+  return true;
+}
+
+// Flags of a finished line (SPEC sections 4 / 5) from the OR of its automaton states; adds it to the per-file counters.
+__device__ __forceinline__ uint32_t line_flags2(uint32_t s, uint32_t e, uint32_t A, uint32_t g1, uint32_t g2, int ext, SmemByte lb, Accum& ac) {
+  if (ext == 0) return 0;
+  uint32_t fl = (A & (AF_ASSERT | AF_EXPECT)) ? LF_CAND : 0;
+  bool hdr;
+  if (ext == TSM_EXT_PY) {
+    hdr = (A & g1) != 0;
+    if (!hdr && (A & g2)) hdr = starts_with8(lb, s, e, 0x7373616C63ull, 5, true);           // "class" + blank
+  } else {
+    hdr = (A & g1) != 0 && (A & g2) != 0;
+  }
+  if (hdr) { fl |= LF_HDR; if ((A & B_F) && starts_with8(lb, s, e, 0x465F54534554ull, 6, false)) fl |= LF_FIX; }   // "TEST_F"
+  ac.asserts += fl & LF_CAND;
+  ac.hdrs += (fl >> 1) & 1u;
+  ac.fixes += (fl >> 2) & 1u;
+  return fl;
+}
+
+struct FinishState {                                     // carried from one window of line records to the next
+  uint32_t prev_last;                                    // newline in front of the next line
+  unsigned long long prevP;                              // hash prefix of the bytes [0, prev_last]
+};
+
+// Finish pass over the n line records of the window: one lane per line, no inner loops.  The hash of a line is
+// the difference of two prefixes: the one behind its own newline minus the newline byte, and the one behind the
+// newline in front of it, which is the neighbour lane's.  A line belongs to the chunk its first byte lies in
+// (start < lim).  The starts of the assertion lines are compacted (u16 each) over the records already consumed
+// and go to the global candidate list at the end of the window.
+__device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, const uint32_t* lc, uint32_t n, uint32_t lim,
+                                           bool skip_first, uint32_t f, uint32_t cb, int ext, int lane, Accum& ac, FinishState& fs) {
+  uint16_t* ltab = reinterpret_cast<uint16_t*>(wb + O2_LTAB);
   const uint32_t* arun = reinterpret_cast<const uint32_t*>(wb + O2_ARUN);
+  const unsigned long long* t0a = reinterpret_cast<const unsigned long long*>(scan_lut()) + O2_T0A / 8;
   const uint32_t g1 = lc[1], g2 = lc[2];
   const SmemByte lb{wb};
   const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
   Accum a = ac;
   uint32_t nc = 0;
-  uint32_t prev_last = PRE - 1u;                         // newline in front of the next line (the 16 bytes in front of the chunk are zeros)
-  unsigned long long prevP = 0;                          // hash prefix of the bytes [0, prev_last]
-  for (uint32_t base = 0; base < n_tot; base += 32) {    // uniform trip count
+  uint32_t prev_last = fs.prev_last;
+  unsigned long long prevP = fs.prevP;
+  for (uint32_t base = 0; base < n; base += 32) {        // uniform trip count
     const uint32_t j = base + (uint32_t)lane;
-    const bool valid = j < n_tot;
-    const uint32_t ge = valid ? (uint32_t)ent[j] : 0u;
-    const bool isv = valid && j >= n_real;               // the unterminated last line of the file: ends at X
-    const uint32_t g = isv ? (X - 1u) >> 3 : (ge & 0x3FFu);
+    const bool valid = j < n;
+    const uint32_t rec = valid ? (uint32_t)ltab[j] : 0u;
+    const uint32_t e = rec & LR_POS;
+    const bool isv = (rec & LR_VIRT) != 0;
+    const uint32_t g = min(e >> 3, NWORD - 1u), b1 = e - 8u * g + (isv ? 0u : 1u);   // bytes of word g up to and including the newline
+    // ---- Pn: hash prefix of the bytes [0, e] (SPEC section 3; lazily reduced, < 2^62 + 8)
+    const uint32_t l = g / 17u, i = g - 17u * l, c0 = i >> RW2_SHIFT, ns = i & ((1u << RW2_SHIFT) - 1u);
+    unsigned long long R = 0;
+    if (c0) R = *reinterpret_cast<const unsigned long long*>(wb + O2_RW + 8u * (l * RW2_PER_STRIPE + c0 - 1u));
+    const unsigned long long* wp = reinterpret_cast<const unsigned long long*>(wb) + (g - ns);   // words since the checkpoint
+#pragma unroll
+    for (uint32_t t = 0; t + 1u < (1u << RW2_SHIFT); ++t)
+      if (ns > t) R = ror3_61(R) + fold61(wp[t]);
     const unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + 8u * g);
-    const uint32_t nl8 = isv ? (1u << (X - 8u * g)) : (valid ? nl8_of(w) : 1u);
-    const uint32_t p1 = (uint32_t)__ffs((int)nl8) - 1u, p2 = 31u - (uint32_t)__clz((int)nl8);
-    const uint32_t e = 8u * g + p1, eL = 8u * g + p2;
-    unsigned long long Pe, Pn;
-    prefix_pair(wb, g, w, p1, p2 + 1u, Pe, Pn);
-    if (isv) Pe = *reinterpret_cast<const unsigned long long*>(wb + O2_BASE + 8u * 32u);   // everything staged (zeros behind X)
-    uint32_t s = __shfl_up_sync(0xffffffffu, eL, 1) + 1u;
+    const uint32_t r3g = (3u * g) % 61u;
+    const unsigned long long X = ror3_61(R) + fold61(w & low_mask(b1));
+    unsigned long long Pn = *reinterpret_cast<const unsigned long long*>(wb + O2_BASE + 8u * l) + rotl61(fold61(fold61(X)), r3g);
+    // ---- Pe: the same without the newline byte
+    uint32_t r8e = r3g + 8u * (e & 7u);
+    if (r8e >= 61u) r8e -= 61u;
+    const unsigned long long Pe = isv ? Pn : Pn + M61 - t0a[r8e];
+    uint32_t s = __shfl_up_sync(0xffffffffu, e, 1) + 1u;
     unsigned long long Ps = __shfl_up_sync(0xffffffffu, Pn, 1);
     if (lane == 0) { s = prev_last + 1u; Ps = prevP; }
-    prev_last = __shfl_sync(0xffffffffu, eL, 31);
-    prevP = __shfl_sync(0xffffffffu, Pn, 31);
+    const int src = base + 32u <= n ? 31 : (int)(n - 1u - base);         // the round's last record
+    prev_last = __shfl_sync(0xffffffffu, e, src);
+    prevP = __shfl_sync(0xffffffffu, Pn, src);
     const bool owned = valid && s < lim && !(s == PRE && skip_first);
     uint32_t fl = 0;
     if (owned) {
-      const uint32_t A = arun[isv ? SLOT_TAIL : g];
       const unsigned long long hr = canon61(Pe + 4ull * M61 - Ps);       // bytes [s, e), weighted from position 0
       const uint32_t sh = (8u * s) % 61u;
-      const unsigned long long h0 = rotl61(hr, sh ? 61u - sh : 0u);
-      fl = line_finish_h(s, e, h0, flag_nibble(A, g1, g2, 0u), ext, lb, a);
+      unsigned long long h = rotl61(hr, sh ? 61u - sh : 0u);
+      uint32_t len = e - s;
+      if (len && lb(e - 1u) == 0x0D) {                   // drop one trailing CR: subtract 0x0D * 256^(len-1)
+        --len;
+        const unsigned long long cr = rotl61(0x0Dull, (8u * len) % 61u);
+        h = h >= cr ? h - cr : h + M61 - cr;
+      }
+      a.lines++;
+      a.digest += mix_hash(h, len);
+      uint32_t A = 0;
+      if (rec & LR_FIRST) A = arun[isv ? SLOT_TAIL : g];
+      else if (rec & LR_MIXED) {                         // a line inside a mixed word: its own states
+        const uint32_t* lut = scan_lut();
+        uint32_t D = 0;
+        for (uint32_t q = s; q < e; ++q) { D = ((D + D) | B_FIRST) & lut[lb(q)]; A |= D; }
+      }
+      fl = line_flags2(s, e, A, g1, g2, ext, lb, a);
       if (want_hev && (fl & LF_HDR)) emit_header(p, f, cb + s - PRE, e - s, fl);
     }
-    __syncwarp();                                        // every entry of the round is read: the list may grow over them
+    __syncwarp();                                        // every record of the round is read: the list may grow over them
     const uint32_t mc = __ballot_sync(0xffffffffu, fl & LF_CAND);
-    if (fl & LF_CAND) ent[nc + __popc(mc & ((1u << lane) - 1u))] = (uint16_t)s;
+    if (fl & LF_CAND) ltab[nc + __popc(mc & ((1u << lane) - 1u))] = (uint16_t)s;
     nc += __popc(mc);
-    // ---- lines inside the word (behind its first newline): content of at most 6 bytes
-    uint32_t rest = (valid && !isv) ? (nl8 & (nl8 - 1u)) : 0u;
-    while (__any_sync(0xffffffffu, rest != 0u)) {
-      if (rest) {
-        const uint32_t q2 = (uint32_t)__ffs((int)rest) - 1u;
-        const uint32_t q1 = 31u - (uint32_t)__clz((int)(nl8 & ((1u << q2) - 1u)));
-        const uint32_t si = 8u * g + q1 + 1u, len = q2 - q1 - 1u;
-        if (si < lim) {
-          const unsigned long long v = (w >> (8u * (q1 + 1u))) & low_mask(len);   // < 2^48: canonical as it is
-          uint32_t A2 = 0;
-          if ((ge & 0x8000u) && len) {                   // mixed word: the line's own states
-            const uint32_t* lut = scan_lut();
-            uint32_t D = 0;
-            unsigned long long t = v;
-            for (uint32_t c = 0; c < len; ++c) { D = ((D + D) | B_FIRST) & lut[(uint32_t)t & 0xFFu]; A2 |= D; t >>= 8; }
-          }
-          const uint32_t fl2 = line_finish_h(si, si + len, v, flag_nibble(A2, g1, g2, 0u), ext, lb, a);
-          if (fl2 & LF_CAND) {
-            const uint32_t slot = atomicAdd(&p.ctrl->n_cand, 1u);
-            if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | (cb + si - PRE);
-            else p.ctrl->overflow = 1;
-          }
-          if (want_hev && (fl2 & LF_HDR)) emit_header(p, f, cb + si - PRE, len, fl2);
-        }
-        rest &= rest - 1u;
-      }
-    }
-    __syncwarp();
   }
+  __syncwarp();
+  if (nc) {                                              // candidates of the window to their global list
+    const uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
+    for (uint32_t i = (uint32_t)lane; i < nc; i += 32) {
+      const uint32_t slot = cbase + i;
+      if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | (cb + (uint32_t)ltab[i] - PRE);
+      else p.ctrl->overflow = 1;
+    }
+  }
+  __syncwarp();
   ac = a;
-  return nc;
+  fs.prev_last = prev_last;
+  fs.prevP = prevP;
 }
 
 __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t f,
@@ -277,30 +354,26 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   const uint32_t gx = __reduce_min_sync(0xffffffffu, extbits ? w0 + (uint32_t)__ffs((int)extbits) - 1u : 0xFFFFu);
   uint32_t kept = wo.nlw & ownbits;
   if (gx - w0 < 17u) kept |= 1u << (gx - w0);
-  // ---- states of a line that spans stripes: OR of the stripe tails back to the stripe of its first byte
+  // ---- states of a line that spans stripes: OR of the stripe tails back to the stripe of its first byte;
+  //      and the positions of the kept newline words in the entry table (two scans, one loop)
   uint32_t tv = wo.tail, tf = wo.nlw != 0u;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t uv = __shfl_up_sync(0xffffffffu, tv, d), uf = __shfl_up_sync(0xffffffffu, tf, d);
-    if (lane >= d) { if (!tf) tv |= uv; tf |= uf; }
-  }
-  uint32_t carry = __shfl_up_sync(0xffffffffu, tv, 1);
-  if (lane == 0) carry = 0;
-  const uint32_t tail_all = __shfl_sync(0xffffffffu, tv, 31);
-  // ---- entry table: the kept newline words in order
   const uint32_t cnt = __popc(kept);
   uint32_t incl = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t uv = __shfl_up_sync(0xffffffffu, tv, d), uf = __shfl_up_sync(0xffffffffu, tf, d);
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
+    if (lane >= d) { if (!tf) tv |= uv; tf |= uf; incl += t; }
   }
-  const uint32_t n_real = __shfl_sync(0xffffffffu, incl, 31), ebase = incl - cnt;
-  uint16_t* ent = reinterpret_cast<uint16_t*>(wb + O2_ENT);
+  uint32_t carry = __shfl_up_sync(0xffffffffu, tv, 1);
+  if (lane == 0) carry = 0;
+  const uint32_t tail_all = __shfl_sync(0xffffffffu, tv, 31);
+  const uint32_t n_went = __shfl_sync(0xffffffffu, incl, 31), ebase = incl - cnt;
+  uint16_t* went = reinterpret_cast<uint16_t*>(wb + O2_WENT);
   uint32_t* arun = reinterpret_cast<uint32_t*>(wb + O2_ARUN);
   {
     uint32_t b = kept, idx = ebase;
-    while (b) { ent[idx++] = (uint16_t)(w0 + (uint32_t)__ffs((int)b) - 1u); b &= b - 1u; }
+    while (b) { went[idx++] = (uint16_t)(w0 + (uint32_t)__ffs((int)b) - 1u); b &= b - 1u; }
     if (wo.nlw) arun[w0 + (uint32_t)__ffs((int)wo.nlw) - 1u] |= carry;
     if (lane == 0) arun[SLOT_TAIL] = tail_all;
   }
@@ -317,44 +390,66 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
         const uint32_t m = __shfl_sync(0xffffffffu, kept, (int)l), eb = __shfl_sync(0xffffffffu, ebase, (int)l);
         const bool act = t < nq_all && ((m >> k) & 1u);
         const uint32_t i = eb + __popc(m & ((1u << k) - 1u));
-        if (act) resolve_mixed(wb, g, i, n_real);
+        if (act) resolve_mixed(wb, g, i, n_went);
         __syncwarp();
-        if (act) ent[i] |= 0x8000u;
+        if (act) went[i] |= 0x8000u;
         __syncwarp();
       }
     } else if (lc[0]) {                                  // queue overflow: take every newline word as mixed
-      for (uint32_t base = 0; base < n_real; base += 32) {
+      for (uint32_t base = 0; base < n_went; base += 32) {
         const uint32_t i = base + (uint32_t)lane;
-        if (i < n_real) resolve_mixed(wb, (uint32_t)ent[i] & 0x3FFu, i, n_real);
+        if (i < n_went) resolve_mixed(wb, (uint32_t)went[i] & 0x3FFu, i, n_went);
         __syncwarp();
-        if (i < n_real) ent[i] |= 0x8000u;
+        if (i < n_went) went[i] |= 0x8000u;
         __syncwarp();
       }
     }
   }
-  // ---- the line behind the last newline: ends with the file (virtual entry), lies in the next chunk, or is long
-  uint32_t final_prev = PRE - 1u;
-  if (n_real) {
-    const uint32_t gl = (uint32_t)ent[n_real - 1u] & 0x3FFu;
-    const uint32_t m = nl8_of(*reinterpret_cast<const unsigned long long*>(wb + 8u * gl));
-    final_prev = 8u * gl + 31u - (uint32_t)__clz((int)m);
-  }
-  const uint32_t tail_start = final_prev + 1u;
-  bool virt = false, tail_long = false;
-  if (tail_start < lim && !(skip_first && n_real == 0u)) {
-    if (le == size) virt = tail_start < lim2;            // unterminated last line of the file (the data ends at lim2)
-    else tail_long = true;
-  }
-  const uint32_t nc = finish_entries(p, wb, lc, n_real, n_real + (virt ? 1u : 0u), lim2, lim, skip_first, f, cb, ext, lane, ac);
-  // ---- candidates to their global list
-  if (nc) {
-    const uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
-    for (uint32_t i = (uint32_t)lane; i < nc; i += 32) {
-      const uint32_t slot = cbase + i;
-      if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | (cb + (uint32_t)ent[i] - PRE);
-      else p.ctrl->overflow = 1;
+  // ---- newline words -> one record per line (dense: one lane per newline word, SWAR for the newline bytes),
+  //      finished window by window (one window unless the chunk has more than ~LCAP lines)
+  uint16_t* ltab = reinterpret_cast<uint16_t*>(wb + O2_LTAB);
+  FinishState fs{PRE - 1u, 0ull};                        // (the 16 bytes in front of the chunk are zeros)
+  uint32_t n_rec = 0, last_nl = PRE - 1u;
+  for (uint32_t base = 0; base < n_went; base += 32) {
+    const uint32_t j = base + (uint32_t)lane;
+    const uint32_t ge = j < n_went ? (uint32_t)went[j] : 0u;
+    const uint32_t g = ge & 0x3FFu;
+    uint32_t m = j < n_went ? nl8_of(*reinterpret_cast<const unsigned long long*>(wb + 8u * g)) : 0u;
+    const uint32_t c = __popc(m);
+    uint32_t in2 = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
+      if (lane >= d) in2 += t;
+    }
+    if (base + 32u >= n_went) {                          // position of the chunk's last newline
+      const uint32_t lastl = n_went - 1u - base;
+      last_nl = __shfl_sync(0xffffffffu, 8u * g + 31u - (uint32_t)__clz((int)(m | 1u)), (int)lastl);
+    }
+    uint32_t off = n_rec + in2 - c;
+    uint32_t rec = 8u * g + LR_FIRST + ((ge >> 15) << 14);
+    while (m) {
+      ltab[off++] = (uint16_t)(rec + (uint32_t)__ffs((int)m) - 1u);
+      rec &= ~LR_FIRST;
+      m &= m - 1u;
+    }
+    n_rec += __shfl_sync(0xffffffffu, in2, 31);
+    __syncwarp();
+    if (n_rec + 256u > LCAP && base + 32u < n_went) {    // the next round may not fit: finish what is there
+      finish_lines2(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
+      n_rec = 0;
     }
   }
+  // ---- the line behind the last newline: ends with the file (virtual record), lies in the next chunk, or is long
+  const uint32_t tail_start = last_nl + 1u;
+  bool tail_long = false;
+  if (tail_start < lim && !(skip_first && n_went == 0u)) {
+    if (le == size) {                                    // unterminated last line of the file (the data ends at lim2)
+      if (tail_start < lim2) { if (lane == 0) ltab[n_rec] = (uint16_t)(lim2 | LR_VIRT | LR_FIRST); ++n_rec; }
+    } else tail_long = true;
+  }
+  __syncwarp();
+  if (n_rec) finish_lines2(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
   if (tail_long && lane == 0) long_line(p, scan_lut(), B_FIRST, f, fo, size, ext, cb + tail_start - PRE, ac);
   // ---- per-file counters: warp reduce (the digest as three partial sums: low halves keep their carries),
   //      then one store (single-chunk file) or one atomic per counter
@@ -383,31 +478,37 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   }
 }
 
-__global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan2(ScanParams p) {
+__global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan2(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) the automaton table, then 3 x 4 per-language masks
+  uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) the automaton table, then 3 x 4 per-language masks, the opaque 4
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[i] = c_lut2[i];
   if (threadIdx.x < 12) {                                // per language (PY, C family, none): pattern ends that count, then the header groups
     const int t = threadIdx.x, lang = t >> 2, q = t & 3;
     const uint32_t g1 = lang == 0 ? PY_G1 : CJ_G1, g2 = lang == 0 ? PY_G2 : CJ_G2;
-    const uint32_t v = q == 0 ? (AF_ASSERT | AF_EXPECT | g1 | g2) : (q == 1 ? g1 : (q == 2 ? g2 : 0u));
+    const uint32_t v = q == 0 ? (AF_ASSERT | AF_EXPECT | g1 | g2 | B_F) : (q == 1 ? g1 : (q == 2 ? g2 : 0u));
     lut_all[256 + t] = lang == 2 ? 0u : v;
   }
+  if (threadIdx.x == 12) lut_all[256 + 12] = p.four;
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + 61)        // rotations of the newline byte: 0x0A * 2^r mod 2^61-1
+    reinterpret_cast<unsigned long long*>(smem + O2_T0A)[threadIdx.x - 32] = rotl61(0x0Aull, threadIdx.x - 32);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* wb = smem + LUT_BYTES + warp * WARP_SMEM2;
+  uint8_t* wb = smem + CTA_BYTES2 + warp * WARP_SMEM2;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wb + O2_CTL + 8);
   if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   __syncwarp();
   const uint32_t n_units = p.slab->n_units;
   uint32_t phase = 0;
   Unit cur = claim_unit(p, n_units, lane);
-#if TSM_LOCKSTEP
+#ifndef TSM_LOCKSTEP2
+#define TSM_LOCKSTEP2 0
+#endif
+#if TSM_LOCKSTEP2
   while (__syncthreads_or(cur.u < n_units)) {
     if (cur.u >= n_units) continue;
 #else
-  while (cur.u < n_units) {
-#endif
+  while (cur.u < n_units) {                              // (no CTA-wide chunk start: with the walk as one rolled loop the hot code fits the
+#endif                                                   //  instruction cache and the barrier only costs; profiles/r2_variants.txt)
     fence_proxy_async();                                 // this warp's zero fill and reads of the last chunk come first
     __syncwarp();
     if (lane == 0) issue_load(p, wb, bar, cur.fo, cur.size, cur.cb);
