@@ -40,6 +40,7 @@ enum { TSM_EXT_OTHER = 0, TSM_EXT_PY = 1, TSM_EXT_CC = 2, TSM_EXT_CPP = 3, TSM_E
 /* scan flags */
 #define TSM_SCAN_ASSERT_EVENTS 1u  /* produce assertion events (raw scan rows need them) */
 #define TSM_SCAN_HEADER_EVENTS 2u  /* produce header events (method column needs them) */
+#define TSM_SCAN_LINE_HASHES 4u    /* internal to tsm_line_hashes / tsm_diff_pairs*: per-line records; ignored by tsm_scan* */
 
 /* Per-file record; replaces the per-file summary stage (S6: `total assert` of
  * selection/completed-labels/Release-Meta-tpot.csv:1-2). */
@@ -127,6 +128,16 @@ int tsm_diff_pairs(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
 typedef struct tsm_diff_detail { int64_t hunks_add, hunks_del, hunks_mod, added_assert, removed_assert; } tsm_diff_detail;
 int tsm_diff_pairs_detail(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
                           int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream);
+
+/* S9 line / n-gram hashes (docs/SPEC.md section 3; SURVEY.md section 8a S9 - a design choice of the north star, attested by no
+ * artefact of the package): the records of every line of every file, files in order, from ONE pass of the scan
+ * kernel over the source.  line_base[n_files+1] and *n_lines are always filled; line_hash (SPEC section 3), line_end
+ * (file-relative position of the line's LF, or the file size), line_flag (1 = assertion line, SPEC section 4, by the
+ * file's ext) and ngram_hash hold `cap` lines each and may be NULL; if cap < *n_lines the call returns TSM_E_CAPACITY
+ * so that the caller can size the arrays and call again.  ngram_hash[i] = hash of the window of up to ngram_n
+ * consecutive lines of the same file that starts at line i.  tsm_diff_pairs* and tsm_statements use the same pass. */
+int tsm_line_hashes(tsm_ctx* ctx, const tsm_corpus* corpus, int64_t* line_base, uint64_t* line_hash, uint32_t* line_end,
+                    uint8_t* line_flag, int64_t cap, int64_t* n_lines, int32_t ngram_n, uint64_t* ngram_hash, void* stream);
 
 /* Body statements (docs/SPEC.md section 10; Important-files/ML-Analysis-v4.xlsx!Apollo:R2-R26, golden G2): the
  * kind of every line of every file - 0 blank, 1 first line of a statement, 2 continuation (lines

@@ -55,6 +55,28 @@ uint64_t orc_line_hash(const uint8_t* line, uint64_t len) {
   return orc_bytes_hash(line, len);
 }
 
+/* SPEC section 3, n-gram hash: the window of up to n consecutive line hashes of one file that starts at line i,
+ * G = sum over k of (line_hash[i+k] mod 2^61-1) * 2^(13k)  mod 2^61-1, finalised with the window length.
+ * (S9 is a design choice of the north star; no artefact of the package attests it: SURVEY.md section 8a.) */
+void orc_ngram_hashes(const uint64_t* line_hash, const int64_t* line_base, int32_t n_files, int32_t n, uint64_t* out) {
+  for (int32_t f = 0; f < n_files; ++f)
+    for (int64_t i = line_base[f]; i < line_base[f + 1]; ++i) {
+      uint64_t acc = 0;
+      unsigned r = 0;
+      int32_t k = 0;
+      for (; k < n && i + k < line_base[f + 1]; ++k) {
+        uint64_t h = fold61(fold61(line_hash[i + k]));
+        if (h == M61) h = 0;
+        acc = fold61(acc + rotl61(h, r));
+        r += 13;
+        if (r >= 61) r -= 61;
+      }
+      acc = fold61(acc);
+      if (acc == M61) acc = 0;
+      out[i] = finalise(acc, (uint64_t)k);
+    }
+}
+
 /* ---------------------------------------------------------------- helpers */
 static inline int is_w(uint8_t c) { return c == 0x20 || c == 0x09 || c == 0x0D || c == 0x0B || c == 0x0C; }
 static inline int is_ident(uint8_t c) {

@@ -31,6 +31,9 @@ typedef struct { uint32_t file, line_off, line_len, kind; } orc_header_event;
 uint64_t orc_bytes_hash(const uint8_t* p, uint64_t len);
 uint64_t orc_line_hash(const uint8_t* line, uint64_t len); /* drops one trailing CR */
 
+/* SPEC section 3: n-gram hashes over the line hashes of every file (window of up to n lines starting at every line). */
+void orc_ngram_hashes(const uint64_t* line_hash, const int64_t* line_base, int32_t n_files, int32_t n, uint64_t* out);
+
 /* SPEC section 6: category id of statement T; ident_off/ident_len locate L inside T. */
 int orc_classify(const uint8_t* t, uint32_t len, uint32_t* ident_off, uint32_t* ident_len);
 const char* orc_category_name(int id);

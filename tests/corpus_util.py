@@ -171,3 +171,13 @@ def edge_corpus():
     exts = np.array([e for _, e in EDGE_FILES], np.uint8)
     grps = np.array([i % 3 for i in range(len(files))], np.uint16)
     return files, exts, grps
+
+
+def load_fixture(path):
+    """Files of a tests/golden/*.npz corpus fixture (tools/make_golden.py: c1_fixture, c1_hazards)."""
+    d = np.load(path)
+    blob, size = d["blob"], d["size"].astype(np.int64)
+    ends = np.cumsum(size)
+    files = [blob[e - s:e].tobytes() for s, e in zip(size, ends)]
+    grps = d["grp"].astype(np.uint16)
+    return files, d["ext"].astype(np.uint8), grps, int(grps.max()) + 1 if len(grps) else 1

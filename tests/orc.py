@@ -69,6 +69,8 @@ def lib():
         L.orc_statements.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_reduce.restype = C.c_int
         L.orc_reduce.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+        L.orc_ngram_hashes.restype = None
+        L.orc_ngram_hashes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_mt_affinity_cpus.restype = C.c_int
         L.orc_mt_create.restype = C.c_int
         L.orc_mt_create.argtypes = [C.c_int, C.c_int32]
@@ -169,6 +171,42 @@ def scan(arena, off, length, ext, grp, n_groups=1, events=True, line_hashes=Fals
             out["line_hash"] = lh[:nl]
             out["line_base"] = lb
     return out
+
+
+def ngram_hashes(line_hash, line_base, n):
+    line_hash = np.ascontiguousarray(line_hash, np.uint64)
+    line_base = np.ascontiguousarray(line_base, np.int64)
+    out = np.zeros(max(len(line_hash), 1), np.uint64)
+    lib().orc_ngram_hashes(_p(line_hash), _p(line_base), len(line_base) - 1, int(n), _p(out))
+    return out[:len(line_hash)]
+
+
+def line_records(arena, off, length, ext):
+    """(line_base, line_hash, line_end, line_flag) of every line, files in order: the oracle's side of tsm_line_hashes."""
+    n = len(length)
+    res = scan(arena, off, length, ext, np.zeros(n, np.uint16), 1, events=True, line_hashes=True)
+    base, lh = res["line_base"], res["line_hash"]
+    end = np.zeros(len(lh), np.uint32)
+    flag = np.zeros(len(lh), np.uint8)
+    starts = np.zeros(len(lh), np.int64)
+    for f in range(n):
+        b = arena[int(off[f]):int(off[f]) + int(length[f])]
+        nl = np.nonzero(b == 10)[0]
+        k = int(base[f + 1] - base[f])
+        e = np.full(k, int(length[f]), np.int64)
+        e[:len(nl)] = nl[:k] if len(nl) >= k else nl
+        end[int(base[f]):int(base[f + 1])] = e
+        st = np.zeros(k, np.int64)
+        st[1:] = e[:-1] + 1
+        starts[int(base[f]):int(base[f + 1])] = st
+    ev = res["assert_events"]
+    if len(ev):
+        key = {(int(f), int(o)) for f, o in zip(ev["file"], ev["line_off"])}
+        for f in range(n):
+            for i in range(int(base[f]), int(base[f + 1])):
+                if (f, int(starts[i])) in key:
+                    flag[i] = 1
+    return base, lh, end, flag
 
 
 class MtScanner:

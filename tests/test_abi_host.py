@@ -35,8 +35,8 @@ def test_struct_layouts():
 
 
 def test_no_cpu_fallback():
-    import torch
-    if torch.cuda.is_available():
+    from conftest import _have_gpu
+    if _have_gpu():
         pytest.skip("GPU present")
     with pytest.raises(ts.TsmError) as e:
         ts.Scanner(device=0)

@@ -286,3 +286,26 @@ def test_statement_kinds(scanner):
         assert np.array_equal(gb, ob) and np.array_equal(ge, oe)
         bad = np.nonzero(gk != ok)[0]
         assert bad.size == 0, (bad[:10], gk[bad[:10]], ok[bad[:10]])
+
+
+def check_line_records(scanner, c, ngram=3):
+    gb, gh, ge, gf, gn = scanner.line_hashes(c, ngram=ngram)
+    ob, oh, oe, of_ = orc.line_records(c.arena, c.off, c.len, c.ext)
+    assert np.array_equal(gb, ob), (gb[:5], ob[:5])
+    for name, a, b in (("hash", gh, oh), ("end", ge, oe), ("flag", gf, of_), ("ngram", gn, orc.ngram_hashes(oh, ob, ngram))):
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, (name, bad[:8], a[bad[:4]], b[bad[:4]])
+
+
+def test_line_records_and_ngrams(scanner):
+    """S9 (SPEC section 3): line_hash / line_end / line_flag of every line in file order and the n-gram hashes over
+    them, from the scan kernel's one pass, against the oracle: edge files, fuzz (long lines, many chunks), C4 shape."""
+    files, exts, _ = cu.edge_corpus()
+    check_line_records(scanner, ts.pack(files, exts))
+    check_line_records(scanner, ts.pack(files, exts), ngram=1)
+    files, exts, _ = cu.fuzz_corpus(41, 200, 30000, long_lines=True)
+    check_line_records(scanner, ts.pack(files, exts), ngram=5)
+    check_line_records(scanner, ts.pack([b"\n" * 9000 + b"assert x\n" * 50, b"", b"a" * 9000, b"x\n" * 5000 + b"tail"], [1, 1, 2, 3]))
+    check_line_records(scanner, ts.gen_corpus(0x7053454D0004, 300, 1, pinned=False), ngram=2)
+    gb, gh, ge, gf = scanner.line_hashes(ts.pack([], []))
+    assert gb.tolist() == [0] and len(gh) == 0

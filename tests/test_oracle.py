@@ -305,3 +305,21 @@ def test_mt_harness_equals_single_thread_scan():
     mt = orc.MtScanner(0)
     assert mt.threads == orc.lib().orc_mt_affinity_cpus()
     mt.close()
+
+
+def test_c1_fixture_reproduces_the_committed_summary():
+    """The committed C1 test files (tests/golden/c1_testfiles.npz) give the committed summary: runs on every box,
+    with or without /root/reference."""
+    files, exts, grps, n_groups = cu.load_fixture(os.path.join(GOLD, "c1_testfiles.npz"))
+    want = json.load(open(os.path.join(GOLD, "c1_summary.json")))
+    arena, off, ln = orc.pack(files)
+    res = orc.scan(arena, off, ln, exts, grps, n_groups, events=False)
+    st = res["stats"]
+    assert len(files) == want["n_files"] and int(ln.astype(np.int64).sum()) == want["bytes"]
+    assert [int(st[k].astype(np.int64).sum()) for k in ("n_lines", "n_assert", "n_headers", "n_fixture")] == \
+        [want["n_lines"], want["n_assert"], want["n_headers"], want["n_fixture"]]
+    assert "%016x" % int(np.bitwise_xor.reduce(st["digest"])) == want["digest_xor"]
+    hz = json.load(open(os.path.join(GOLD, "ledger.json")))["C1"]
+    assert hz["fixture"]["files"] == 1779 and hz["hazard_fixture"]["non_utf8"] == 1 and hz["hazard_fixture"]["crlf_files"] == 5
+    hfiles, _, _, _ = cu.load_fixture(os.path.join(GOLD, "c1_hazard_files.npz"))
+    assert max(len(f) for f in hfiles) == 2501857 and sum(1 for f in hfiles if f and not f.endswith(b"\n")) == 115

@@ -14,6 +14,7 @@
 #include "tsm_reduce_kernels.cuh"
 #include "tsm_diff_kernels.cuh"
 #include "tsm_stmt_kernels.cuh"
+#include "tsm_lines_kernels.cuh"
 
 using namespace tsm;
 
@@ -394,6 +395,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
 
 extern "C" int tsm_scan_resident(tsm_ctx* c, uint32_t flags, void* stream) {
   if (!c) return TSM_E_ARG;
+  flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS;
   if (!c->resident) return TSM_E_STATE;
   CU(cudaSetDevice(c->device));
   return launch_scan(c, flags, (cudaStream_t)stream, nullptr);
@@ -470,6 +472,7 @@ extern "C" int tsm_scan(tsm_ctx* c, const tsm_corpus* k, tsm_result* r, uint32_t
   if (!c || !r) return TSM_E_ARG;
   int rc = check_corpus(c, k);
   if (rc != TSM_OK) return rc;
+  flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS;
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t n = k->n_files;
@@ -553,48 +556,109 @@ struct DevBuf {                                           // device scratch from
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
-struct HostSide {                                         // device image of one side of the pairs
-  DevBuf arena, off, len, n_lines, line_base, line_end, line_hash, ext, line_flag;
+struct HostSide {                                         // device image of one side of the pairs + its line records
+  DevBuf arena, off, len, ext, line_base, line_end, line_hash, line_flag;
+  DevBuf unit_file, unit_begin, cnt, unit_first, bsum, zero, stats, unit_lines, unit_out, unit_line_base, s_hash, s_end, s_flag;
   std::vector<unsigned long long> base;                   // host copy of line_base
   DiffSide d{};
+  int launches = 0;
 };
 
-int side_lines(const tsm_corpus* k, HostSide& h, cudaStream_t st, bool want_flags) {
+// Exclusive scan of n u32 counts into n + 1 u64 (tsm_lines_kernels.cuh); bsum holds n / 1024 + 2 u64.
+static void xscan(const uint32_t* in, uint32_t n, unsigned long long* bsum, unsigned long long* out, cudaStream_t st) {
+  const uint32_t nb = (n + XS_TILE - 1) / XS_TILE;
+  if (nb == 0) { cudaMemsetAsync(out, 0, sizeof(unsigned long long), st); return; }
+  k_xscan_sums<<<nb, 256, 0, st>>>(in, n, bsum);
+  k_xscan_top<<<1, 256, 0, st>>>(bsum, nb);
+  k_xscan_apply<<<nb, 256, 0, st>>>(in, n, bsum, out);
+}
+
+// One side's line records in file order (docs/SPEC.md sections 2-4): line_base[n+1], and per line its hash, its
+// end and whether it is an assertion line.  One pass of k_scan2 over the source (TSM_SCAN_LINE_HASHES: every
+// chunk writes the records of its own lines into a region of the staging arrays), one exclusive scan of the
+// lines per unit, one gather.  The staging arrays are sized for 8-byte lines; a corpus with more lines than
+// that is scanned a second time with the exact size (the first pass counted them).
+int side_lines(tsm_ctx* c, const tsm_corpus* k, HostSide& h, cudaStream_t st) {
   const int32_t n = k->n_files;
   const size_t ab = (size_t)k->off[n];
+  const uint32_t unit_cap = (uint32_t)(ab / CH + (size_t)n + 1);
+  const size_t zero_bytes = 256 + sizeof(SlabCtl);
   if (!h.arena.alloc(ab + 4096) || !h.off.alloc(sizeof(int32_t) * ((size_t)n + 1)) || !h.len.alloc(sizeof(int32_t) * (size_t)n) ||
-      !h.n_lines.alloc(sizeof(uint32_t) * (size_t)n) || !h.line_base.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
+      !h.ext.alloc((size_t)n) || !h.unit_file.alloc(sizeof(uint32_t) * unit_cap) || !h.unit_begin.alloc(sizeof(uint32_t) * unit_cap) ||
+      !h.cnt.alloc(sizeof(uint32_t) * (size_t)n) || !h.unit_first.alloc(sizeof(unsigned long long) * ((size_t)n + 1)) ||
+      !h.bsum.alloc(sizeof(unsigned long long) * (unit_cap / XS_TILE + 4)) || !h.zero.alloc(zero_bytes) ||
+      !h.stats.alloc(sizeof(tsm_file_stat) * (size_t)n) || !h.unit_lines.alloc(sizeof(uint32_t) * unit_cap) ||
+      !h.unit_out.alloc(sizeof(uint32_t) * unit_cap) || !h.unit_line_base.alloc(sizeof(unsigned long long) * ((size_t)unit_cap + 1)) ||
+      !h.line_base.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
     return TSM_E_CUDA;
   CU(cudaMemsetAsync(h.arena.as<uint8_t>() + ab, 0, 4096, st));
   CU(cudaMemcpyAsync(h.arena.p, k->arena, ab, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h.off.p, k->off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h.len.p, k->len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-  h.d.arena = h.arena.as<uint8_t>(); h.d.off = h.off.as<int32_t>(); h.d.len = h.len.as<int32_t>();
-  h.d.n_lines = h.n_lines.as<uint32_t>();
-  k_count_lines<<<(n * 32 + 255) / 256, 256, 0, st>>>(h.d, n);
-  std::vector<uint32_t> nl((size_t)n);
-  CU(cudaMemcpyAsync(nl.data(), h.n_lines.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (k->ext) CU(cudaMemcpyAsync(h.ext.p, k->ext, (size_t)n, cudaMemcpyHostToDevice, st));
+  else CU(cudaMemsetAsync(h.ext.p, 0, (size_t)n, st));
+  ScanParams p{};
+  p.arena = h.arena.as<uint8_t>(); p.off = h.off.as<int32_t>(); p.len = h.len.as<int32_t>(); p.ext = h.ext.as<uint8_t>();
+  p.grp = nullptr; p.n_files = n; p.n_groups = 1;
+  p.unit_file = h.unit_file.as<uint32_t>(); p.unit_begin = h.unit_begin.as<uint32_t>(); p.unit_cap = unit_cap;
+  p.ctrl = reinterpret_cast<Ctrl*>(h.zero.as<uint8_t>()); p.slab = reinterpret_cast<SlabCtl*>(h.zero.as<uint8_t>() + 256);
+  p.f_begin = 0; p.f_end = n; p.unit_base = 0;
+  p.stats = h.stats.as<tsm_file_stat>();
+  p.cand = nullptr; p.cand_cap = 0; p.hev = nullptr; p.hev_cap = 0; p.aev = nullptr; p.aev_cap = 0; p.counts = nullptr;
+  p.flags = TSM_SCAN_LINE_HASHES; p.four = 4;
+  p.unit_lines = h.unit_lines.as<uint32_t>(); p.unit_out = h.unit_out.as<uint32_t>();
+  // units in (file, chunk) order
+  k_file_units<<<(n + 255) / 256, 256, 0, st>>>(p.len, (uint32_t)n, h.cnt.as<uint32_t>());
+  xscan(h.cnt.as<uint32_t>(), (uint32_t)n, h.bsum.as<unsigned long long>(), h.unit_first.as<unsigned long long>(), st);
+  size_t cap = ab / 8 + 2 * (size_t)unit_cap + 64;
+  Ctrl hc{};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (cap > 0xFFFFFFF0ull) return TSM_E_CAPACITY;
+    if (!h.s_hash.alloc(sizeof(unsigned long long) * cap) || !h.s_end.alloc(sizeof(uint32_t) * cap) || !h.s_flag.alloc(cap)) return TSM_E_CUDA;
+    p.lh_hash = h.s_hash.as<unsigned long long>(); p.lh_end = h.s_end.as<uint32_t>(); p.lh_flag = h.s_flag.as<uint8_t>();
+    p.lh_cap = (uint32_t)cap;
+    CU(cudaMemsetAsync(h.zero.p, 0, zero_bytes, st));
+    k_plan_det<<<(n + 1 + 255) / 256, 256, 0, st>>>(p, h.unit_first.as<unsigned long long>());
+    k_scan2<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hc, p.ctrl, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    h.launches += 6;
+    if (hc.overflow) return TSM_E_CAPACITY;
+    if (!hc.lh_overflow) break;
+    if (attempt == 1) return TSM_E_CAPACITY;
+    cap = (size_t)hc.n_lh + 64;                            // the first pass counted every region
+  }
+  SlabCtl hs{};
+  CU(cudaMemcpyAsync(&hs, p.slab, sizeof hs, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  h.base.assign((size_t)n + 1, 0);
-  for (int32_t i = 0; i < n; ++i) h.base[(size_t)i + 1] = h.base[(size_t)i] + nl[(size_t)i];
-  const unsigned long long total = h.base[(size_t)n];
-  if (!h.line_end.alloc(sizeof(uint32_t) * (size_t)total) || !h.line_hash.alloc(sizeof(unsigned long long) * (size_t)total))
+  const uint32_t n_units = hs.n_units;
+  xscan(p.unit_lines, n_units, h.bsum.as<unsigned long long>(), h.unit_line_base.as<unsigned long long>(), st);
+  unsigned long long total = 0;
+  CU(cudaMemcpyAsync(&total, h.unit_line_base.as<unsigned long long>() + n_units, sizeof total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (!h.line_end.alloc(sizeof(uint32_t) * (size_t)total) || !h.line_hash.alloc(sizeof(unsigned long long) * (size_t)total) ||
+      !h.line_flag.alloc((size_t)total))
     return TSM_E_CUDA;
-  CU(cudaMemcpyAsync(h.line_base.p, h.base.data(), sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  if (n_units)
+    k_gather_lines<<<(n_units * 32 + 255) / 256, 256, 0, st>>>(p.unit_lines, p.unit_out, h.unit_line_base.as<unsigned long long>(), n_units,
+                                                                 p.lh_hash, p.lh_end, p.lh_flag, h.line_hash.as<unsigned long long>(),
+                                                                 h.line_end.as<uint32_t>(), h.line_flag.as<uint8_t>());
+  k_line_base<<<(n + 1 + 255) / 256, 256, 0, st>>>(h.unit_first.as<unsigned long long>(), h.unit_line_base.as<unsigned long long>(),
+                                                     (uint32_t)n, h.line_base.as<unsigned long long>());
+  CU(cudaGetLastError());
+  h.base.assign((size_t)n + 1, 0);
+  CU(cudaMemcpyAsync(h.base.data(), h.line_base.p, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  h.launches += 5;
+  h.s_hash.reset(); h.s_end.reset(); h.s_flag.reset();    // staging is done with
+  h.d.arena = h.arena.as<uint8_t>(); h.d.off = h.off.as<int32_t>(); h.d.len = h.len.as<int32_t>();
+  h.d.n_lines = nullptr;
   h.d.line_base = h.line_base.as<unsigned long long>();
   h.d.line_end = h.line_end.as<uint32_t>();
   h.d.line_hash = h.line_hash.as<unsigned long long>();
-  h.d.ext = nullptr; h.d.line_flag = nullptr;
-  if (want_flags) {
-    if (!h.line_flag.alloc((size_t)total) || !h.ext.alloc((size_t)n)) return TSM_E_CUDA;
-    if (k->ext) CU(cudaMemcpyAsync(h.ext.p, k->ext, (size_t)n, cudaMemcpyHostToDevice, st));
-    else CU(cudaMemsetAsync(h.ext.p, 0, (size_t)n, st));
-    h.d.ext = h.ext.as<uint8_t>();
-    h.d.line_flag = h.line_flag.as<uint8_t>();
-  }
-  k_mark_lines<<<(n * 32 + 255) / 256, 256, 0, st>>>(h.d, n);
-  if (total) k_hash_lines<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h.d, n, total);
-  CU(cudaGetLastError());
+  h.d.ext = h.ext.as<uint8_t>();
+  h.d.line_flag = h.line_flag.as<uint8_t>();
   return TSM_OK;
 }
 }  // namespace
@@ -615,8 +679,8 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
   PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   HostSide A, B;
-  int rc = side_lines(olds, A, st, detail != nullptr);
-  if (rc == TSM_OK) rc = side_lines(news, B, st, detail != nullptr);
+  int rc = side_lines(c, olds, A, st);
+  if (rc == TSM_OK) rc = side_lines(c, news, B, st);
   if (rc != TSM_OK) return rc;
   std::vector<unsigned long long> vbase((size_t)n + 1, 0);
   for (int32_t i = 0; i < n; ++i)
@@ -634,7 +698,7 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
   CU(cudaMemcpyAsync(added, d_add.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(removed, d_rem.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  c->launches = 7;
+  c->launches = A.launches + B.launches + 1;
   if (!detail) return TSM_OK;
   // ---- hunks: second search with the rows of V kept; rows sized from the distances just computed,
   //      pairs processed in batches of at most 2^28 trace ints (1 GiB)
@@ -678,6 +742,49 @@ extern "C" int tsm_diff_pairs(tsm_ctx* c, const tsm_corpus* olds, const tsm_corp
   return tsm_diff_pairs_detail(c, olds, news, added, removed, nullptr, stream);
 }
 
+// ------------------------------------------------------------------------------------- S9 line / n-gram hashes
+extern "C" int tsm_line_hashes(tsm_ctx* c, const tsm_corpus* k, int64_t* line_base, uint64_t* line_hash, uint32_t* line_end,
+                               uint8_t* line_flag, int64_t cap, int64_t* n_lines, int32_t ngram_n, uint64_t* ngram_hash,
+                               void* stream) {
+  if (!c || !k || !line_base || !n_lines || cap < 0 || k->n_files < 0 || ngram_n < 0 || (ngram_hash && ngram_n < 1)) return TSM_E_ARG;
+  const int32_t n = k->n_files;
+  *n_lines = 0;
+  line_base[0] = 0;
+  if (n == 0) return TSM_OK;
+  if (!k->arena || !k->off || !k->len) return TSM_E_ARG;
+  for (int32_t i = 0; i < n; ++i)
+    if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1] ||
+        (k->ext && k->ext[i] > TSM_EXT_H))
+      return TSM_E_LAYOUT;
+  CU(cudaSetDevice(c->device));
+  PoolScope pool_scope(&c->pool);
+  cudaStream_t st = (cudaStream_t)stream;
+  HostSide S;
+  int rc = side_lines(c, k, S, st);
+  if (rc != TSM_OK) return rc;
+  const unsigned long long total = S.base[(size_t)n];
+  for (int32_t i = 0; i <= n; ++i) line_base[i] = (int64_t)S.base[(size_t)i];
+  *n_lines = (int64_t)total;
+  c->launches = S.launches;
+  if ((unsigned long long)cap < total) return TSM_E_CAPACITY;   // line_base / n_lines are filled: allocate and call again
+  if (total == 0) return TSM_OK;
+  if (line_hash) CU(cudaMemcpyAsync(line_hash, S.d.line_hash, sizeof(uint64_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  if (line_end) CU(cudaMemcpyAsync(line_end, S.d.line_end, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  if (line_flag) CU(cudaMemcpyAsync(line_flag, S.d.line_flag, (size_t)total, cudaMemcpyDeviceToHost, st));
+  if (ngram_hash) {
+    DevBuf d_ng;
+    if (!d_ng.alloc(sizeof(unsigned long long) * (size_t)total)) { cudaStreamSynchronize(st); return TSM_E_CUDA; }
+    k_ngrams<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S.d.line_hash, S.d.line_base, (uint32_t)n, total, (uint32_t)ngram_n,
+                                                               d_ng.as<unsigned long long>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ngram_hash, d_ng.p, sizeof(uint64_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->launches++;
+  }
+  CU(cudaStreamSynchronize(st));
+  return TSM_OK;
+}
+
 // ------------------------------------------------------------------------------------- SPEC section 10 statements
 extern "C" int tsm_statements(tsm_ctx* c, const tsm_corpus* k, int64_t* line_base, uint32_t* line_end,
                               uint8_t* line_kind, int64_t cap, int64_t* n_lines, void* stream) {
@@ -694,7 +801,7 @@ extern "C" int tsm_statements(tsm_ctx* c, const tsm_corpus* k, int64_t* line_bas
   PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   HostSide S;
-  int rc = side_lines(k, S, st, false);                   // newline count, ordered line ends (and hashes)
+  int rc = side_lines(c, k, S, st);                       // line records from one pass of the scan
   if (rc != TSM_OK) return rc;
   const unsigned long long total = S.base[(size_t)n];
   for (int32_t i = 0; i <= n; ++i) line_base[i] = (int64_t)S.base[(size_t)i];
@@ -710,6 +817,6 @@ extern "C" int tsm_statements(tsm_ctx* c, const tsm_corpus* k, int64_t* line_bas
   CU(cudaMemcpyAsync(line_end, S.d.line_end, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(line_kind, d_kind.p, (size_t)total, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  c->launches = 5;
+  c->launches = S.launches + 2;
   return TSM_OK;
 }

@@ -84,6 +84,8 @@ struct Ctrl {                     // device control block, zeroed before every s
   uint32_t n_hev;
   uint32_t n_aev;
   uint32_t overflow;              // some list hit its capacity
+  uint32_t n_lh;                  // line-record slots reserved by k_scan2 (TSM_SCAN_LINE_HASHES)
+  uint32_t lh_overflow;           // ... and whether the staging arrays were too small for them
 };
 
 struct SlabCtl { uint32_t n_units, work; };   // per-slab unit count (k_plan) and work cursor (k_scan)
@@ -112,6 +114,14 @@ struct ScanParams {
   uint32_t aev_cap;
   unsigned long long* counts;     // [n_groups + 1][K]
   uint32_t flags;
+  // per-line output (TSM_SCAN_LINE_HASHES; docs/SPEC.md section 3, S9): every chunk reserves one region of the staging
+  // arrays and writes the records of its own lines in order; unit_out / unit_lines say where and how many
+  unsigned long long* lh_hash;    // line_hash
+  uint32_t* lh_end;               // file-relative end of the line (position of its LF, or the file size)
+  uint8_t* lh_flag;               // 1 = assertion line (SPEC section 4)
+  uint32_t lh_cap;
+  uint32_t* unit_lines;           // [unit slots]
+  uint32_t* unit_out;             // [unit slots]
   uint32_t four;                  // 4 (a multiplier the compiler must not see: tsm_scan2_kernels.cuh, lut_at)
 };
 

@@ -235,6 +235,7 @@ __device__ __forceinline__ uint32_t line_flags2(uint32_t s, uint32_t e, uint32_t
 struct FinishState {                                     // carried from one window of line records to the next
   uint32_t prev_last;                                    // newline in front of the next line
   unsigned long long prevP;                              // hash prefix of the bytes [0, prev_last]
+  uint32_t lh_base, lh_done;                             // TSM_SCAN_LINE_HASHES: the chunk's region of the staging arrays, records written
 };
 
 // Finish pass over the n line records of the window: one lane per line, no inner loops.  The hash of a line is
@@ -249,9 +250,9 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
   const unsigned long long* t0a = reinterpret_cast<const unsigned long long*>(scan_lut()) + O2_T0A / 8;
   const uint32_t g1 = lc[1], g2 = lc[2];
   const SmemByte lb{wb};
-  const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0;
+  const bool want_hev = (p.flags & TSM_SCAN_HEADER_EVENTS) != 0, want_lh = (p.flags & TSM_SCAN_LINE_HASHES) != 0;
   Accum a = ac;
-  uint32_t nc = 0;
+  uint32_t nc = 0, lh_done = fs.lh_done;
   uint32_t prev_last = fs.prev_last;
   unsigned long long prevP = fs.prevP;
   for (uint32_t base = 0; base < n; base += 32) {        // uniform trip count
@@ -285,6 +286,7 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
     prevP = __shfl_sync(0xffffffffu, Pn, src);
     const bool owned = valid && s < lim && !(s == PRE && skip_first);
     uint32_t fl = 0;
+    unsigned long long lh = 0;
     if (owned) {
       const unsigned long long hr = canon61(Pe + 4ull * M61 - Ps);       // bytes [s, e), weighted from position 0
       const uint32_t sh = (8u * s) % 61u;
@@ -296,7 +298,8 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
         h = h >= cr ? h - cr : h + M61 - cr;
       }
       a.lines++;
-      a.digest += mix_hash(h, len);
+      lh = mix_hash(h, len);
+      a.digest += lh;
       uint32_t A = 0;
       if (rec & LR_FIRST) A = arun[isv ? SLOT_TAIL : g];
       else if (rec & LR_MIXED) {                         // a line inside a mixed word: its own states
@@ -307,13 +310,23 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
       fl = line_flags2(s, e, A, g1, g2, ext, lb, a);
       if (want_hev && (fl & LF_HDR)) emit_header(p, f, cb + s - PRE, e - s, fl);
     }
+    if (want_lh) {                                       // the line's record, in line order inside the chunk's region
+      const uint32_t mo = __ballot_sync(0xffffffffu, owned);
+      const uint32_t slot = fs.lh_base + lh_done + __popc(mo & ((1u << lane) - 1u));
+      if (owned && slot < p.lh_cap) {
+        p.lh_hash[slot] = lh;
+        p.lh_end[slot] = cb + e - PRE;
+        p.lh_flag[slot] = (uint8_t)(fl & LF_CAND);
+      }
+      lh_done += __popc(mo);
+    }
     __syncwarp();                                        // every record of the round is read: the list may grow over them
     const uint32_t mc = __ballot_sync(0xffffffffu, fl & LF_CAND);
     if (fl & LF_CAND) ltab[nc + __popc(mc & ((1u << lane) - 1u))] = (uint16_t)s;
     nc += __popc(mc);
   }
   __syncwarp();
-  if (nc) {                                              // candidates of the window to their global list
+  if (nc && p.cand_cap) {                                // candidates of the window to their global list
     const uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
     for (uint32_t i = (uint32_t)lane; i < nc; i += 32) {
       const uint32_t slot = cbase + i;
@@ -325,9 +338,10 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
   ac = a;
   fs.prev_last = prev_last;
   fs.prevP = prevP;
+  fs.lh_done = lh_done;
 }
 
-__device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t f,
+__device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t uslot, uint32_t f,
                                                uint32_t cb, uint32_t fo, uint32_t size, int ext, int lane) {
   const uint32_t ce = min(cb + CH, size);
   const uint32_t le = min(ce + EXT, size);
@@ -408,7 +422,21 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   // ---- newline words -> one record per line (dense: one lane per newline word, SWAR for the newline bytes),
   //      finished window by window (one window unless the chunk has more than ~LCAP lines)
   uint16_t* ltab = reinterpret_cast<uint16_t*>(wb + O2_LTAB);
-  FinishState fs{PRE - 1u, 0ull};                        // (the 16 bytes in front of the chunk are zeros)
+  FinishState fs{PRE - 1u, 0ull, 0u, 0u};                // (the 16 bytes in front of the chunk are zeros)
+  const bool want_lh = (p.flags & TSM_SCAN_LINE_HASHES) != 0;
+  if (want_lh) {                                         // one region for the chunk's line records: newlines of the kept words + 1
+    uint32_t tot = 0;
+    for (uint32_t j = (uint32_t)lane; j < n_went; j += 32)
+      tot += __popc(nl8_of(*reinterpret_cast<const unsigned long long*>(wb + 8u * ((uint32_t)went[j] & 0x3FFu))));
+    tot = __reduce_add_sync(0xffffffffu, tot) + 1u;
+    uint32_t base = 0;
+    if (lane == 0) {
+      base = atomicAdd(&p.ctrl->n_lh, tot);
+      if (base + tot > p.lh_cap) p.ctrl->lh_overflow = 1;
+      p.unit_out[uslot] = base;
+    }
+    fs.lh_base = __shfl_sync(0xffffffffu, base, 0);
+  }
   uint32_t n_rec = 0, last_nl = PRE - 1u;
   for (uint32_t base = 0; base < n_went; base += 32) {
     const uint32_t j = base + (uint32_t)lane;
@@ -450,7 +478,15 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   }
   __syncwarp();
   if (n_rec) finish_lines2(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
-  if (tail_long && lane == 0) long_line(p, scan_lut(), B_FIRST, f, fo, size, ext, cb + tail_start - PRE, ac);
+  if (tail_long && lane == 0) {
+    const unsigned long long d0 = ac.digest;
+    uint32_t fl = 0;
+    const uint32_t e = long_line(p, scan_lut(), B_FIRST, f, fo, size, ext, cb + tail_start - PRE, ac, &fl);
+    if (want_lh) {                                       // the chunk's last line
+      const uint32_t slot = fs.lh_base + fs.lh_done;
+      if (slot < p.lh_cap) { p.lh_hash[slot] = ac.digest - d0; p.lh_end[slot] = e; p.lh_flag[slot] = (uint8_t)(fl & LF_CAND); }
+    }
+  }
   // ---- per-file counters: warp reduce (the digest as three partial sums: low halves keep their carries),
   //      then one store (single-chunk file) or one atomic per counter
   ac.lines = __reduce_add_sync(0xffffffffu, ac.lines);
@@ -464,6 +500,7 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
     const unsigned long long s2 = __reduce_add_sync(0xffffffffu, dhi);
     ac.digest = s0 + (s1 << 16) + (s2 << 32);
   }
+  if (want_lh && lane == 0) p.unit_lines[uslot] = ac.lines;
   if (lane == 0) {
     tsm_file_stat* st = p.stats + f;
     if (size <= CH) {                                    // sole owner of the record: plain store
@@ -516,7 +553,7 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan2(S
     while (!mbar_try_wait(bar, phase)) {}
     phase ^= 1;
     const uint32_t lang = cur.ext == 0 ? 2u : (cur.ext == TSM_EXT_PY ? 0u : 1u);
-    process_chunk2(p, lut_all + 256u + 4u * lang, wb, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
+    process_chunk2(p, lut_all + 256u + 4u * lang, wb, p.unit_base + cur.u, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
     __syncwarp();
     cur = nxt;
   }

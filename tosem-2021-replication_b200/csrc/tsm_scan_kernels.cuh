@@ -467,8 +467,8 @@ __device__ __forceinline__ void drain(const ScanParams& p, uint8_t* wb, const ui
 
 // Slow path: a line that starts in this chunk but ends behind the staged bytes.  Walked by lane 0
 // straight from HBM (correct for any length; lines longer than 240 B past a chunk edge are rare).
-__device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut, uint32_t first, uint32_t f,
-                                       uint32_t fo, uint32_t size, int ext, uint32_t s, Accum& ac) {
+__device__ __noinline__ uint32_t long_line(const ScanParams& p, const uint32_t* lut, uint32_t first, uint32_t f,
+                                           uint32_t fo, uint32_t size, int ext, uint32_t s, Accum& ac, uint32_t* fl_out = nullptr) {
   const uint8_t* g = p.arena + fo;
   const GmemByte lb{g};
   uint32_t e = s;
@@ -480,7 +480,7 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
     line_block(L, w, lut, first);
   }
   const uint32_t fl = line_finish(s, e, L.A, L.B, ext, lb, ac);
-  if (fl & LF_CAND) {
+  if ((fl & LF_CAND) && p.cand_cap) {
     const uint32_t slot = atomicAdd(&p.ctrl->n_cand, 1u);
     if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | s;
     else p.ctrl->overflow = 1;
@@ -490,6 +490,8 @@ __device__ __noinline__ void long_line(const ScanParams& p, const uint32_t* lut,
     if (slot < p.hev_cap) p.hev[slot] = tsm_header_event{f, s, e - s, (fl >> 2) & 1u};
     else p.ctrl->overflow = 1;
   }
+  if (fl_out) *fl_out = fl;
+  return e;                                              // file-relative end of the line
 }
 
 __device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t f,

@@ -31,7 +31,7 @@ DIFF_DETAIL = np.dtype([("hunks_add", "<i8"), ("hunks_del", "<i8"), ("hunks_mod"
 # every symbol include/tosemscan.h declares (tests check the library exports exactly these)
 SYMBOLS = ["tsm_abi_version", "tsm_strerror", "tsm_category_name", "tsm_create", "tsm_destroy", "tsm_scan",
            "tsm_upload", "tsm_scan_resident", "tsm_download", "tsm_device_counts", "tsm_last_launch_count", "tsm_last_kernel_ms", "tsm_kernel_ms_stats",
-           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_statements", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
+           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_statements", "tsm_line_hashes", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
            "tsm_gen_fill", "tsm_gen_edit", "tsm_gen_pair_sizes", "tsm_gen_pair_fill"]
 
 
@@ -97,6 +97,9 @@ def lib():
         L.tsm_statements.restype = C.c_int
         L.tsm_statements.argtypes = [C.c_void_p, C.POINTER(_Corpus), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.POINTER(C.c_int64), C.c_void_p]
+        L.tsm_line_hashes.restype = C.c_int
+        L.tsm_line_hashes.argtypes = [C.c_void_p, C.POINTER(_Corpus)] + [C.c_void_p] * 4 + [C.c_int64, C.POINTER(C.c_int64), C.c_int32,
+                                      C.c_void_p, C.c_void_p]
         L.tsm_reduce.restype = C.c_int
         L.tsm_reduce.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3
         L.tsm_host_alloc.restype = C.c_void_p
@@ -343,6 +346,7 @@ class Scanner:
         rc = lib().tsm_scan(self._ctx, C.byref(cs), C.byref(r), flags, stream)
         if rc:
             raise TsmError(rc, "tsm_scan")
+        self._corpus = corpus                               # tsm_scan leaves this corpus resident: download() reads its results
         return self._finish(res, r, flags)
 
     def upload(self, corpus, stream=None):
@@ -392,6 +396,25 @@ class Scanner:
         if rc:
             raise TsmError(rc, "tsm_kernel_ms_stats")
         return [float(x) for x in sums], int(n.value)
+
+    def line_hashes(self, corpus, ngram=0, stream=None):
+        """S9: (line_base[n+1], line_hash, line_end, line_flag[, ngram_hash]) of every line, files in order."""
+        cs = corpus.c_struct()
+        base = np.zeros(corpus.n_files + 1, np.int64)
+        n = C.c_int64()
+        rc = lib().tsm_line_hashes(self._ctx, C.byref(cs), _p(base), None, None, None, 0, C.byref(n), 0, None, stream)
+        if rc not in (0, -3):
+            raise TsmError(rc, "tsm_line_hashes")
+        t = max(int(n.value), 1)
+        lh, le, lf = np.zeros(t, np.uint64), np.zeros(t, np.uint32), np.zeros(t, np.uint8)
+        ng = np.zeros(t, np.uint64) if ngram else None
+        if n.value:
+            rc = lib().tsm_line_hashes(self._ctx, C.byref(cs), _p(base), _p(lh), _p(le), _p(lf), t, C.byref(n), int(ngram), _p(ng), stream)
+            if rc:
+                raise TsmError(rc, "tsm_line_hashes")
+        m = int(n.value)
+        out = (base, lh[:m], le[:m], lf[:m])
+        return out + (ng[:m],) if ngram else out
 
     def reduce(self, flags, repo, case_id, n_repos, n_cases, stream=None):
         flags = np.ascontiguousarray(flags, np.uint8)
