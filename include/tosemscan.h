@@ -129,6 +129,18 @@ typedef struct tsm_diff_detail { int64_t hunks_add, hunks_del, hunks_mod, added_
 int tsm_diff_pairs_detail(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news,
                           int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream);
 
+/* A pair whose edit distance D is larger than 23 168 lines needs more than 2^28 trace entries ((D+1)(D+2)/2 ints, 1 GiB)
+ * for its backtrack: tsm_diff_pairs_detail does not trace it - added / removed are exact, the detail reports ONE hunk
+ * (add, del or mod by the counts) and added_assert = removed_assert = -1.  Every other pair of the call is unaffected.
+ *
+ * Resident variant (bench.py's `value` for config C5): tsm_diff_upload copies both sides to HBM once and keeps them in
+ * the ctx; every tsm_diff_resident call runs the kernels over them (k_scan over both sides for the line records,
+ * k_myers, k_myers_trace when detail != NULL) and copies the per-pair results back.  tsm_diff_last_ms: device time
+ * (CUDA events on the launching stream) of the last diff call: ms3 = { k_scan over both sides, k_myers, k_myers_trace }. */
+int tsm_diff_upload(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news, void* stream);
+int tsm_diff_resident(tsm_ctx* ctx, int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream);
+int tsm_diff_last_ms(tsm_ctx* ctx, float* ms3);
+
 /* S9 line / n-gram hashes (docs/SPEC.md section 3; SURVEY.md section 8a S9 - a design choice of the north star, attested by no
  * artefact of the package): the records of every line of every file, files in order, from ONE pass of the scan
  * kernel over the source.  line_base[n_files+1] and *n_lines are always filled; line_hash (SPEC section 3), line_end
@@ -175,12 +187,13 @@ int64_t tsm_gen_edit(uint64_t seed, const uint8_t* src, int32_t src_len, double 
                      uint8_t* dst, int64_t cap);
 
 /* BASELINE config C5: n (old, new) revision pairs; old ~ the size law 1 with the target clamped to cap bytes,
- * new = old with Poisson(lambda) line edits.  Slot i holds logical pair first_index + i*index_stride.
+ * new = old with Poisson(lambda) line edits.  Slot i holds logical pair index[i], or first_index + i*index_stride
+ * when index is NULL (ranks take size-balanced shares of one logical pair set through index lists).
  * tsm_gen_pair_sizes -> tsm_layout (twice) -> tsm_gen_pair_fill. */
-int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
-                       double lambda, int32_t* len_old, int32_t* len_new, uint8_t* ext);
-int tsm_gen_pair_fill(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
-                      double lambda, const uint8_t* ext, const int32_t* off_old, const int32_t* len_old,
+int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, const int32_t* index, int32_t first_index, int32_t index_stride,
+                       int32_t cap, double lambda, int32_t* len_old, int32_t* len_new, uint8_t* ext);
+int tsm_gen_pair_fill(uint64_t seed, int32_t n_pairs, const int32_t* index, int32_t first_index, int32_t index_stride,
+                      int32_t cap, double lambda, const uint8_t* ext, const int32_t* off_old, const int32_t* len_old,
                       uint8_t* arena_old, const int32_t* off_new, const int32_t* len_new, uint8_t* arena_new);
 
 #ifdef __cplusplus

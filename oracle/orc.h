@@ -92,6 +92,9 @@ int orc_mt_create(int n_threads, int32_t max_groups);
 void orc_mt_destroy(void);
 int orc_mt_scan(const uint8_t* arena, const int32_t* off, const int32_t* len, const uint8_t* ext, const uint16_t* grp,
                 int32_t n_files, int32_t n_groups, orc_file_stat* stats, int64_t* group_counts, int64_t* global_counts);
+int orc_mt_diff(const uint8_t* arena_old, const int32_t* off_old, const int32_t* len_old, const uint8_t* ext_old,
+                const uint8_t* arena_new, const int32_t* off_new, const int32_t* len_new, const uint8_t* ext_new,
+                int32_t n_pairs, int64_t* added, int64_t* removed, orc_diff_detail* detail);
 
 #ifdef __cplusplus
 }

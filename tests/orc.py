@@ -77,6 +77,8 @@ def lib():
         L.orc_mt_destroy.restype = None
         L.orc_mt_scan.restype = C.c_int
         L.orc_mt_scan.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 3
+        L.orc_mt_diff.restype = C.c_int
+        L.orc_mt_diff.argtypes = [C.c_void_p] * 8 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -228,6 +230,17 @@ class MtScanner:
         if rc != 0:
             raise ValueError("orc_mt_scan failed (%d)" % rc)
         return {"stats": stats, "group_counts": gc, "global_counts": glob}
+
+    def diff(self, a, b):
+        """(added, removed, detail) of the pairs (a[i], b[i]); a, b = (arena, off, len, ext)."""
+        n = len(a[2])
+        if getattr(self, "_dbufs", None) is None or self._dbufs[0].size != n:
+            self._dbufs = (np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(max(n, 1), DIFF_DETAIL))
+        add, rem, det = self._dbufs
+        rc = lib().orc_mt_diff(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]), n, _p(add), _p(rem), _p(det))
+        if rc != 0:
+            raise ValueError("orc_mt_diff failed (%d)" % rc)
+        return add, rem, det[:n]
 
     def close(self):
         lib().orc_mt_destroy()

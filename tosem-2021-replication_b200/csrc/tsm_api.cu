@@ -10,7 +10,7 @@
 #include "tsm_device.cuh"
 
 #include "tsm_scan_kernels.cuh"
-#include "tsm_scan2_kernels.cuh"
+#include "tsm_scan_walk.cuh"
 #include "tsm_reduce_kernels.cuh"
 #include "tsm_diff_kernels.cuh"
 #include "tsm_stmt_kernels.cuh"
@@ -50,12 +50,25 @@ struct PoolScope {
   ~PoolScope() { t_pool = nullptr; }
 };
 
+struct DevBuf {                                           // device scratch from the ctx's pool, returned on scope exit
+  void* p = nullptr;
+  ~DevBuf() { reset(); }
+  void reset() { if (p && t_pool) t_pool->give(p); p = nullptr; }
+  bool alloc(size_t bytes) { reset(); p = t_pool ? t_pool->take(bytes ? bytes : 16) : nullptr; return p != nullptr; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct SyncGuard {                                        // error paths: wait for the work queued on st before the DevBufs of the
+  cudaStream_t st;                                        // scope hand their slots back to the pool (the next call may reuse or free them)
+  explicit SyncGuard(cudaStream_t s) : st(s) {}
+  ~SyncGuard() { cudaStreamSynchronize(st); }
+};
+
 struct tsm_ctx {
   int device = 0;
   ScratchPool pool;
   int cls_grid = 0; size_t cls_smem = (size_t)-1;        // launch shape of k_classify for the current histogram size
   int sms = 0;
-  bool scan_v1 = false;
   int64_t max_arena = 0;
   int32_t max_files = 0, max_groups = 0;
   int64_t max_events = 0;
@@ -74,6 +87,9 @@ struct tsm_ctx {
   cudaStream_t copy_stream = nullptr;       // H2D of arena slabs, overlapped with the scan of earlier slabs
   cudaEvent_t slab_ev[64] = {};
   cudaEvent_t ready_ev = nullptr;
+  cudaEvent_t diff_ev[6] = {};             // around the kernels of the diff path (tsm_diff_last_ms)
+  float diff_ms[3] = {0, 0, 0};            // k_scan over both sides, k_myers, k_myers_trace of the last diff
+  struct HostSidePair* res_pair = nullptr; // sides kept in HBM by tsm_diff_upload
   static constexpr int kMaxSlabs = 64;
   tsm_file_stat* d_stats = nullptr;
   unsigned long long* d_cand = nullptr;
@@ -134,20 +150,7 @@ extern "C" const char* tsm_category_name(int id) {
   return kNames[id];
 }
 
-static void build_lut(uint32_t* lut) {                   // the one automaton table of tsm_device.cuh
-  struct Pat { const char* s; int first; bool ci; };
-  static const Pat pats[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"class", 13, false}, {"def", 18, false},
-                             {"test", 21, true}, {"void", 25, false}, {"{", 29, false}, {"_F", 30, false}};
-  memset(lut, 0, 256 * sizeof(uint32_t));
-  for (const Pat& p : pats)
-    for (int k = 0; p.s[k]; ++k) {
-      const unsigned char c = (unsigned char)p.s[k];
-      lut[c] |= 1u << (p.first + k);
-      if (p.ci && c >= 'a' && c <= 'z') lut[c - 32] |= 1u << (p.first + k);
-    }
-}
-
-static void build_lut2(uint32_t* lut) {                  // table of k_scan2: bit 30 = 'F' (gate of the TEST_F check), bit 31 = newline
+static void build_lut(uint32_t* lut) {                   // the automaton table of tsm_device.cuh (bit 30 = 'F', bit 31 = newline)
   struct Pat { const char* s; int first; bool ci; };
   static const Pat pats[] = {{"assert", 0, true}, {"EXPECT_", 6, false}, {"class", 13, false}, {"def", 18, false},
                              {"test", 21, true}, {"void", 25, false}, {"{", 29, false}, {"F", 30, false}, {"\n", 31, false}};
@@ -169,6 +172,8 @@ static void build_elut(uint32_t* lut) {                  // operator patterns of
     for (int k = 0; p.s[k]; ++k) lut[(unsigned char)p.s[k]] |= 1u << (p.first + k);
 }
 
+static void free_res_pair(tsm_ctx* c);
+
 extern "C" void tsm_destroy(tsm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -178,6 +183,8 @@ extern "C" void tsm_destroy(tsm_ctx* c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (cudaEvent_t e : c->slab_ev) if (e) cudaEventDestroy(e);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);
+  for (cudaEvent_t e : c->diff_ev) if (e) cudaEventDestroy(e);
+  free_res_pair(c);
   cudaFree(c->d_cand); cudaFree(c->d_hev); cudaFree(c->d_aev);
   if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
   for (auto& set : c->ev) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
@@ -198,9 +205,11 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   tsm_ctx* c = new (std::nothrow) tsm_ctx;
   if (!c) return TSM_E_NOMEM;
   c->device = device;
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  c->sms = prop.multiProcessorCount;
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) { tsm_destroy(c); return TSM_E_CUDA; }
+    c->sms = sms;
+  }
   c->max_arena = (max_arena_bytes + 127) / 128 * 128;
   c->max_files = max_files;
   c->max_groups = max_groups;
@@ -226,6 +235,7 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   if (rc == TSM_OK && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = TSM_E_CUDA;
   for (cudaEvent_t& e : c->slab_ev) if (rc == TSM_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = TSM_E_CUDA;
   if (rc == TSM_OK && cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming) != cudaSuccess) rc = TSM_E_CUDA;
+  for (cudaEvent_t& e : c->diff_ev) if (rc == TSM_OK && cudaEventCreate(&e) != cudaSuccess) rc = TSM_E_CUDA;
   A((void**)&c->d_stats, sizeof(tsm_file_stat) * (size_t)max_files);
   A((void**)&c->d_cand, sizeof(unsigned long long) * (size_t)c->max_events);
   if (rc == TSM_OK && cudaHostAlloc((void**)&c->h_ctrl, sizeof(Ctrl) + 64, cudaHostAllocDefault) != cudaSuccess) rc = TSM_E_CUDA;
@@ -236,20 +246,15 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
     static const uint8_t slot[TSM_CAT_SLOTS] = TSM_CAT_SLOT_INIT;
     static const uint16_t offs[TSM_CAT_NAMED + 1] = TSM_CAT_OFF_INIT;
     static const char blob[] = TSM_CAT_BLOB_INIT;
-    uint32_t elut[256], lut2[256];
+    uint32_t elut[256];
     build_elut(elut);
-    build_lut2(lut2);
-    const char* impl = getenv("TSM_SCAN_IMPL");          // A/B knob of the round-2 rewrite: 1 = the first-generation k_scan
-    c->scan_v1 = impl && impl[0] == '1';
     if (cudaMemcpyToSymbol(c_lut, lut, sizeof lut) != cudaSuccess ||
-        cudaMemcpyToSymbol(c_lut2, lut2, sizeof lut2) != cudaSuccess ||
-        cudaFuncSetAttribute(k_scan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess ||
         cudaMemcpyToSymbol(c_elut, elut, sizeof elut) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_slot, slot, sizeof slot) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_off, offs, sizeof offs) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_blob, blob, TSM_CAT_BLOB_LEN + 1) != cudaSuccess ||
         cudaMemset(c->d_arena, 0, (size_t)c->max_arena + 4096) != cudaSuccess ||
-        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess)
       rc = TSM_E_CUDA;
   }
   if (rc != TSM_OK) {
@@ -353,7 +358,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     c->ev_next = (es + 1) % tsm_ctx::kRing;
     fold_events(c, es);                                  // only blocks when 32 scans are in flight
     cudaEvent_t* ev = c->ev[es];
-    cudaEventRecord(ev[0], st);
+    CU(cudaEventRecord(ev[0], st));
     const int n_slabs = (int)cut.size() - 1;
     for (int s = 0; s < n_slabs; ++s) {
       const int32_t f0 = cut[(size_t)s], f1 = cut[(size_t)s + 1];
@@ -367,12 +372,13 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       // units of earlier slabs are bounded by (arena bytes before f0) / CH + f0
       p.unit_base = (uint32_t)((host ? (int64_t)host->off[f0] : 0) / CH + f0);
       k_plan<<<(f1 - f0 + 255) / 256, 256, 0, st>>>(p);
-      if (s == 0 && n_slabs == 1) cudaEventRecord(ev[1], st);
-      if (c->scan_v1) k_scan<<<c->sms * SCAN_CTAS_PER_SM, SCAN_WARPS * 32, SCAN_SMEM, st>>>(p);
-      else k_scan2<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+      CU(cudaGetLastError());
+      if (s == 0 && n_slabs == 1) CU(cudaEventRecord(ev[1], st));
+      k_scan<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+      CU(cudaGetLastError());
     }
-    if (n_slabs > 1) cudaEventRecord(ev[1], st);          // per-kernel split is only meaningful for one slab
-    cudaEventRecord(ev[2], st);
+    if (n_slabs > 1) CU(cudaEventRecord(ev[1], st));      // per-kernel split is only meaningful for one slab
+    CU(cudaEventRecord(ev[2], st));
     const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
     if (c->cls_smem != hist) {                           // one resident wave of k_classify (grid-stride inside): measured
       int per_sm = 0;                                    // -7 % on C2 against 8 blocks per SM, equal on C4
@@ -381,8 +387,9 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       c->cls_smem = hist;
     }
     k_classify<<<c->cls_grid, 256, hist, st>>>(p);
-    cudaEventRecord(ev[3], st);
-    cudaEventRecord(ev[4], st);                           // (slot of the former k_totals, now fused into k_classify)
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ev[3], st));
+    CU(cudaEventRecord(ev[4], st));                           // (slot of the former k_totals, now fused into k_classify)
     c->ev_used[es] = (n_slabs == 1);
     c->ev_last = es;
     c->launches = 2 * n_slabs + 1;
@@ -505,15 +512,18 @@ extern "C" int tsm_reduce(tsm_ctx* c, const uint8_t* flags, const int32_t* repo,
   cudaStream_t st = (cudaStream_t)stream;
   const size_t words = ((size_t)n_cases + 31) / 32;
   const size_t nbits = (size_t)(n_flags + 1) * n_repos * words;
-  uint8_t* d_flags = nullptr; int32_t *d_repo = nullptr, *d_case = nullptr; uint32_t* d_bits = nullptr;
-  unsigned long long* d_out = nullptr;
+  DevBuf b_flags, b_repo, b_case, b_bits, b_out;          // scratch from the ctx's pool (kept between calls)
+  SyncGuard guard(st);
+  if (!b_flags.alloc((size_t)n_rows * n_flags) || !b_repo.alloc(sizeof(int32_t) * (size_t)n_rows) ||
+      !b_case.alloc(sizeof(int32_t) * (size_t)n_rows) || !b_bits.alloc(sizeof(uint32_t) * nbits) ||
+      !b_out.alloc(sizeof(unsigned long long) * (size_t)(n_flags + 1) * n_repos))
+    return TSM_E_CUDA;
+  uint8_t* d_flags = b_flags.as<uint8_t>(); int32_t *d_repo = b_repo.as<int32_t>(), *d_case = b_case.as<int32_t>();
+  uint32_t* d_bits = b_bits.as<uint32_t>();
+  unsigned long long* d_out = b_out.as<unsigned long long>();
   int rc = TSM_OK;
-  auto A = [&](void** p, size_t b) { if (rc == TSM_OK && cudaMalloc(p, b ? b : 16) != cudaSuccess) rc = TSM_E_CUDA; };
-  A((void**)&d_flags, (size_t)n_rows * n_flags); A((void**)&d_repo, sizeof(int32_t) * (size_t)n_rows);
-  A((void**)&d_case, sizeof(int32_t) * (size_t)n_rows); A((void**)&d_bits, sizeof(uint32_t) * nbits);
-  A((void**)&d_out, sizeof(unsigned long long) * (size_t)(n_flags + 1) * n_repos);
   std::vector<unsigned long long> h((size_t)(n_flags + 1) * n_repos);
-  if (rc == TSM_OK) {
+  {
     bool ok = true;
     if (n_rows) {
       ok &= cudaMemcpyAsync(d_flags, flags, (size_t)n_rows * n_flags, cudaMemcpyHostToDevice, st) == cudaSuccess;
@@ -527,7 +537,6 @@ extern "C" int tsm_reduce(tsm_ctx* c, const uint8_t* flags, const int32_t* repo,
     ok &= cudaStreamSynchronize(st) == cudaSuccess;
     if (!ok) rc = TSM_E_CUDA;
   }
-  cudaFree(d_flags); cudaFree(d_repo); cudaFree(d_case); cudaFree(d_bits); cudaFree(d_out);
   if (rc != TSM_OK) return rc;
   // row 0 of the device table = "any row" (cases per repo), rows 1.. = the flags
   for (int32_t r = 0; r < n_repos; ++r) if (cases_per_repo) cases_per_repo[r] = (int64_t)h[r];
@@ -548,15 +557,8 @@ extern "C" void tsm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------- S8 diff
 namespace {
-struct DevBuf {                                           // device scratch from the ctx's pool, returned on scope exit
-  void* p = nullptr;
-  ~DevBuf() { reset(); }
-  void reset() { if (p && t_pool) t_pool->give(p); p = nullptr; }
-  bool alloc(size_t bytes) { reset(); p = t_pool ? t_pool->take(bytes ? bytes : 16) : nullptr; return p != nullptr; }
-  template <typename T> T* as() const { return static_cast<T*>(p); }
-};
-
 struct HostSide {                                         // device image of one side of the pairs + its line records
+  int32_t n = 0; size_t ab = 0; uint32_t unit_cap = 0;
   DevBuf arena, off, len, ext, line_base, line_end, line_hash, line_flag;
   DevBuf unit_file, unit_begin, cnt, unit_first, bsum, zero, stats, unit_lines, unit_out, unit_line_base, s_hash, s_end, s_flag;
   std::vector<unsigned long long> base;                   // host copy of line_base
@@ -573,20 +575,16 @@ static void xscan(const uint32_t* in, uint32_t n, unsigned long long* bsum, unsi
   k_xscan_apply<<<nb, 256, 0, st>>>(in, n, bsum, out);
 }
 
-// One side's line records in file order (docs/SPEC.md sections 2-4): line_base[n+1], and per line its hash, its
-// end and whether it is an assertion line.  One pass of k_scan2 over the source (TSM_SCAN_LINE_HASHES: every
-// chunk writes the records of its own lines into a region of the staging arrays), one exclusive scan of the
-// lines per unit, one gather.  The staging arrays are sized for 8-byte lines; a corpus with more lines than
-// that is scanned a second time with the exact size (the first pass counted them).
-int side_lines(tsm_ctx* c, const tsm_corpus* k, HostSide& h, cudaStream_t st) {
+int side_upload(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
   const int32_t n = k->n_files;
   const size_t ab = (size_t)k->off[n];
-  const uint32_t unit_cap = (uint32_t)(ab / CH + (size_t)n + 1);
-  const size_t zero_bytes = 256 + sizeof(SlabCtl);
+  h.n = n; h.ab = ab;
+  h.unit_cap = (uint32_t)(ab / CH + (size_t)n + 1);
+  const uint32_t unit_cap = h.unit_cap;
   if (!h.arena.alloc(ab + 4096) || !h.off.alloc(sizeof(int32_t) * ((size_t)n + 1)) || !h.len.alloc(sizeof(int32_t) * (size_t)n) ||
       !h.ext.alloc((size_t)n) || !h.unit_file.alloc(sizeof(uint32_t) * unit_cap) || !h.unit_begin.alloc(sizeof(uint32_t) * unit_cap) ||
       !h.cnt.alloc(sizeof(uint32_t) * (size_t)n) || !h.unit_first.alloc(sizeof(unsigned long long) * ((size_t)n + 1)) ||
-      !h.bsum.alloc(sizeof(unsigned long long) * (unit_cap / XS_TILE + 4)) || !h.zero.alloc(zero_bytes) ||
+      !h.bsum.alloc(sizeof(unsigned long long) * (unit_cap / XS_TILE + 4)) || !h.zero.alloc(256 + sizeof(SlabCtl)) ||
       !h.stats.alloc(sizeof(tsm_file_stat) * (size_t)n) || !h.unit_lines.alloc(sizeof(uint32_t) * unit_cap) ||
       !h.unit_out.alloc(sizeof(uint32_t) * unit_cap) || !h.unit_line_base.alloc(sizeof(unsigned long long) * ((size_t)unit_cap + 1)) ||
       !h.line_base.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
@@ -597,6 +595,20 @@ int side_lines(tsm_ctx* c, const tsm_corpus* k, HostSide& h, cudaStream_t st) {
   CU(cudaMemcpyAsync(h.len.p, k->len, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
   if (k->ext) CU(cudaMemcpyAsync(h.ext.p, k->ext, (size_t)n, cudaMemcpyHostToDevice, st));
   else CU(cudaMemsetAsync(h.ext.p, 0, (size_t)n, st));
+  return TSM_OK;
+}
+
+// One side's line records in file order (docs/SPEC.md sections 2-4) from the uploaded bytes: line_base[n+1], and per
+// line its hash, its end and whether it is an assertion line.  One pass of k_scan over the source
+// (TSM_SCAN_LINE_HASHES: every chunk writes the records of its own lines into a region of the staging arrays), one
+// exclusive scan of the lines per unit, one gather.  The staging arrays are sized for 8-byte lines; a corpus with
+// more lines than that is scanned a second time with the exact size (the first pass counted them).  scan_ms adds
+// the device time of the k_scan launches (CUDA events on st).
+int side_records(tsm_ctx* c, HostSide& h, cudaStream_t st, float* scan_ms) {
+  const int32_t n = h.n;
+  const size_t ab = h.ab;
+  const uint32_t unit_cap = h.unit_cap;
+  const size_t zero_bytes = 256 + sizeof(SlabCtl);
   ScanParams p{};
   p.arena = h.arena.as<uint8_t>(); p.off = h.off.as<int32_t>(); p.len = h.len.as<int32_t>(); p.ext = h.ext.as<uint8_t>();
   p.grp = nullptr; p.n_files = n; p.n_groups = 1;
@@ -619,10 +631,13 @@ int side_lines(tsm_ctx* c, const tsm_corpus* k, HostSide& h, cudaStream_t st) {
     p.lh_cap = (uint32_t)cap;
     CU(cudaMemsetAsync(h.zero.p, 0, zero_bytes, st));
     k_plan_det<<<(n + 1 + 255) / 256, 256, 0, st>>>(p, h.unit_first.as<unsigned long long>());
-    k_scan2<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+    CU(cudaEventRecord(c->diff_ev[0], st));
+    k_scan<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+    CU(cudaEventRecord(c->diff_ev[1], st));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&hc, p.ctrl, sizeof hc, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (scan_ms) { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[0], c->diff_ev[1]) == cudaSuccess) *scan_ms += ms; }
     h.launches += 6;
     if (hc.overflow) return TSM_E_CAPACITY;
     if (!hc.lh_overflow) break;
@@ -663,25 +678,33 @@ int side_lines(tsm_ctx* c, const tsm_corpus* k, HostSide& h, cudaStream_t st) {
 }
 }  // namespace
 
-extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
-                                     int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream) {
-  if (!c || !olds || !news || !added || !removed || olds->n_files != news->n_files) return TSM_E_ARG;
+struct HostSidePair { HostSide A, B; int32_t n = 0; bool have_records = false; };
+
+static void free_res_pair(tsm_ctx* c) {
+  if (!c->res_pair) return;
+  PoolScope pool_scope(&c->pool);                          // the buffers go back to the ctx's pool
+  delete c->res_pair;
+  c->res_pair = nullptr;
+}
+
+static int check_pair_layout(const tsm_corpus* olds, const tsm_corpus* news, bool with_ext) {
   const int32_t n = olds->n_files;
-  if (n == 0) return TSM_OK;
   for (const tsm_corpus* k : {olds, news}) {              // same layout rules as the scan (SPEC section 1)
     if (!k->arena || !k->off || !k->len) return TSM_E_ARG;
     for (int32_t i = 0; i < n; ++i)
       if (k->off[i] < 0 || (k->off[i] & (TSM_ALIGN - 1)) || k->len[i] < 0 || (int64_t)k->off[i] + k->len[i] > k->off[i + 1] ||
-          (detail && k->ext && k->ext[i] > TSM_EXT_H))
+          (with_ext && k->ext && k->ext[i] > TSM_EXT_H))
         return TSM_E_LAYOUT;
   }
-  CU(cudaSetDevice(c->device));
-  PoolScope pool_scope(&c->pool);
-  cudaStream_t st = (cudaStream_t)stream;
-  HostSide A, B;
-  int rc = side_lines(c, olds, A, st);
-  if (rc == TSM_OK) rc = side_lines(c, news, B, st);
-  if (rc != TSM_OK) return rc;
+  return TSM_OK;
+}
+
+// The diff proper over two sides whose line records exist: k_myers (edit distance per pair), then for `detail`
+// k_myers_trace (the canonical script: hunks, changed assertion lines).  A pair whose distance D needs more
+// than TSM_DIFF_TRACE_MAX_INTS trace entries ((D+1)(D+2)/2) is not traced: it is reported as ONE hunk
+// (add / del / mod by its counts) with added_assert = removed_assert = -1 (tosemscan.h).
+static int diff_core(tsm_ctx* c, HostSide& A, HostSide& B, int32_t n, int64_t* added, int64_t* removed,
+                     tsm_diff_detail* detail, cudaStream_t st) {
   std::vector<unsigned long long> vbase((size_t)n + 1, 0);
   for (int32_t i = 0; i < n; ++i)
     vbase[(size_t)i + 1] = vbase[(size_t)i] + 2 * ((A.base[(size_t)i + 1] - A.base[(size_t)i]) + (B.base[(size_t)i + 1] - B.base[(size_t)i])) + 3;
@@ -690,15 +713,19 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
       !d_add.alloc(sizeof(long long) * (size_t)n) || !d_rem.alloc(sizeof(long long) * (size_t)n))
     return TSM_E_CUDA;
   CU(cudaMemcpyAsync(d_vbase.p, vbase.data(), sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(c->diff_ev[2], st));
   k_myers<<<(n * 32 + 127) / 128, 128, 0, st>>>(A.d.line_hash, A.d.line_base, B.d.line_hash, B.d.line_base, n,
                                                d_v.as<int32_t>(), d_vbase.as<unsigned long long>(),
                                                d_add.as<long long>(), d_rem.as<long long>());
+  CU(cudaEventRecord(c->diff_ev[3], st));
   CU(cudaGetLastError());
   static_assert(sizeof(long long) == sizeof(int64_t), "int64");
   CU(cudaMemcpyAsync(added, d_add.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(removed, d_rem.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[2], c->diff_ev[3]) == cudaSuccess) c->diff_ms[1] = ms; }
   c->launches = A.launches + B.launches + 1;
+  c->diff_ms[2] = 0;
   if (!detail) return TSM_OK;
   // ---- hunks: second search with the rows of V kept; rows sized from the distances just computed,
   //      pairs processed in batches of at most 2^28 trace ints (1 GiB)
@@ -706,34 +733,110 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
   DevBuf d_detail, d_tbase;
   if (!d_detail.alloc(sizeof(tsm_diff_detail) * (size_t)n) || !d_tbase.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
     return TSM_E_CUDA;
+  CU(cudaMemsetAsync(d_detail.p, 0, sizeof(tsm_diff_detail) * (size_t)n, st));
   std::vector<unsigned long long> tbase((size_t)n + 1, 0);
-  const unsigned long long kBatch = 1ull << 28;
+  std::vector<int32_t> untraced;
+  const unsigned long long kBatch = TSM_DIFF_TRACE_MAX_INTS;
   int32_t p0 = 0;
   while (p0 < n) {
     int32_t p1 = p0;
     unsigned long long tot = 0;
     while (p1 < n) {
       const unsigned long long D = (unsigned long long)(added[p1] + removed[p1]);
-      const unsigned long long need = (D + 1) * (D + 2) / 2;
+      unsigned long long need = (D + 1) * (D + 2) / 2;
+      if (need > kBatch) { untraced.push_back(p1); need = 1; }      // k_myers_trace skips it (row table of one int)
       if (p1 > p0 && tot + need > kBatch) break;
       tbase[(size_t)p1] = tot;
       tot += need;
       ++p1;
     }
     DevBuf d_trace;
-    if (!d_trace.alloc(sizeof(int32_t) * (size_t)tot)) return TSM_E_CAPACITY;   // one pair alone exceeds device memory
+    if (!d_trace.alloc(sizeof(int32_t) * (size_t)tot)) return TSM_E_CUDA;
     CU(cudaMemcpyAsync(d_tbase.as<unsigned long long>() + p0, tbase.data() + p0, sizeof(unsigned long long) * (size_t)(p1 - p0),
                        cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->diff_ev[4], st));
     k_myers_trace<<<((p1 - p0) * 32 + 127) / 128, 128, 0, st>>>(
         A.d.line_hash, A.d.line_base, A.d.line_flag, B.d.line_hash, B.d.line_base, B.d.line_flag, p0, p1 - p0,
-        d_trace.as<int32_t>(), d_tbase.as<unsigned long long>(), d_detail.as<tsm_diff_detail>());
+        d_trace.as<int32_t>(), d_tbase.as<unsigned long long>(), d_add.as<long long>(), d_rem.as<long long>(),
+        (long long)TSM_DIFF_TRACE_MAX_D, d_detail.as<tsm_diff_detail>());
+    CU(cudaEventRecord(c->diff_ev[5], st));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
+    { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[4], c->diff_ev[5]) == cudaSuccess) c->diff_ms[2] += ms; }
     c->launches++;
     p0 = p1;
   }
   CU(cudaMemcpyAsync(detail, d_detail.p, sizeof(tsm_diff_detail) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  for (int32_t i : untraced) {                              // too far apart to trace: one hunk, assertion counts unknown
+    tsm_diff_detail d{0, 0, 0, -1, -1};
+    if (added[i] && removed[i]) d.hunks_mod = 1; else if (added[i]) d.hunks_add = 1; else d.hunks_del = 1;
+    detail[i] = d;
+  }
+  return TSM_OK;
+}
+
+extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news,
+                                     int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream) {
+  if (!c || !olds || !news || !added || !removed || olds->n_files != news->n_files) return TSM_E_ARG;
+  const int32_t n = olds->n_files;
+  if (n == 0) return TSM_OK;
+  int rc = check_pair_layout(olds, news, detail != nullptr);
+  if (rc != TSM_OK) return rc;
+  CU(cudaSetDevice(c->device));
+  PoolScope pool_scope(&c->pool);
+  cudaStream_t st = (cudaStream_t)stream;
+  HostSide A, B;
+  SyncGuard guard(st);                                     // no buffer goes back to the pool while work on st may still use it
+  c->diff_ms[0] = 0;
+  rc = side_upload(olds, A, st);
+  if (rc == TSM_OK) rc = side_upload(news, B, st);
+  if (rc == TSM_OK) rc = side_records(c, A, st, &c->diff_ms[0]);
+  if (rc == TSM_OK) rc = side_records(c, B, st, &c->diff_ms[0]);
+  if (rc != TSM_OK) return rc;
+  return diff_core(c, A, B, n, added, removed, detail, st);
+}
+
+// Resident variant (what bench.py's `value` times for config C5): the two sides go to HBM once ...
+extern "C" int tsm_diff_upload(tsm_ctx* c, const tsm_corpus* olds, const tsm_corpus* news, void* stream) {
+  if (!c || !olds || !news || olds->n_files != news->n_files || olds->n_files <= 0) return TSM_E_ARG;
+  int rc = check_pair_layout(olds, news, true);
+  if (rc != TSM_OK) return rc;
+  CU(cudaSetDevice(c->device));
+  free_res_pair(c);
+  PoolScope pool_scope(&c->pool);
+  cudaStream_t st = (cudaStream_t)stream;
+  SyncGuard guard(st);
+  c->res_pair = new (std::nothrow) HostSidePair;
+  if (!c->res_pair) return TSM_E_NOMEM;
+  c->res_pair->n = olds->n_files;
+  rc = side_upload(olds, c->res_pair->A, st);
+  if (rc == TSM_OK) rc = side_upload(news, c->res_pair->B, st);
+  if (rc == TSM_OK) rc = cudaStreamSynchronize(st) == cudaSuccess ? TSM_OK : TSM_E_CUDA;
+  if (rc != TSM_OK) { delete c->res_pair; c->res_pair = nullptr; }
+  return rc;
+}
+
+// ... and every call runs the kernels over them: k_scan over both sides (line records), k_myers, k_myers_trace.
+extern "C" int tsm_diff_resident(tsm_ctx* c, int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream) {
+  if (!c || !added || !removed) return TSM_E_ARG;
+  if (!c->res_pair) return TSM_E_STATE;
+  CU(cudaSetDevice(c->device));
+  PoolScope pool_scope(&c->pool);
+  cudaStream_t st = (cudaStream_t)stream;
+  SyncGuard guard(st);
+  HostSidePair& P = *c->res_pair;
+  c->diff_ms[0] = 0;
+  P.A.launches = P.B.launches = 0;
+  int rc = side_records(c, P.A, st, &c->diff_ms[0]);
+  if (rc == TSM_OK) rc = side_records(c, P.B, st, &c->diff_ms[0]);
+  if (rc != TSM_OK) return rc;
+  return diff_core(c, P.A, P.B, P.n, added, removed, detail, st);
+}
+
+extern "C" int tsm_diff_last_ms(tsm_ctx* c, float* ms3) {
+  if (!c || !ms3) return TSM_E_ARG;
+  for (int i = 0; i < 3; ++i) ms3[i] = c->diff_ms[i];
   return TSM_OK;
 }
 
@@ -760,7 +863,9 @@ extern "C" int tsm_line_hashes(tsm_ctx* c, const tsm_corpus* k, int64_t* line_ba
   PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   HostSide S;
-  int rc = side_lines(c, k, S, st);
+  SyncGuard guard(st);
+  int rc = side_upload(k, S, st);
+  if (rc == TSM_OK) rc = side_records(c, S, st, nullptr);
   if (rc != TSM_OK) return rc;
   const unsigned long long total = S.base[(size_t)n];
   for (int32_t i = 0; i <= n; ++i) line_base[i] = (int64_t)S.base[(size_t)i];
@@ -801,7 +906,9 @@ extern "C" int tsm_statements(tsm_ctx* c, const tsm_corpus* k, int64_t* line_bas
   PoolScope pool_scope(&c->pool);
   cudaStream_t st = (cudaStream_t)stream;
   HostSide S;
-  int rc = side_lines(c, k, S, st);                       // line records from one pass of the scan
+  SyncGuard guard(st);
+  int rc = side_upload(k, S, st);                         // line records from one pass of the scan
+  if (rc == TSM_OK) rc = side_records(c, S, st, nullptr);
   if (rc != TSM_OK) return rc;
   const unsigned long long total = S.base[(size_t)n];
   for (int32_t i = 0; i <= n; ++i) line_base[i] = (int64_t)S.base[(size_t)i];

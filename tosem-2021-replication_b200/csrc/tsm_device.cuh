@@ -3,7 +3,7 @@
 // Data layout in HBM (docs/SPEC.md section 1, DESIGN.md "layout"):
 //   arena      u8   files end-to-end, each start 128-B aligned (cp.async.bulk needs 16 B)
 //   off/len    i32  per-file start and size          ext u8, grp u16 per-file tags
-//   unit_file / unit_begin  u32  work units = (file, 4 KiB chunk), built by k_plan
+//   unit_file / unit_begin  u32  work units = (file, 4 KiB chunk), built by k_plan (or k_plan_det, in file order)
 //   stats      {u32 lines, asserts, headers, fixtures; u64 digest} per file
 //   cand       u64  (file << 32 | line offset) of every assertion line, consumed by k_classify
 //   counts     i64  [n_groups + 1][128]   (row n_groups = global)
@@ -22,61 +22,22 @@ constexpr uint32_t EXT = 240;                 // bytes loaded behind (terminator
 constexpr uint32_t BUF = PRE + CH + EXT;      // 4352 = 34 * 128 = 32 * 136
 constexpr uint32_t STRIPE = BUF / 32;         // 136 = 8 * 17: stride of conflict-free per-lane LDS.64
 static_assert(STRIPE * 32 == BUF && STRIPE % 8 == 0 && (STRIPE / 8) % 2 == 1, "stripe geometry");
-#ifndef TSM_NL_CAP
-#define TSM_NL_CAP 384
-#endif
-#ifndef TSM_LOCKSTEP
-#define TSM_LOCKSTEP 1
-#endif
-#ifndef TSM_RW_SHIFT
-#define TSM_RW_SHIFT 2
-#endif
-#ifndef TSM_SCAN_WARPS
-#define TSM_SCAN_WARPS 8
-#endif
-#ifndef TSM_SCAN_CTAS
-#define TSM_SCAN_CTAS 3
-#endif
-constexpr uint32_t NL_CAP = TSM_NL_CAP;       // line-table entries per window
-constexpr uint32_t TAB_BYTES = (NL_CAP + 8) * 2;    // u16 per line: newline position (13 bits) | LF_* flags << 13 (NL_CAP + 1 used)
-constexpr uint32_t TAB_POS = 0x1FFFu;                // BUF < 8192
-constexpr uint32_t FLAG_CAP = NL_CAP + 8;            // u32 per line of the window: OR of the automaton states (pass 2 -> pass 3)
-#ifndef TSM_Q_CAP
-#define TSM_Q_CAP 64
-#endif
-constexpr uint32_t Q_CAP = TSM_Q_CAP;                       // words whose matches need a byte-exact line (pass 2b)
-// per-warp shared memory of k_scan, offsets from the warp's base
-constexpr uint32_t OFF_TAB = BUF;                    // u16[NL_CAP + 8]   line table
-constexpr uint32_t RW_SHIFT = TSM_RW_SHIFT, RW_STRIDE = 1u << RW_SHIFT;   // hash-prefix checkpoint every RW_STRIDE words
-constexpr uint32_t RW_PER_STRIPE = 16u >> RW_SHIFT;  // (the 17th word of a stripe needs none: the next stripe starts from its base)
-constexpr uint32_t OFF_RW = OFF_TAB + TAB_BYTES;     // u64[32 * RW_PER_STRIPE]  running hash prefix behind the checkpointed words
-constexpr uint32_t OFF_FLAGS = OFF_RW + 32 * RW_PER_STRIPE * 8;         // u32[FLAG_CAP]     (pass 3 compacts the candidate list into it, u16 each)
-constexpr uint32_t OFF_MSK = OFF_FLAGS + FLAG_CAP * 4;   // u32[5][32]    newline bits of every stripe
-constexpr uint32_t OFF_BASE = OFF_MSK + 5 * 32 * 4;  // u64[33]           hash prefix at every stripe start (+ total)
-constexpr uint32_t OFF_Q = OFF_BASE + 34 * 8;        // u32[Q_CAP]
-constexpr uint32_t OFF_CTL = OFF_Q + Q_CAP * 4;      // u32 queue length, pad, u64 mbarrier
-constexpr uint32_t WARP_SMEM = ((OFF_CTL + 16 + 127) / 128) * 128;
-static_assert(NL_CAP % 4 == 0 && NL_CAP >= 64, "window size");
-static_assert(BUF <= TAB_POS + 1, "line-table positions must fit 13 bits");
-static_assert(OFF_RW % 8 == 0 && OFF_FLAGS % 4 == 0 && OFF_MSK % 4 == 0 && OFF_BASE % 8 == 0 && OFF_CTL % 8 == 0, "alignment");
 constexpr uint32_t LUT_BYTES = 1024 + 128;    // the 256-entry automaton table + the per-language pattern-end masks
-constexpr int SCAN_WARPS = TSM_SCAN_WARPS;    // warps per CTA of k_scan (each warp is independent)
-constexpr int SCAN_CTAS_PER_SM = TSM_SCAN_CTAS;
-constexpr uint32_t SCAN_SMEM = LUT_BYTES + SCAN_WARPS * WARP_SMEM;
 
 // ---- multi-pattern Shift-And automaton (SPEC sections 4, 5) ------------------------------------------
 // One state bit per pattern byte; D' = ((D << 1) | FIRST) & LUT[c]; a line's OR of all D tells which
 // patterns ended somewhere inside it.  ONE table for all languages (its address is a compile-time
-// constant: the lookups are LDS [byte * 4 + const]); the language only decides which pattern ends count:
+// constant); the language only decides which pattern ends count:
 //   bits  0.. 5  assert (ci)    bits  6..12  EXPECT_ (cs)   bits 13..17  class     bits 18..20  def
-//   bits 21..24  test (ci)      bits 25..28  void           bit  29      {         bits 30..31  _F (gate of the TEST_F check)
-constexpr uint32_t A_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 18) | (1u << 21) | (1u << 25) | (1u << 29) | (1u << 30);
+//   bits 21..24  test (ci)      bits 25..28  void           bit  29      {         bit  30      F (gate of the TEST_F check)
+//   bit  31      '\n' (the OR of a word's states says whether the word holds a newline)
+constexpr uint32_t B_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 18) | (1u << 21) | (1u << 25) | (1u << 29) | (1u << 30) | (1u << 31);
 constexpr uint32_t AF_ASSERT = 1u << 5, AF_EXPECT = 1u << 12, A_CLASS = 1u << 17, A_DEF = 1u << 20, A_TEST = 1u << 24,
-                   A_VOID = 1u << 28, A_BRACE = 1u << 29, A_STF = 1u << 31;
-// header patterns per language family: group 1, group 2, TEST_F gate (SPEC section 5)
+                   A_VOID = 1u << 28, A_BRACE = 1u << 29, B_F = 1u << 30;
+// header patterns per language family: group 1, group 2 (SPEC section 5)
 constexpr uint32_t PY_G1 = A_DEF, PY_G2 = A_CLASS, CJ_G1 = A_TEST, CJ_G2 = A_BRACE | A_CLASS | A_VOID;
 
-// per-line flag byte written by k_scan's pass 3
+// flags of a finished line
 constexpr uint8_t LF_CAND = 1, LF_HDR = 2, LF_FIX = 4;
 
 struct Ctrl {                     // device control block, zeroed before every scan
@@ -84,9 +45,14 @@ struct Ctrl {                     // device control block, zeroed before every s
   uint32_t n_hev;
   uint32_t n_aev;
   uint32_t overflow;              // some list hit its capacity
-  uint32_t n_lh;                  // line-record slots reserved by k_scan2 (TSM_SCAN_LINE_HASHES)
+  uint32_t n_lh;                  // line-record slots reserved by k_scan (TSM_SCAN_LINE_HASHES)
   uint32_t lh_overflow;           // ... and whether the staging arrays were too small for them
 };
+
+// tsm_diff_pairs_detail keeps (D+1)(D+2)/2 ints per pair for the backtrack: at most 2^28 (1 GiB), i.e. D <= 23 168
+constexpr unsigned long long TSM_DIFF_TRACE_MAX_INTS = 1ull << 28;
+constexpr long long TSM_DIFF_TRACE_MAX_D = 23168;
+static_assert((TSM_DIFF_TRACE_MAX_D + 1) * (TSM_DIFF_TRACE_MAX_D + 2) / 2 <= (long long)TSM_DIFF_TRACE_MAX_INTS && (TSM_DIFF_TRACE_MAX_D + 2) * (TSM_DIFF_TRACE_MAX_D + 3) / 2 > (long long)TSM_DIFF_TRACE_MAX_INTS, "cap");
 
 struct SlabCtl { uint32_t n_units, work; };   // per-slab unit count (k_plan) and work cursor (k_scan)
 
@@ -122,7 +88,7 @@ struct ScanParams {
   uint32_t lh_cap;
   uint32_t* unit_lines;           // [unit slots]
   uint32_t* unit_out;             // [unit slots]
-  uint32_t four;                  // 4 (a multiplier the compiler must not see: tsm_scan2_kernels.cuh, lut_at)
+  uint32_t four;                  // 4 (a multiplier the compiler must not see: tsm_scan_walk.cuh, lut_at)
 };
 
 // ---- hashing (SPEC section 3) -------------------------------------------------------------------------

@@ -23,80 +23,6 @@ struct DiffSide {                   // one corpus (old or new) on the device
   uint8_t* line_flag;               // [total lines] 1 = assertion line (SPEC section 4); NULL = not wanted
 };
 
-__device__ __forceinline__ uint32_t nl16_at(const uint8_t* g, uint32_t pos, uint32_t size) {
-  // 16 bytes at file offset pos (16-B aligned; the arena is padded so the load is in bounds)
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + pos));
-  uint32_t bits = nl16(v);
-  const uint32_t valid = size - pos;
-  if (valid < 16) bits &= (1u << valid) - 1u;
-  return bits;
-}
-
-__global__ void k_count_lines(DiffSide d, int32_t n) {
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (f >= n) return;
-  const uint8_t* g = d.arena + (uint32_t)d.off[f];
-  const uint32_t size = (uint32_t)d.len[f];
-  uint32_t c = 0;
-  for (uint32_t pos = lane * 16; pos < size; pos += 512) c += __popc(nl16_at(g, pos, size));
-#pragma unroll
-  for (int k = 16; k; k >>= 1) c += __shfl_xor_sync(0xffffffffu, c, k);
-  if (lane == 0) d.n_lines[f] = c + ((size && __ldg(g + size - 1) != '\n') ? 1u : 0u);   // unterminated last line
-}
-
-__global__ void k_mark_lines(DiffSide d, int32_t n) {
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (f >= n) return;
-  const uint8_t* g = d.arena + (uint32_t)d.off[f];
-  const uint32_t size = (uint32_t)d.len[f];
-  unsigned long long at = d.line_base[f];
-  for (uint32_t tp = 0; tp < size; tp += 512) {
-    const uint32_t pos = tp + lane * 16;
-    uint32_t bits = pos < size ? nl16_at(g, pos, size) : 0u;
-    const uint32_t c = __popc(bits);
-    uint32_t incl = c;
-#pragma unroll
-    for (int k = 1; k < 32; k <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, k);
-      if (lane >= k) incl += t;
-    }
-    unsigned long long idx = at + incl - c;
-    while (bits) { d.line_end[idx++] = pos + (__ffs(bits) - 1); bits &= bits - 1; }
-    at += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lane == 0 && size && __ldg(g + size - 1) != '\n') d.line_end[at] = size;
-}
-
-__global__ void k_hash_lines(DiffSide d, int32_t n, unsigned long long total) {
-  __shared__ uint32_t lut[256];                          // the automaton table
-  const bool want_flags = d.line_flag != nullptr;
-  if (want_flags) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_lut[i];
-    __syncthreads();
-  }
-  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  // file of line i: binary search in line_base
-  int lo = 0, hi = n;                                   // line_base[lo] <= i < line_base[hi]
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (d.line_base[mid] <= i) lo = mid; else hi = mid; }
-  const int f = lo;
-  const uint8_t* g = d.arena + (uint32_t)d.off[f];
-  const uint32_t e = d.line_end[i];
-  const uint32_t s = (i == d.line_base[f]) ? 0u : d.line_end[i - 1] + 1u;
-  LineState L;
-  line_init(L, s, e);
-  if (want_flags) {
-    const int ext = d.ext ? d.ext[f] : 0;
-    while (L.pos < L.e) line_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)), lut, A_FIRST);
-    d.line_flag[i] = (ext != 0 && (L.A & (AF_ASSERT | AF_EXPECT))) ? 1 : 0;
-  } else {
-    while (L.pos < L.e) hash_block(L, __ldg(reinterpret_cast<const unsigned long long*>(g + L.pos)));
-  }
-  Accum ac{0, 0, 0, 0, 0};
-  line_finish(s, e, 0u, L.B, 0, GmemByte{g}, ac);       // ext 0: hash only; digest of one line = its hash
-  d.line_hash[i] = ac.digest;
-}
-
 // Edit distance D (insertions + deletions) of hash sequences a[0..n) and b[0..m); one warp per pair.
 // V (furthest x per diagonal) lives in global scratch of 2*(n+m)+3 ints per pair.
 __global__ void k_myers(const unsigned long long* ha, const unsigned long long* la, const unsigned long long* hb,
@@ -162,9 +88,10 @@ __global__ void k_myers(const unsigned long long* ha, const unsigned long long* 
 __global__ void k_myers_trace(const unsigned long long* ha, const unsigned long long* la, const uint8_t* fa,
                               const unsigned long long* hb, const unsigned long long* lb, const uint8_t* fb,
                               int32_t pair0, int32_t n_pairs, int32_t* trace, const unsigned long long* trace_base,
-                              tsm_diff_detail* detail) {
+                              const long long* added, const long long* removed, long long max_d, tsm_diff_detail* detail) {
   const int pr = pair0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (pr >= pair0 + n_pairs) return;
+  if (added[pr] + removed[pr] > max_d) return;             // too far apart to keep the rows of V: the host reports one hunk
   const unsigned long long* a = ha + la[pr];
   const unsigned long long* b = hb + lb[pr];
   const uint8_t* qa = fa + la[pr];

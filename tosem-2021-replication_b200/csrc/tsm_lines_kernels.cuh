@@ -1,7 +1,7 @@
 // tsm_lines_kernels.cuh - S9 line records in file order (docs/SPEC.md section 3): the small kernels around
-// k_scan2's TSM_SCAN_LINE_HASHES output.
+// k_scan's TSM_SCAN_LINE_HASHES output.
 //
-// k_scan2 hands out work units in any order, so a chunk cannot know the index of its first line.  Instead every
+// k_scan hands out work units in any order, so a chunk cannot know the index of its first line.  Instead every
 // chunk writes the records of its own lines, in order, into one region of the staging arrays and notes where
 // (unit_out) and how many (unit_lines).  With the unit table in (file, chunk) order - the deterministic plan below -
 // one exclusive scan of unit_lines gives every unit's first line index, and one gather puts the records in place.

@@ -1,11 +1,7 @@
-// tsm_scan_kernels.cuh - hand-written sm_100a kernels of the corpus scan (docs/SPEC.md).
+// tsm_scan_kernels.cuh - hand-written sm_100a kernels of the corpus scan (docs/SPEC.md), part 1:
 //
 //   k_plan      files -> (file, 4 KiB chunk) work units                         [tiny]
-//   k_scan      THE hot kernel: every source byte is read from HBM exactly once.  One warp per
-//               work unit, chunk staged global->shared by a 1-D TMA bulk copy (cp.async.bulk +
-//               mbarrier), pass 1 = SWAR newline table, pass 2 = lane-per-stripe Shift-And
-//               automaton + Mersenne-61 running prefix, pass 3 = lane-per-line finalise, then
-//               per-file counters, digest and the candidate (assertion-line) list.
+//   (k_scan     the hot kernel: tsm_scan_walk.cuh; this file holds the line helpers it shares with the slow path)
 //   k_classify  one thread per candidate: statement, last identifier, category (S5), events, the
 //               cross-file aggregate into a shared-memory privatised [group][category] table, and
 //               the totals of the per-file records.
@@ -18,7 +14,7 @@
 
 namespace tsm {
 
-__constant__ uint32_t c_lut[256];                       // automaton byte classes (one table, tsm_device.cuh)
+__constant__ uint32_t c_lut[256];                       // automaton table (tsm_device.cuh; built by tsm_create)
 __constant__ uint32_t c_elut[256];                      // bare-assert operator automaton (k_classify)
 // category tables: read once per block of k_classify into shared memory (coalesced, hence plain device memory)
 __device__ uint8_t c_cat_slot[TSM_CAT_SLOTS];            // perfect hash slot -> category id
@@ -53,26 +49,14 @@ __global__ void k_plan(ScanParams p) {
   }
 }
 
-// ================================================================================= k_scan
-// Work unit = (file, 4 KiB chunk).  Per warp, per unit:
-//   stage   one 1-D TMA bulk copy (cp.async.bulk + mbarrier) of [chunk-16, chunk+4096+240) into shared
-//   pass 1  SWAR newline bits, one 136-byte stripe per lane; one warp scan orders them into the line table
-//   pass 2  stripe walk (all lanes busy whatever the line lengths): Shift-And automaton (one LDS per
-//           byte), pattern ends -> per-line flag words, Mersenne-61 running prefix (checkpoint every 4 words)
-//   pass 2b words with a newline AND a pattern end, byte by byte, one lane per word
-//   pass 3  balanced finalise, one lane per line: hash = difference of two prefixes, header / assertion flags
-//   pass 4  ballot compaction of candidate (and header-event) lines into the global lists
-// SWAR: 16-bit mask of the bytes equal to '\n' in a 16-byte vector.
+// ================================================================================= line helpers (k_scan, its slow path)
+// SWAR: 4-bit mask of the bytes equal to '\n' in a 32-bit word.
 __device__ __forceinline__ uint32_t nl_word(uint32_t w) {
   const uint32_t y = w ^ 0x0A0A0A0Au;
   const uint32_t t = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
   const uint32_t z = ~(t | y | 0x7F7F7F7Fu);            // 0x80 in every byte that was '\n'
   return (z * 0x00204081u) >> 28;                        // gather the four flag bits: 7+21, 15+14, 23+7, 31+0 -> 28..31
 }
-__device__ __forceinline__ uint32_t nl16(const uint4& v) {
-  return nl_word(v.x) | (nl_word(v.y) << 4) | (nl_word(v.z) << 8) | (nl_word(v.w) << 12);
-}
-
 // Per-lane state of the line currently walked by this lane.
 struct LineState {
   uint32_t s, e;            // [s, e) = line
@@ -112,21 +96,6 @@ __device__ __forceinline__ void line_block(LineState& L, unsigned long long w, c
     L.D = D; L.A = A;
   }
   // B = B * 2^-64 + w  (2^-64 = 2^-3 = 2^58 mod 2^61-1: a rotation by 3 to the right)
-  const unsigned long long b = L.B;
-  const unsigned long long rot = (b >> 3) | ((b & 7ull) << 58);
-  L.B = fold61(fold61(rot + fold61(w)));
-  L.pos = pos + 8;
-}
-
-// Hash-only variant (S8 line hashes): same masking and Horner step, no automaton.
-__device__ __forceinline__ void hash_block(LineState& L, unsigned long long w) {
-  const uint32_t pos = L.pos;
-  if (pos < L.s || pos + 8 > L.e) {
-    unsigned long long m = ~0ull;
-    if (pos < L.s) m <<= 8u * (L.s - pos);
-    if (pos + 8 > L.e) m &= ~0ull >> (8u * (pos + 8 - L.e));
-    w &= m;
-  }
   const unsigned long long b = L.B;
   const unsigned long long rot = (b >> 3) | ((b & 7ull) << 58);
   L.B = fold61(fold61(rot + fold61(w)));
@@ -185,7 +154,7 @@ __device__ __forceinline__ uint32_t flag_nibble(uint32_t A, uint32_t g1, uint32_
   return ((A & (AF_ASSERT | AF_EXPECT)) ? 1u : 0u) | ((A & g1) ? 2u : 0u) | ((A & g2) ? 4u : 0u) | ((A & g3) ? 8u : 0u);
 }
 __device__ __forceinline__ uint32_t flag_nibble_ext(uint32_t A, int ext) {
-  return ext == TSM_EXT_PY ? flag_nibble(A, PY_G1, PY_G2, A_STF) : flag_nibble(A, CJ_G1, CJ_G2, A_STF);
+  return ext == TSM_EXT_PY ? flag_nibble(A, PY_G1, PY_G2, 0u) : flag_nibble(A, CJ_G1, CJ_G2, 0u);
 }
 
 // Finish one line: h0 = Mersenne-61 value of its bytes (SPEC section 3, trailing CR still inside), nib = its
@@ -247,224 +216,6 @@ __device__ __forceinline__ const uint32_t* scan_lut() {
   return reinterpret_cast<const uint32_t*>(smem);
 }
 
-// Eight automaton steps over one 8-byte word; A collects every state of the word.
-__device__ __forceinline__ void step8(unsigned long long w, uint32_t& D, uint32_t& A) {
-  const uint32_t* lut = scan_lut();
-  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | A_FIRST) & lut[__byte_perm(lo, 0, 0x4440 + k)];
-    A |= D;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | A_FIRST) & lut[__byte_perm(hi, 0, 0x4440 + k)];
-    A |= D;
-  }
-}
-
-// OR automaton states into the window's per-line flag words (lines outside the window: dropped).
-__device__ __forceinline__ void flag_or(uint8_t* wb, uint32_t rel, uint32_t A) {
-  if (rel < FLAG_CAP) atomicOr(reinterpret_cast<uint32_t*>(wb + OFF_FLAGS) + rel, A);
-}
-
-// Pass 2b: a word that holds both a pattern end and a newline - walk its bytes one at a time so that
-// every match lands on its own line.  entry = word index | line index at the word's first byte << 10.
-// The automaton state in front of the word follows from the eight bytes before it (no pattern is longer).
-__device__ __noinline__ void resolve_word(uint8_t* wb, uint32_t fin, uint32_t wlo, uint32_t entry) {
-  const uint32_t k = entry & 1023u, pos = 8u * k;
-  uint32_t idx = (entry >> 10) - wlo;
-  const uint32_t l = k / 17u, i = k - 17u * l;
-  uint32_t nl8 = (reinterpret_cast<const uint32_t*>(wb + OFF_MSK)[(i >> 2) * 32u + l] >> (8u * (i & 3u))) & 0xFFu;
-  uint32_t D = 0, A = 0;
-  if (pos > PRE) step8(*reinterpret_cast<const unsigned long long*>(wb + pos - 8), D, A);
-  unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + pos);
-  const uint32_t* lut = scan_lut();
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    D = ((D + D) | A_FIRST) & lut[(uint32_t)w & 0xFFu];
-    if (D & fin) flag_or(wb, idx, D);
-    idx += nl8 & 1u;
-    nl8 >>= 1;
-    w >>= 8;
-  }
-}
-
-// Pass 2: every lane walks the 17 words of its own 136-byte stripe (all 32 lanes busy for the whole
-// pass, whatever the line lengths are; the bytes outside the chunk's staged range are zeros):
-//   automaton   8 steps per word; the OR of the word's states goes to the flag word of the line the
-//               word lies in (its index follows from the stripe's newline bits); a word with a
-//               newline AND a pattern end goes to the pass-2b queue instead
-//   hash        R_k = R_{k-1} * 2^-64 + w_k (mod 2^61-1) is stored behind every word: pass 3 gets the
-//               Mersenne value of any byte range as a difference of two such prefixes
-// then one warp scan turns the stripe totals into the absolute prefix at every stripe start.
-// Not inlined on purpose: the hot loop gets its own register allocation.
-__device__ __noinline__ void walk_stripes(uint8_t* wb, uint32_t fin, uint32_t wlo, uint32_t base_all, int lane) {
-  const uint32_t pos0 = (uint32_t)lane * STRIPE;
-  uint8_t* sp = wb + pos0;
-  const uint32_t* msk = reinterpret_cast<const uint32_t*>(wb + OFF_MSK) + lane;
-  uint32_t* flags = reinterpret_cast<uint32_t*>(wb + OFF_FLAGS);
-  unsigned long long* rw = reinterpret_cast<unsigned long long*>(wb + OFF_RW) + (uint32_t)lane * RW_PER_STRIPE;
-  uint32_t D = 0;
-  if (lane) {                                            // state in front of the stripe
-    uint32_t A = 0;
-    step8(*reinterpret_cast<const unsigned long long*>(sp - 8), D, A);
-  }
-  unsigned long long R = 0;
-  uint32_t idxg = base_all - wlo;                        // window-relative line index at the group's first byte
-#pragma unroll 1
-  for (uint32_t g = 0; g < 5; ++g) {
-    const uint32_t mg = msk[g * 32u];
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k) {
-      if (g == 4 && k) break;
-      const uint32_t off = 32u * g + 8u * k;
-      const unsigned long long w = *reinterpret_cast<const unsigned long long*>(sp + off);
-      uint32_t A = 0;
-      step8(w, D, A);
-      R = (R >> 3) + ((R & 7ull) << 58) + fold61(w);      // lazily reduced: stays below 2^63
-      if ((k & (RW_STRIDE - 1u)) == RW_STRIDE - 1u && g < 4)   // checkpoint behind every RW_STRIDE-th word (not the 17th)
-        rw[(4u * g + k) >> RW_SHIFT] = R;
-      const uint32_t nl8 = (mg >> (8u * k)) & 0xFFu;
-      const uint32_t idx = idxg + __popc(mg & ((1u << (8u * k)) - 1u));
-      atomicOr(flags + min(idx, FLAG_CAP - 1u), nl8 ? 0u : A);            // entry FLAG_CAP-1 is never a line
-      if (nl8 && (A & fin)) {
-        const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(wb + OFF_CTL), 1u);
-        const uint32_t entry = ((pos0 + off) >> 3) | ((idx + wlo) << 10);
-        if (slot < Q_CAP) reinterpret_cast<uint32_t*>(wb + OFF_Q)[slot] = entry;
-        else resolve_word(wb, fin, wlo, entry);
-      }
-    }
-    idxg += __popc(mg);
-  }
-  // stripe totals (frame of the stripe's last word) -> absolute frame -> exclusive scan
-  unsigned long long incl = rotl61(canon61(R), (3u * (17u * (uint32_t)lane + 16u)) % 61u);
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl = fold61(incl + t);
-  }
-  unsigned long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) excl = 0;
-  unsigned long long* sbase = reinterpret_cast<unsigned long long*>(wb + OFF_BASE);
-  sbase[lane] = excl;
-  if (lane == 31) sbase[32] = incl;
-  __syncwarp();
-  const uint32_t nq = min(*reinterpret_cast<const uint32_t*>(wb + OFF_CTL), Q_CAP);
-  for (uint32_t t = (uint32_t)lane; t < nq; t += 32)
-    resolve_word(wb, fin, wlo, reinterpret_cast<const uint32_t*>(wb + OFF_Q)[t]);
-  __syncwarp();
-}
-
-// Mersenne-61 value of the staged bytes [0, x), every byte weighted 256^position; lazily reduced (< 2^62 + 2).
-// x = 8k + b, r3k = 3k mod 61.  Starts from the last checkpoint in front of word k and folds the words between.
-__device__ __forceinline__ unsigned long long prefix_at(const uint8_t* wb, uint32_t k, uint32_t b, uint32_t r3k) {
-  const uint32_t l = k / 17u, i = k - 17u * l, c0 = i >> RW_SHIFT;
-  unsigned long long R = 0;                              // prefix inside the stripe behind word k-1, frame of word k-1
-  if (c0) R = *reinterpret_cast<const unsigned long long*>(wb + OFF_RW + 8u * (l * RW_PER_STRIPE + c0 - 1u));
-#pragma unroll 1
-  for (uint32_t t = c0 << RW_SHIFT; t < i; ++t)          // at most RW_STRIDE - 1 words
-    R = (R >> 3) + ((R & 7ull) << 58) + fold61(*reinterpret_cast<const unsigned long long*>(wb + 8u * (k - i + t)));
-  unsigned long long loc = (R >> 3) + ((R & 7ull) << 58);                // frame of word k
-  if (b) loc += *reinterpret_cast<const unsigned long long*>(wb + 8u * k) & ((1ull << (8u * b)) - 1ull);
-  return *reinterpret_cast<const unsigned long long*>(wb + OFF_BASE + 8u * l) + rotl61(fold61(fold61(loc)), r3k);
-}
-
-// Pass 3: balanced finalise, one lane per line: hash = difference of two prefixes, flags from the
-// line's flag word; the starts of the candidate lines are compacted (u16 each) over the flag words
-// already consumed.  Returns the number of candidates.
-__device__ __noinline__ uint32_t finish_lines(uint8_t* wb, const uint32_t* lc, uint32_t j0, uint32_t cnt, uint32_t ns,
-                                              int ext, int lane, Accum& ac) {
-  uint16_t* tab = reinterpret_cast<uint16_t*>(wb + OFF_TAB);
-  const uint32_t* flags = reinterpret_cast<const uint32_t*>(wb + OFF_FLAGS);
-  uint16_t* clist = reinterpret_cast<uint16_t*>(wb + OFF_FLAGS);
-  const uint32_t g1 = lc[1], g2 = lc[2], g3 = lc[3];
-  const SmemByte lb{wb};
-  Accum a = ac;
-  uint32_t nc = 0;
-  uint32_t cs = j0 ? ((uint32_t)tab[j0 - 1] & TAB_POS) + 1u : ns;       // start of the round's first line
-  unsigned long long cP = prefix_at(wb, cs >> 3, cs & 7u, (3u * (cs >> 3)) % 61u);   // ... and the prefix in front of it
-  for (uint32_t base = j0; base < cnt; base += 32) {                     // uniform trip count
-    const uint32_t j = base + (uint32_t)lane;
-    const bool valid = j < cnt;
-    const uint32_t e = valid ? (uint32_t)tab[j] & TAB_POS : 0u;
-    const uint32_t A = valid ? flags[j] : 0u;
-    const uint32_t k = e >> 3, b = e & 7u, r3k = (3u * k) % 61u;
-    uint32_t r8e = r3k + 8u * b;                                         // (8 * e) mod 61
-    if (r8e >= 61u) r8e -= 61u;
-    const unsigned long long Pe = prefix_at(wb, k, b, r3k);
-    const unsigned long long Pn = Pe + rotl61(0x0Aull, r8e);             // prefix behind the terminator (< 2^63 - 4)
-    uint32_t s = __shfl_up_sync(0xffffffffu, e, 1) + 1u;
-    unsigned long long Ps = __shfl_up_sync(0xffffffffu, Pn, 1);
-    if (lane == 0) { s = cs; Ps = cP; }
-    cs = __shfl_sync(0xffffffffu, e, 31) + 1u;
-    cP = __shfl_sync(0xffffffffu, Pn, 31);
-    uint32_t fl = 0;
-    if (valid) {
-      const unsigned long long hr = canon61(Pe + 4ull * M61 - Ps);       // bytes [s, e), weighted from position 0
-      const unsigned long long h0 = rotl61(hr, (61u - (8u * s) % 61u) % 61u);
-      fl = line_finish_h(s, e, h0, flag_nibble(A, g1, g2, g3), ext, lb, a);
-      tab[j] = (uint16_t)(e | (fl << 13));               // flags ride in the 3 spare bits of the entry
-    }
-    __syncwarp();                                        // every flag word of the round is read: the list may grow over them
-    const uint32_t mc = __ballot_sync(0xffffffffu, fl & LF_CAND);
-    if (fl & LF_CAND) clist[nc + __popc(mc & ((1u << lane) - 1u))] = (uint16_t)s;
-    nc += __popc(mc);
-  }
-  ac = a;
-  __syncwarp();
-  return nc;
-}
-
-// Passes 3-4 over the current line table: lines j in [j0, cnt), line j = [start_j, tab[j]).
-__device__ __forceinline__ void drain(const ScanParams& p, uint8_t* wb, const uint32_t* lc, uint32_t cnt,
-                                      bool& skip_first, uint32_t& next_start, uint32_t f, uint32_t cb, int ext, int lane,
-                                      Accum& ac) {
-  __syncwarp();
-  if (cnt == 0) return;
-  const uint16_t* tab = reinterpret_cast<const uint16_t*>(wb + OFF_TAB);
-  const uint32_t j0 = skip_first ? 1u : 0u;
-  const uint32_t ns = next_start;
-  const uint32_t nc = finish_lines(wb, lc, j0, cnt, ns, ext, lane, ac);   // pass 3
-  // ---- pass 4: candidates (always) and header events (on request) to their global lists
-  if (nc) {
-    const uint16_t* clist = reinterpret_cast<const uint16_t*>(wb + OFF_FLAGS);
-    const uint32_t cbase = warp_reserve(&p.ctrl->n_cand, nc, lane);
-    for (uint32_t i = (uint32_t)lane; i < nc; i += 32) {
-      const uint32_t slot = cbase + i;
-      if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | (cb + (uint32_t)clist[i] - PRE);
-      else p.ctrl->overflow = 1;
-    }
-  }
-  if ((p.flags & TSM_SCAN_HEADER_EVENTS) && ext != 0) {
-    uint32_t nh = 0;
-    for (uint32_t b = j0; b < cnt; b += 32) {
-      const uint32_t j = b + lane;
-      const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
-      nh += __popc(__ballot_sync(0xffffffffu, fb & LF_HDR));
-    }
-    if (nh) {
-      uint32_t hbase = warp_reserve(&p.ctrl->n_hev, nh, lane);
-      for (uint32_t b = j0; b < cnt; b += 32) {
-        const uint32_t j = b + lane;
-        const uint32_t fb = j < cnt ? (uint32_t)tab[j] >> 13 : 0u;
-        uint32_t s = 0, e = 0;
-        if (j < cnt) { s = j ? ((uint32_t)tab[j - 1] & TAB_POS) + 1u : ns; e = (uint32_t)tab[j] & TAB_POS; }
-        const uint32_t mh = __ballot_sync(0xffffffffu, fb & LF_HDR);
-        if (fb & LF_HDR) {
-          const uint32_t slot = hbase + __popc(mh & ((1u << lane) - 1u));
-          if (slot < p.hev_cap) p.hev[slot] = tsm_header_event{f, cb + s - PRE, e - s, (fb >> 2) & 1u};
-          else p.ctrl->overflow = 1;
-        }
-        hbase += __popc(mh);
-      }
-    }
-  }
-  next_start = ((uint32_t)tab[cnt - 1] & TAB_POS) + 1u;
-  skip_first = false;
-  __syncwarp();
-}
-
 // Slow path: a line that starts in this chunk but ends behind the staged bytes.  Walked by lane 0
 // straight from HBM (correct for any length; lines longer than 240 B past a chunk edge are rare).
 __device__ __noinline__ uint32_t long_line(const ScanParams& p, const uint32_t* lut, uint32_t first, uint32_t f,
@@ -494,129 +245,6 @@ __device__ __noinline__ uint32_t long_line(const ScanParams& p, const uint32_t* 
   return e;                                              // file-relative end of the line
 }
 
-__device__ __forceinline__ void process_chunk(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t f,
-                                              uint32_t cb, uint32_t fo, uint32_t size, int ext, int lane) {
-  const uint8_t* buf = wb;
-  uint16_t* tab = reinterpret_cast<uint16_t*>(wb + OFF_TAB);
-  const uint32_t ce = min(cb + CH, size);
-  const uint32_t le = min(ce + EXT, size);
-  const uint32_t lim = PRE + (ce - cb);                  // buffer position just past the owned bytes
-  const uint32_t lim2 = PRE + (le - cb);                 // ... past the staged bytes
-  bool skip_first = (cb != 0) && (buf[PRE - 1] != '\n'); // chunk starts inside a foreign line
-  uint32_t next_start = PRE;
-  Accum ac{0, 0, 0, 0, 0};
-  uint32_t cnt = 0;
-  __syncwarp();
-  // ---- everything outside the staged range [PRE, lim2) becomes zeros: no pass has to mask its loads
-  //      (a zero byte is no newline, matches no pattern and adds nothing to the hash prefix)
-  if (lane < 2) reinterpret_cast<unsigned long long*>(wb)[lane] = 0ull;
-  {
-    const uint32_t za = (lim2 + 7u) & ~7u;
-    if ((uint32_t)lane < za - lim2) wb[lim2 + lane] = 0;
-    for (uint32_t q = za + 8u * (uint32_t)lane; q < BUF; q += 256u) *reinterpret_cast<unsigned long long*>(wb + q) = 0ull;
-  }
-  __syncwarp();
-  // ---- pass 1: every lane takes one 136-byte stripe of the 4 352 staged bytes (17 conflict-free
-  //      LDS.64) and keeps the newline positions of its stripe as a 136-bit mask in registers;
-  //      one warp scan then orders them into the u16 line table, NL_CAP entries per window
-  const uint32_t pos0 = (uint32_t)lane * STRIPE;
-  uint32_t* msk = reinterpret_cast<uint32_t*>(wb + OFF_MSK) + lane;       // msk[g * 32]: newline bits of the stripe's bytes [32g, 32g+32)
-  uint32_t own[5], extm[5];                              // newlines at positions [PRE, lim) / [lim, lim2)
-  {
-    uint32_t m[5] = {0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int i = 0; i < 17; ++i) {
-      const uint2 w = *reinterpret_cast<const uint2*>(buf + pos0 + 8u * (uint32_t)i);
-      m[i >> 2] |= (nl_word(w.x) | (nl_word(w.y) << 4)) << (8 * (i & 3));
-    }
-    const uint32_t rel = lim > pos0 ? lim - pos0 : 0u;   // owned bytes of this stripe (may exceed 136)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const uint32_t below = rel >= 32u * (j + 1) ? 0xFFFFFFFFu : (rel <= 32u * j ? 0u : (1u << (rel - 32u * j)) - 1u);
-      own[j] = m[j] & below;
-      extm[j] = m[j] & ~below;
-      msk[j * 32] = m[j];                                // pass 2 reads them back
-    }
-  }
-  const uint32_t mine = __popc(own[0]) + __popc(own[1]) + __popc(own[2]) + __popc(own[3]) + __popc(own[4]);
-  const uint32_t mine_ext = __popc(extm[0]) + __popc(extm[1]) + __popc(extm[2]) + __popc(extm[3]) + __popc(extm[4]);
-  uint32_t incl = mine | (mine_ext << 16);               // both counts in one scan (each < 2^13)
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31) & 0xFFFFu;
-  const uint32_t base_idx = (incl & 0xFFFFu) - mine;
-  const uint32_t base_all = base_idx + (incl >> 16) - mine_ext;          // newlines (of either kind) in front of the stripe
-  uint32_t ext_first = 0xFFFFu;                          // first newline behind the owned bytes
-#pragma unroll
-  for (int j = 4; j >= 0; --j)
-    if (extm[j]) ext_first = pos0 + 32u * (uint32_t)j + (uint32_t)(__ffs(extm[j]) - 1);
-  ext_first = __reduce_min_sync(0xffffffffu, ext_first);
-  for (uint32_t wstart = 0;; wstart += NL_CAP) {
-    cnt = min(total - wstart, NL_CAP);
-    uint32_t idx = base_idx - wstart;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      uint32_t b = own[j];
-      while (b) {
-        if (idx < cnt) tab[idx] = (uint16_t)(pos0 + 32u * (uint32_t)j + (uint32_t)(__ffs(b) - 1));
-        ++idx;
-        b &= b - 1;
-      }
-    }
-    for (uint32_t i = (uint32_t)lane; i < cnt + 2u; i += 32) reinterpret_cast<uint32_t*>(wb + OFF_FLAGS)[i] = 0u;
-    if (lane == 0) *reinterpret_cast<uint32_t*>(wb + OFF_CTL) = 0u;
-    __syncwarp();
-    walk_stripes(wb, lc[0], wstart, base_all, lane);         // pass 2 (the window's flag words)
-    if (wstart + cnt >= total) break;                    // last window: the tail line joins it below
-    drain(p, wb, lc, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-  }
-  // ---- the last owned line: starts in the chunk, may end behind it (its line index = total)
-  const uint32_t tail_start = cnt ? ((uint32_t)tab[cnt - 1] & TAB_POS) + 1u : next_start;
-  const bool owned = !(skip_first && cnt == 0);
-  bool have_tail = false, tail_long = false;
-  uint32_t tail_end = 0;
-  if (owned && tail_start < lim) {
-    if (ce == size) { tail_end = lim; have_tail = true; }              // unterminated last line of the file
-    else if (ext_first != 0xFFFFu) { tail_end = ext_first; have_tail = true; }
-    else if (le == size) { tail_end = lim2; have_tail = true; }        // file ends inside the staged bytes
-    else tail_long = true;
-  }
-  if (have_tail) {                                       // the table has room for NL_CAP + 1 entries
-    if (lane == 0) tab[cnt] = (uint16_t)tail_end;
-    ++cnt;
-  }
-  drain(p, wb, lc, cnt, skip_first, next_start, f, cb, ext, lane, ac);
-  if (tail_long && lane == 0) long_line(p, scan_lut(), A_FIRST, f, fo, size, ext, cb + tail_start - PRE, ac);
-  // ---- per-file counters: warp reduce (the digest as three partial sums: low halves keep their carries),
-  //      then one store (single-chunk file) or one atomic per counter
-  ac.lines = __reduce_add_sync(0xffffffffu, ac.lines);
-  ac.asserts = __reduce_add_sync(0xffffffffu, ac.asserts);
-  ac.hdrs = __reduce_add_sync(0xffffffffu, ac.hdrs);
-  ac.fixes = __reduce_add_sync(0xffffffffu, ac.fixes);
-  {
-    const uint32_t dlo = (uint32_t)ac.digest, dhi = (uint32_t)(ac.digest >> 32);
-    const unsigned long long s0 = __reduce_add_sync(0xffffffffu, dlo & 0xFFFFu);
-    const unsigned long long s1 = __reduce_add_sync(0xffffffffu, dlo >> 16);
-    const unsigned long long s2 = __reduce_add_sync(0xffffffffu, dhi);
-    ac.digest = s0 + (s1 << 16) + (s2 << 32);
-  }
-  if (lane == 0) {
-    tsm_file_stat* st = p.stats + f;
-    if (size <= CH) {                                    // sole owner of the record: plain store
-      *st = tsm_file_stat{ac.lines, ac.asserts, ac.hdrs, ac.fixes, ac.digest};
-    } else {
-      if (ac.lines) atomicAdd(&st->n_lines, ac.lines);
-      if (ac.asserts) atomicAdd(&st->n_assert, ac.asserts);
-      if (ac.hdrs) atomicAdd(&st->n_headers, ac.hdrs);
-      if (ac.fixes) atomicAdd(&st->n_fixture, ac.fixes);
-      if (ac.digest) atomicAdd(reinterpret_cast<unsigned long long*>(&st->digest), ac.digest);
-    }
-  }
-}
-
 // Stage the bytes [max(cb-16,0), min(cb+CH+EXT, size)) of a file so that file byte cb sits at buf+PRE.
 __device__ __forceinline__ void issue_load(const ScanParams& p, uint8_t* buf, uint64_t* bar, uint32_t fo,
                                            uint32_t size, uint32_t cb) {
@@ -643,47 +271,6 @@ __device__ __forceinline__ Unit claim_unit(const ScanParams& p, uint32_t n_units
     x.ext = p.ext[x.f];
   }
   return x;
-}
-
-__global__ void __launch_bounds__(SCAN_WARPS * 32, SCAN_CTAS_PER_SM) k_scan(ScanParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) the automaton table, then 3 x 4 per-language masks
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[i] = c_lut[i];
-  if (threadIdx.x < 12) {                                // per language (PY, C family, none): all pattern ends that count, then the header groups
-    const int t = threadIdx.x, lang = t >> 2, q = t & 3;
-    const uint32_t g1 = lang == 0 ? PY_G1 : CJ_G1, g2 = lang == 0 ? PY_G2 : CJ_G2;
-    const uint32_t v = q == 0 ? (AF_ASSERT | AF_EXPECT | g1 | g2 | A_STF) : (q == 1 ? g1 : (q == 2 ? g2 : A_STF));
-    lut_all[256 + t] = lang == 2 ? 0u : v;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* wb = smem + LUT_BYTES + warp * WARP_SMEM;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wb + OFF_CTL + 8);
-  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  __syncwarp();
-  const uint32_t n_units = p.slab->n_units;
-  uint32_t phase = 0;
-  Unit cur = claim_unit(p, n_units, lane);
-#if TSM_LOCKSTEP
-  // the warps of a CTA start every chunk together: they then run the same pass at about the same time and
-  // share its instructions in the SM's instruction caches (the hot code is larger than the 32 KB L1.5;
-  // measured -6 % kernel time, profiles/README.md)
-  while (__syncthreads_or(cur.u < n_units)) {
-    if (cur.u >= n_units) continue;
-#else
-  while (cur.u < n_units) {
-#endif
-    fence_proxy_async();                                 // this warp's zero fill and reads of the last chunk come first
-    __syncwarp();
-    if (lane == 0) issue_load(p, wb, bar, cur.fo, cur.size, cur.cb);
-    const Unit nxt = claim_unit(p, n_units, lane);       // metadata of the next unit arrives during this chunk
-    while (!mbar_try_wait(bar, phase)) {}
-    phase ^= 1;
-    const uint32_t lang = cur.ext == 0 ? 2u : (cur.ext == TSM_EXT_PY ? 0u : 1u);
-    process_chunk(p, lut_all + 256u + 4u * lang, wb, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
-    __syncwarp();
-    cur = nxt;
-  }
 }
 
 // ================================================================================= k_classify

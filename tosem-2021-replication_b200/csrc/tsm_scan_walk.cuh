@@ -1,34 +1,27 @@
-// tsm_scan2_kernels.cuh - k_scan, second generation (round 2): the "streaming stripe walk".
+// tsm_scan_walk.cuh - k_scan, THE hot kernel of the corpus scan (docs/SPEC.md sections 2-5, 7): one warp
+// per (file, 4 KiB chunk) work unit, the chunk staged global -> shared by one 1-D TMA bulk copy (cp.async.bulk + mbarrier),
+// every source byte read from HBM exactly once.  Per chunk:
 //
-// Same contract as the first k_scan (docs/SPEC.md sections 2-5, 7): one warp per
-// (file, 4 KiB chunk) work unit, chunk staged global -> shared by one 1-D TMA bulk copy, every source byte
-// read from HBM exactly once.  What changed is how the per-line facts are produced:
+//   walk     every lane takes the 17 words of its own 136-byte stripe (all 32 lanes busy whatever the line lengths are):
+//            multi-pattern Shift-And automaton, one LUT lookup per byte.  '\n' is one of its patterns (state bit 31), so the
+//            OR of a word's eight states says for free whether the word holds a newline: there is no newline pass over every
+//            byte.  The OR of the states since the last newline word stays in a REGISTER and is stored in front of every word
+//            (one STS); the Mersenne-61 running hash prefix is checkpointed every 4 words;
+//   mixed    a word that holds a newline AND a pattern end (a few per chunk) is re-walked byte by byte by a dense pass that
+//            splits its states between the line that ends in it and the line that starts;
+//   records  only the words that hold a newline (~ 1 in 5) are looked at again: a dense pass (one lane per such word, SWAR
+//            for the newline bytes) turns them into one 16-bit record per LINE;
+//   finish   one line per lane, no inner loops: one hash prefix per line (the one behind its newline; the one in front of
+//            the line is the neighbour lane's), pattern flags from the word's stored OR, per-file counters, the candidate
+//            (assertion line) list for k_classify; with TSM_SCAN_LINE_HASHES the line's record (hash, end, flag) as well.
 //
-//   * '\n' is one more pattern of the Shift-And automaton (state bit 31), so the OR of a word's eight
-//     states says for free whether the word holds a newline: no SWAR newline pass over every byte;
-//   * the walk keeps the OR of the states since the last newline word in a REGISTER and stores it in front
-//     of every word (one STS): no per-word shared-memory atomicOr, no per-word line index arithmetic;
-//   * only the words that hold a newline (~ 1 in 5) are looked at again: a dense pass turns them into one
-//     16-bit record per LINE, and the finish pass takes one line per lane with no inner loops: one hash
-//     prefix per line (the prefix behind its newline; the one in front of the line is the neighbour lane's);
-//   * a word that holds a newline AND a pattern end ("mixed", a few per chunk) is re-walked byte by byte
-//     by a dense pass that splits its states between the line that ends in it and the line that starts;
-//   * table addresses are formed by IMAD (FMA pipe) instead of LEA (ALU pipe): the kernel is bound by the ALU
-//     pipe, the FMA pipe is mostly idle (profiles/).
-//
-// The hash prefix machinery (Mersenne-61 running prefix, checkpoints, warp scan of the stripe totals) is
-// the first generation's.  There is no reference kernel; rules cite docs/SPEC.md.
+// Table addresses are formed by IMAD (FMA pipe) instead of LEA (ALU pipe), and the walk is one rolled loop: the kernel is
+// latency / issue bound and sensitive to its instruction-cache footprint (profiles/r2_variants.txt).
+// There is no reference kernel: the reference ships data only.  Rules cite docs/SPEC.md.
 #pragma once
 #include "tsm_scan_kernels.cuh"
 
 namespace tsm {
-
-__constant__ uint32_t c_lut2[256];                       // automaton table of this kernel (bit 30 = 'F', bit 31 = '\n')
-
-// Pattern layout: the first generation's (tsm_device.cuh), with the `_F` gate reduced to one bit ('F' occurs in
-// the line) and the newline bit.
-constexpr uint32_t B_FIRST = (1u << 0) | (1u << 6) | (1u << 13) | (1u << 18) | (1u << 21) | (1u << 25) | (1u << 29) | (1u << 30) | (1u << 31);
-constexpr uint32_t B_F = 1u << 30;                       // gate of the TEST_F check
 
 #ifndef TSM_SCAN2_WARPS
 #define TSM_SCAN2_WARPS 11
@@ -515,10 +508,10 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   }
 }
 
-__global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan2(ScanParams p) {
+__global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) the automaton table, then 3 x 4 per-language masks, the opaque 4
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[i] = c_lut2[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[i] = c_lut[i];
   if (threadIdx.x < 12) {                                // per language (PY, C family, none): pattern ends that count, then the header groups
     const int t = threadIdx.x, lang = t >> 2, q = t & 3;
     const uint32_t g1 = lang == 0 ? PY_G1 : CJ_G1, g2 = lang == 0 ? PY_G2 : CJ_G2;

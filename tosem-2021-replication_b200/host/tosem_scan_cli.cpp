@@ -34,6 +34,7 @@
 #include <fstream>
 #include <future>
 #include <map>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -183,34 +184,34 @@ static std::string method_string(int ext, const uint8_t* line, uint32_t len) {  
 }
 
 // ---------------------------------------------------------------------------------- scan
-struct Batch {                                             // one packed arena (<= ~1 GiB) of consecutive files
-  size_t first = 0, count = 0;
-  Batch() = default;
-  Batch(size_t f, size_t c) : first(f), count(c) {}
+struct Batch {                                             // one packed arena (<= ~1 GiB) of files of one GPU's share
+  std::vector<uint32_t> idx;                               // indices into the walk's file list, ascending
   std::vector<int32_t> off, len;
   std::vector<uint8_t> ext;
   std::vector<uint16_t> grp;
   uint8_t* arena = nullptr;
   int64_t bytes = 0;
+  size_t count() const { return idx.size(); }
 };
 
 static void load_batch(const std::vector<FileEntry>& files, Batch& b) {
-  b.len.resize(b.count); b.off.resize(b.count + 1); b.ext.resize(b.count); b.grp.resize(b.count);
-  for (size_t i = 0; i < b.count; ++i) {
-    const FileEntry& f = files[b.first + i];
+  const size_t n = b.count();
+  b.len.resize(n); b.off.resize(n + 1); b.ext.resize(n); b.grp.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const FileEntry& f = files[b.idx[i]];
     b.len[i] = (int32_t)f.size; b.ext[i] = (uint8_t)f.ext; b.grp[i] = (uint16_t)f.grp;
   }
-  b.bytes = tsm_layout(b.len.data(), (int32_t)b.count, b.off.data());
+  b.bytes = tsm_layout(b.len.data(), (int32_t)n, b.off.data());
   if (b.bytes < 0) die("batch does not fit an int32-indexed arena");
   b.arena = (uint8_t*)tsm_host_alloc(std::max<int64_t>(b.bytes, 128));
   if (!b.arena) die("pinned arena allocation failed (no CUDA device? there is no CPU fallback)");
   memset(b.arena, 0, (size_t)std::max<int64_t>(b.bytes, 128));
   // the reads of a batch run on a few host threads (a source tree is many small files: latency-bound)
-  const unsigned nt = std::max(1u, std::min({std::thread::hardware_concurrency(), 32u, (unsigned)((b.count + 63) / 64)}));
+  const unsigned nt = std::max(1u, std::min({std::thread::hardware_concurrency(), 32u, (unsigned)((n + 63) / 64)}));
   std::atomic<long> bad{-1};
   auto reader = [&](unsigned t) {
-    for (size_t i = t; i < b.count && bad.load(std::memory_order_relaxed) < 0; i += nt) {
-      const int fd = open(files[b.first + i].abs.c_str(), O_RDONLY);
+    for (size_t i = t; i < n && bad.load(std::memory_order_relaxed) < 0; i += nt) {
+      const int fd = open(files[b.idx[i]].abs.c_str(), O_RDONLY);
       int64_t got = 0;
       while (fd >= 0 && got < b.len[i]) {
         const ssize_t r = read(fd, b.arena + b.off[i] + got, (size_t)(b.len[i] - got));
@@ -225,15 +226,57 @@ static void load_batch(const std::vector<FileEntry>& files, Batch& b) {
   for (unsigned t = 1; t < nt; ++t) th.emplace_back(reader, t);
   reader(0);
   for (std::thread& x : th) x.join();
-  if (bad.load() >= 0) die("short read: " + files[b.first + (size_t)bad.load()].abs);
+  if (bad.load() >= 0) die("short read: " + files[b.idx[(size_t)bad.load()]].abs);
 }
 
-struct ScanOut {
-  std::vector<tsm_file_stat> stats;
-  std::vector<tsm_assert_event> aev;
-  std::vector<tsm_header_event> hev;
-  std::vector<int64_t> group_counts;
-};
+static void cu_ck(cudaError_t e, const char* what) { if (e != cudaSuccess) die(std::string(what) + ": " + cudaGetErrorString(e)); }
+static void nccl_ck(ncclResult_t r, const char* what) { if (r != ncclSuccess) die(std::string(what) + ": " + ncclGetErrorString(r)); }
+
+// The raw rows (fileName, extension, test_name, method, statement, counts, category: ML-Testing-v1.xlsx!apollo_tests:R1) and
+// the summary row (Id, FileName, total assert, assertion: Release-Meta-tpot.csv:1-2) of one file, from its events.
+static void render_file(const FileEntry& f, int64_t id, const uint8_t* base, int32_t size, uint32_t slot, const tsm_file_stat& st,
+                        const std::vector<tsm_assert_event>& aev, size_t& ai, const std::vector<tsm_header_event>& hev, size_t& hi,
+                        bool want_rows, bool want_sum, std::string& rows_txt, std::string& sum_txt) {
+  struct Row { int64_t hdr; std::string stmt; int cat; std::string catname; int64_t count; bool fixture; std::string method; };
+  std::vector<Row> rows;
+  std::map<std::pair<int64_t, std::string>, size_t> index;
+  std::map<std::string, int64_t> hist; std::vector<std::string> hist_order;
+  int64_t cur_hdr = -1; bool cur_fix = false; std::string cur_method = "xxxx";
+  while (ai < aev.size() && aev[ai].file == slot) {
+    const tsm_assert_event& ev = aev[ai++];
+    while (hi < hev.size() && hev[hi].file == slot && hev[hi].line_off <= ev.line_off) {   // governing header
+      const tsm_header_event& h = hev[hi++];
+      cur_hdr = h.line_off; cur_fix = (h.kind & 1u) != 0;
+      cur_method = method_string(f.ext, base + h.line_off, h.line_len);
+    }
+    // the statement may be longer than the 16-bit event field: re-derive its end on the host if saturated
+    uint32_t sl = ev.stmt_len;
+    if (sl == 65535) { const uint8_t* p = base + ev.stmt_off; uint32_t e = 0, last = 0; while (ev.stmt_off + e < (uint32_t)size && p[e] != '\n' && p[e] != '(') { if (!is_w(p[e])) last = e + 1; ++e; } sl = last; }
+    std::string stmt((const char*)base + ev.stmt_off, sl);
+    std::string cat = ev.cat == 127 ? std::string((const char*)base + ev.ident_off, ev.ident_len) : std::string(tsm_category_name(ev.cat));
+    auto key = std::make_pair(cur_hdr, stmt);
+    auto it = index.find(key);
+    if (it == index.end()) { index[key] = rows.size(); rows.push_back({cur_hdr, stmt, ev.cat, cat, 1, cur_fix, cur_method}); }
+    else rows[it->second].count++;
+    if (!hist.count(cat)) hist_order.push_back(cat);
+    hist[cat]++;
+  }
+  while (hi < hev.size() && hev[hi].file == slot) ++hi;
+  if (want_rows && !rows.empty()) {
+    std::ostringstream os;
+    for (const Row& r : rows)
+      csv_row(os, {f.rel, ext_name(f.ext), test_name_tag(f.rel, r.fixture), r.method, r.stmt, std::to_string(r.count), r.catname});
+    rows_txt = os.str();
+  }
+  if (want_sum) {
+    std::stable_sort(hist_order.begin(), hist_order.end(), [&](const std::string& x, const std::string& y) { return hist[x] > hist[y]; });
+    std::string a;
+    for (const std::string& c : hist_order) { if (!a.empty()) a += ", "; a += std::to_string(hist[c]) + ":" + c; }
+    std::ostringstream os;
+    csv_row(os, {std::to_string(id), f.rel, std::to_string(st.n_assert), a});
+    sum_txt = os.str();
+  }
+}
 
 static int cmd_scan(const std::vector<std::string>& roots, const std::string& rows_path, const std::string& summary_path,
                     int gpus, bool all_files, int64_t batch_bytes) {
@@ -241,25 +284,37 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
   for (size_t g = 0; g < roots.size(); ++g) walk(roots[g], (int)g, all_files, files);
   const int n_groups = (int)std::max<size_t>(roots.size(), 1);
   fprintf(stderr, "tosem-scan: %zu files selected under %zu root(s)\n", files.size(), roots.size());
-  // batches of consecutive files, each at most ~1 GiB of arena (--batch-bytes) and 1M files
-  std::vector<Batch> batches;
-  {
-    int64_t cur = 0; size_t first = 0;
-    for (size_t i = 0; i < files.size(); ++i) {
-      if (files[i].size >= (1ll << 30)) die("file larger than 1 GiB: " + files[i].abs);
-      const int64_t padded = (files[i].size + 127) / 128 * 128;
-      if (i > first && (cur + padded > batch_bytes || i - first >= (1u << 20))) {
-        batches.emplace_back(first, i - first); first = i; cur = 0;
-      }
-      cur += padded;
-    }
-    if (files.size() > first) batches.emplace_back(first, files.size() - first);
-  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device (there is no CPU fallback)");
   gpus = std::max(1, std::min(gpus, ndev));
-  std::vector<ScanOut> outs(batches.size());
-  // one host thread per GPU; batch b goes to GPU b % gpus; one ncclAllReduce of the count table at the end
+  // ---- shares of the GPUs: files sorted by size, descending, dealt round-robin (LPT), so that
+  //      every GPU gets the same byte total whatever the size law is; then, per GPU, batches of at most
+  //      --batch-bytes of arena (and 1M files) in walk order
+  std::vector<std::vector<Batch>> share((size_t)gpus);
+  {
+    std::vector<uint32_t> order(files.size());
+    for (size_t i = 0; i < files.size(); ++i) {
+      if (files[i].size >= (1ll << 30)) die("file larger than 1 GiB: " + files[i].abs);
+      order[i] = (uint32_t)i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return files[x].size > files[y].size; });
+    std::vector<std::vector<uint32_t>> mine((size_t)gpus);
+    for (size_t k = 0; k < order.size(); ++k) mine[k % (size_t)gpus].push_back(order[k]);
+    for (int g = 0; g < gpus; ++g) {
+      std::sort(mine[(size_t)g].begin(), mine[(size_t)g].end());
+      int64_t cur = 0;
+      share[(size_t)g].emplace_back();
+      for (uint32_t i : mine[(size_t)g]) {
+        const int64_t padded = (files[i].size + 127) / 128 * 128;
+        Batch* b = &share[(size_t)g].back();
+        if (b->count() && (cur + padded > batch_bytes || b->count() >= (1u << 20))) { share[(size_t)g].emplace_back(); b = &share[(size_t)g].back(); cur = 0; }
+        b->idx.push_back(i);
+        cur += padded;
+      }
+      if (share[(size_t)g].back().count() == 0) share[(size_t)g].pop_back();
+    }
+  }
+  // one host thread per GPU; one ncclAllReduce of the count table at the end
   std::vector<ncclComm_t> comms(gpus);
   std::vector<int> devs(gpus);
   for (int i = 0; i < gpus; ++i) devs[i] = i;
@@ -273,60 +328,76 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
     fflush(stdout);
     dup2(saved, 1);
     close(saved);
-    if (nr != ncclSuccess) die("ncclCommInitAll failed");
+    nccl_ck(nr, "ncclCommInitAll");
   }
   const size_t table = (size_t)(n_groups + 1) * TSM_NUM_CATEGORIES + 4;
   std::vector<std::vector<int64_t>> totals(gpus, std::vector<int64_t>(table, 0));
+  const bool want_rows = !rows_path.empty(), want_sum = !summary_path.empty();
+  std::vector<std::string> rows_txt(want_rows ? files.size() : 0), sum_txt(want_sum ? files.size() : 0);   // per file, written in walk order at the end
   auto worker = [&](int g) {
-    cudaSetDevice(g);
+    std::vector<Batch>& batches = share[(size_t)g];
+    cu_ck(cudaSetDevice(g), "cudaSetDevice");
     cudaStream_t st;
-    cudaStreamCreate(&st);
+    cu_ck(cudaStreamCreate(&st), "cudaStreamCreate");
     int64_t max_arena = 1 << 20; int32_t max_files = 16;
-    for (size_t b = g; b < batches.size(); b += gpus) {
+    for (const Batch& b : batches) {
       int64_t bytes = 0;
-      for (size_t i = 0; i < batches[b].count; ++i) bytes += (files[batches[b].first + i].size + 127) / 128 * 128;
+      for (uint32_t i : b.idx) bytes += (files[i].size + 127) / 128 * 128;
       max_arena = std::max(max_arena, bytes + 4096);
-      max_files = std::max<int32_t>(max_files, (int32_t)batches[b].count);
+      max_files = std::max<int32_t>(max_files, (int32_t)b.count());
     }
     tsm_ctx* ctx = nullptr;
     ck(tsm_create(&ctx, g, max_arena, max_files, std::max(n_groups, 1), 0), "tsm_create");
-    int64_t* d_acc = nullptr;                               // running sum of the count tables of this GPU's batches
-    cudaMalloc((void**)&d_acc, table * sizeof(int64_t));
-    cudaMemsetAsync(d_acc, 0, table * sizeof(int64_t), st);
-    // host pipeline: while the GPU scans batch b (tsm_scan overlaps its H2D slabs with the kernels), a
-    // background task already reads the files of this GPU's next batch into its pinned arena
+    int64_t* d_acc = nullptr;                               // this GPU's count table, input and output of the allreduce
+    cu_ck(cudaMalloc((void**)&d_acc, table * sizeof(int64_t)), "cudaMalloc");
+    // host pipeline: while the GPU scans batch b (tsm_scan overlaps its H2D slabs with the kernels), a background
+    // task already reads the files of the next batch into its pinned arena.  At most two arenas per GPU are alive:
+    // a batch's rows are rendered and its arena and events are freed as soon as its scan returns.
     std::future<void> next_load;
-    if ((size_t)g < batches.size()) next_load = std::async(std::launch::async, [&files, &batches, g] { cudaSetDevice(g); load_batch(files, batches[(size_t)g]); });
-    for (size_t b = g; b < batches.size(); b += gpus) {
+    if (!batches.empty()) next_load = std::async(std::launch::async, [&files, &batches, g] { cudaSetDevice(g); load_batch(files, batches[0]); });
+    std::vector<tsm_file_stat> stats;
+    std::vector<tsm_assert_event> aev;
+    std::vector<tsm_header_event> hev;
+    std::vector<int64_t> group_counts, h;
+    for (size_t b = 0; b < batches.size(); ++b) {
       Batch& B = batches[b];
       next_load.get();
-      if (b + gpus < batches.size())
-        next_load = std::async(std::launch::async, [&files, &batches, b, gpus, g] { cudaSetDevice(g); load_batch(files, batches[b + (size_t)gpus]); });
-      tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, n_groups};
-      ScanOut& o = outs[b];
-      o.stats.resize(B.count);
-      o.group_counts.assign((size_t)n_groups * TSM_NUM_CATEGORIES, 0);
+      if (b + 1 < batches.size())
+        next_load = std::async(std::launch::async, [&files, &batches, b, g] { cudaSetDevice(g); load_batch(files, batches[b + 1]); });
+      tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count(), n_groups};
+      stats.resize(B.count());
+      group_counts.assign((size_t)n_groups * TSM_NUM_CATEGORIES, 0);
       const int64_t cap = std::max<int64_t>(B.bytes / 8 + 1024, 1024);
-      o.aev.resize((size_t)cap); o.hev.resize((size_t)cap);
+      aev.resize((size_t)cap); hev.resize((size_t)cap);
       tsm_result r{};
-      r.stats = o.stats.data(); r.group_counts = o.group_counts.data();
-      r.aev = o.aev.data(); r.aev_cap = cap; r.hev = o.hev.data(); r.hev_cap = cap;
+      r.stats = stats.data(); r.group_counts = group_counts.data();
+      r.aev = aev.data(); r.aev_cap = cap; r.hev = hev.data(); r.hev_cap = cap;
       ck(tsm_scan(ctx, &c, &r, TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS, st), "tsm_scan");
-      o.aev.resize((size_t)r.n_aev); o.hev.resize((size_t)r.n_hev);
+      aev.resize((size_t)r.n_aev); hev.resize((size_t)r.n_hev);
       void* dptr = nullptr; int64_t n64 = 0;
       ck(tsm_device_counts(ctx, &dptr, &n64), "tsm_device_counts");
-      // accumulate on the device: acc += counts (tiny; a cudaMemcpy + host add would also do)
-      std::vector<int64_t> h((size_t)n64);
-      cudaMemcpyAsync(h.data(), dptr, (size_t)n64 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-      cudaStreamSynchronize(st);
+      h.resize((size_t)n64);
+      cu_ck(cudaMemcpyAsync(h.data(), dptr, (size_t)n64 * sizeof(int64_t), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+      cu_ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
       for (size_t i = 0; i < (size_t)n64 && i < table; ++i) totals[g][i] += h[i];
+      if (want_rows || want_sum) {
+        size_t ai = 0, hi = 0;
+        static std::string none;
+        for (size_t i = 0; i < B.count(); ++i) {
+          const uint32_t fi = B.idx[i];
+          render_file(files[fi], (int64_t)fi + 1, B.arena + B.off[i], B.len[i], (uint32_t)i, stats[i], aev, ai, hev, hi, want_rows, want_sum,
+                      want_rows ? rows_txt[fi] : none, want_sum ? sum_txt[fi] : none);
+        }
+      }
+      tsm_host_free(B.arena);
+      B.arena = nullptr;
+      std::vector<int32_t>().swap(B.off); std::vector<int32_t>().swap(B.len);
     }
-    cudaMemcpyAsync(d_acc, totals[g].data(), table * sizeof(int64_t), cudaMemcpyHostToDevice, st);
-    if (gpus > 1) {                                         // the single collective of the path
-      ncclAllReduce(d_acc, d_acc, table, ncclInt64, ncclSum, comms[g], st);
-    }
-    cudaMemcpyAsync(totals[g].data(), d_acc, table * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    cudaStreamSynchronize(st);
+    cu_ck(cudaMemcpyAsync(d_acc, totals[g].data(), table * sizeof(int64_t), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync");
+    if (gpus > 1)                                           // the single collective of the path
+      nccl_ck(ncclAllReduce(d_acc, d_acc, table, ncclInt64, ncclSum, comms[g], st), "ncclAllReduce");
+    cu_ck(cudaMemcpyAsync(totals[g].data(), d_acc, table * sizeof(int64_t), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+    cu_ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     cudaFree(d_acc);
     tsm_destroy(ctx);
     cudaStreamDestroy(st);
@@ -338,54 +409,16 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
     for (auto& t : th) t.join();
     for (int g = 0; g < gpus; ++g) ncclCommDestroy(comms[g]);
   }
-  // ---- rows + summary
-  std::ofstream rows_os, sum_os;
-  if (!rows_path.empty()) { rows_os.open(rows_path, std::ios::binary); csv_row(rows_os, {"fileName", "extension", "test_name", "method", "statement", "counts", "category"}); }
-  if (!summary_path.empty()) { sum_os.open(summary_path, std::ios::binary); csv_row(sum_os, {"Id", "FileName", "total assert", "assertion"}); }
-  int64_t id = 0;
-  for (size_t b = 0; b < batches.size(); ++b) {
-    const Batch& B = batches[b];
-    const ScanOut& o = outs[b];
-    size_t ai = 0, hi = 0;
-    for (size_t i = 0; i < B.count; ++i) {
-      const FileEntry& f = files[B.first + i];
-      const uint8_t* base = B.arena + B.off[i];
-      ++id;
-      struct Row { int64_t hdr; std::string stmt; int cat; std::string catname; int64_t count; bool fixture; std::string method; };
-      std::vector<Row> rows;
-      std::map<std::pair<int64_t, std::string>, size_t> index;
-      std::map<std::string, int64_t> hist; std::vector<std::string> hist_order;
-      int64_t cur_hdr = -1; bool cur_fix = false; std::string cur_method = "xxxx";
-      while (ai < o.aev.size() && o.aev[ai].file == i) {
-        const tsm_assert_event& ev = o.aev[ai++];
-        while (hi < o.hev.size() && o.hev[hi].file == i && o.hev[hi].line_off <= ev.line_off) {   // governing header
-          const tsm_header_event& h = o.hev[hi++];
-          cur_hdr = h.line_off; cur_fix = (h.kind & 1u) != 0;
-          cur_method = method_string(f.ext, base + h.line_off, h.line_len);
-        }
-        // the statement may be longer than the 16-bit event field: re-derive its end on the host if saturated
-        uint32_t sl = ev.stmt_len;
-        if (sl == 65535) { const uint8_t* p = base + ev.stmt_off; uint32_t e = 0, last = 0; while (ev.stmt_off + e < (uint32_t)B.len[i] && p[e] != '\n' && p[e] != '(') { if (!is_w(p[e])) last = e + 1; ++e; } sl = last; }
-        std::string stmt((const char*)base + ev.stmt_off, sl);
-        std::string cat = ev.cat == 127 ? std::string((const char*)base + ev.ident_off, ev.ident_len) : std::string(tsm_category_name(ev.cat));
-        auto key = std::make_pair(cur_hdr, stmt);
-        auto it = index.find(key);
-        if (it == index.end()) { index[key] = rows.size(); rows.push_back({cur_hdr, stmt, ev.cat, cat, 1, cur_fix, cur_method}); }
-        else rows[it->second].count++;
-        if (!hist.count(cat)) hist_order.push_back(cat);
-        hist[cat]++;
-      }
-      while (hi < o.hev.size() && o.hev[hi].file == i) ++hi;
-      if (rows_os.is_open())
-        for (const Row& r : rows)
-          csv_row(rows_os, {f.rel, ext_name(f.ext), test_name_tag(f.rel, r.fixture), r.method, r.stmt, std::to_string(r.count), r.catname});
-      if (sum_os.is_open()) {
-        std::stable_sort(hist_order.begin(), hist_order.end(), [&](const std::string& x, const std::string& y) { return hist[x] > hist[y]; });
-        std::string a;
-        for (const std::string& c : hist_order) { if (!a.empty()) a += ", "; a += std::to_string(hist[c]) + ":" + c; }
-        csv_row(sum_os, {std::to_string(id), f.rel, std::to_string(o.stats[i].n_assert), a});
-      }
-    }
+  // ---- rows + summary, in walk order
+  if (want_rows) {
+    std::ofstream os(rows_path, std::ios::binary);
+    csv_row(os, {"fileName", "extension", "test_name", "method", "statement", "counts", "category"});
+    for (const std::string& t : rows_txt) os << t;
+  }
+  if (want_sum) {
+    std::ofstream os(summary_path, std::ios::binary);
+    csv_row(os, {"Id", "FileName", "total assert", "assertion"});
+    for (const std::string& t : sum_txt) os << t;
   }
   // ---- the aggregate table (global counts after the allreduce) to stdout
   const std::vector<int64_t>& T = totals[0];
@@ -395,9 +428,14 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
     if (v) printf("%s,%lld\r\n", k == 0 ? "" : tsm_category_name(k), (long long)v);
   }
   const size_t tot = (size_t)(n_groups + 1) * TSM_NUM_CATEGORIES;
-  fprintf(stderr, "tosem-scan: lines=%lld assertion_lines=%lld headers=%lld fixture_headers=%lld on %d GPU(s)\n",
-          (long long)T[tot], (long long)T[tot + 1], (long long)T[tot + 2], (long long)T[tot + 3], gpus);
-  for (Batch& B : batches) tsm_host_free(B.arena);
+  int64_t share_min = -1, share_max = 0;
+  for (int g = 0; g < gpus; ++g) {
+    int64_t bsum = 0;
+    for (const Batch& b : share[(size_t)g]) for (uint32_t i : b.idx) bsum += files[i].size;
+    share_min = share_min < 0 ? bsum : std::min(share_min, bsum); share_max = std::max(share_max, bsum);
+  }
+  fprintf(stderr, "tosem-scan: lines=%lld assertion_lines=%lld headers=%lld fixture_headers=%lld on %d GPU(s), shares %lld..%lld bytes\n",
+          (long long)T[tot], (long long)T[tot + 1], (long long)T[tot + 2], (long long)T[tot + 3], gpus, (long long)std::max<int64_t>(share_min, 0), (long long)share_max);
   return 0;
 }
 
@@ -609,22 +647,22 @@ static int cmd_body(const std::vector<std::string>& roots, const std::string& ou
   int64_t index = 0, cases = 0, file_id = 0, n_stmt = 0;
   size_t first = 0;
   while (first < files.size()) {
-    Batch B; B.first = first;
+    Batch B;
     int64_t cur = 0;
-    while (first < files.size() && (B.count == 0 || (cur + files[first].size < (1ll << 29) && B.count < (1u << 19)))) {
-      cur += (files[first].size + 127) / 128 * 128; ++B.count; ++first;
+    while (first < files.size() && (B.count() == 0 || (cur + files[first].size < (1ll << 29) && B.count() < (1u << 19)))) {
+      cur += (files[first].size + 127) / 128 * 128; B.idx.push_back((uint32_t)first); ++first;
     }
     load_batch(files, B);
     tsm_ctx* ctx = nullptr;
-    ck(tsm_create(&ctx, 0, B.bytes + 4096, (int32_t)B.count, (int32_t)std::max<size_t>(roots.size(), 1), 0), "tsm_create");
-    tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, (int32_t)std::max<size_t>(roots.size(), 1)};
+    ck(tsm_create(&ctx, 0, B.bytes + 4096, (int32_t)B.count(), (int32_t)std::max<size_t>(roots.size(), 1), 0), "tsm_create");
+    tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count(), (int32_t)std::max<size_t>(roots.size(), 1)};
     const int64_t cap = std::max<int64_t>(B.bytes / 8 + 1024, 1024);
     std::vector<tsm_header_event> hev((size_t)cap);
     tsm_result r{};
     r.hev = hev.data(); r.hev_cap = cap;
     ck(tsm_scan(ctx, &c, &r, TSM_SCAN_HEADER_EVENTS, nullptr), "tsm_scan");
     hev.resize((size_t)r.n_hev);
-    std::vector<int64_t> base(B.count + 1);
+    std::vector<int64_t> base(B.count() + 1);
     int64_t nl = 0;
     int rc = tsm_statements(ctx, &c, base.data(), nullptr, nullptr, 0, &nl, nullptr);
     if (rc != TSM_OK && rc != TSM_E_CAPACITY) ck(rc, "tsm_statements");
@@ -633,8 +671,8 @@ static int cmd_body(const std::vector<std::string>& roots, const std::string& ou
     ck(tsm_statements(ctx, &c, base.data(), lend.data(), kind.data(), nl, &nl, nullptr), "tsm_statements");
     tsm_destroy(ctx);
     size_t hi = 0;
-    for (size_t i = 0; i < B.count; ++i) {
-      const FileEntry& f = files[B.first + i];
+    for (size_t i = 0; i < B.count(); ++i) {
+      const FileEntry& f = files[B.idx[i]];
       const uint8_t* p = B.arena + B.off[i];
       ++file_id;
       bool in_case = false;
@@ -683,24 +721,24 @@ static std::vector<SnapFile> scan_snapshot(const std::string& root) {
   std::vector<SnapFile> out;
   size_t first = 0;
   while (first < files.size()) {
-    Batch B; B.first = first;
+    Batch B;
     int64_t cur = 0;
-    while (first < files.size() && (B.count == 0 || (cur + files[first].size < (1ll << 29) && B.count < (1u << 19)))) {
-      cur += (files[first].size + 127) / 128 * 128; ++B.count; ++first;
+    while (first < files.size() && (B.count() == 0 || (cur + files[first].size < (1ll << 29) && B.count() < (1u << 19)))) {
+      cur += (files[first].size + 127) / 128 * 128; B.idx.push_back((uint32_t)first); ++first;
     }
     load_batch(files, B);
     tsm_ctx* ctx = nullptr;
-    ck(tsm_create(&ctx, 0, B.bytes + 4096, (int32_t)B.count, 1, 0), "tsm_create");
-    tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count, 1};
+    ck(tsm_create(&ctx, 0, B.bytes + 4096, (int32_t)B.count(), 1, 0), "tsm_create");
+    tsm_corpus c{B.arena, B.off.data(), B.len.data(), B.ext.data(), B.grp.data(), (int32_t)B.count(), 1};
     const int64_t cap = std::max<int64_t>(B.bytes / 8 + 1024, 1024);
-    std::vector<tsm_file_stat> stats(B.count);
+    std::vector<tsm_file_stat> stats(B.count());
     std::vector<tsm_assert_event> aev((size_t)cap);
     tsm_result r{};
     r.stats = stats.data(); r.aev = aev.data(); r.aev_cap = cap;
     ck(tsm_scan(ctx, &c, &r, TSM_SCAN_ASSERT_EVENTS, nullptr), "tsm_scan");
     tsm_destroy(ctx);
     size_t ai = 0;
-    for (size_t i = 0; i < B.count; ++i) {
+    for (size_t i = 0; i < B.count(); ++i) {
       const uint8_t* base = B.arena + B.off[i];
       std::map<std::string, int64_t> hist; std::vector<std::string> order;
       for (; ai < (size_t)r.n_aev && aev[ai].file == i; ++ai) {
@@ -712,7 +750,7 @@ static std::vector<SnapFile> scan_snapshot(const std::string& root) {
       std::stable_sort(order.begin(), order.end(), [&](const std::string& x, const std::string& y) { return hist[x] > hist[y]; });
       std::string a;
       for (const std::string& k : order) { if (!a.empty()) a += ", "; a += std::to_string(hist[k]) + ":" + k; }
-      out.push_back({files[B.first + i].rel, stats[i].digest, files[B.first + i].size, stats[i].n_assert, a});
+      out.push_back({files[B.idx[i]].rel, stats[i].digest, files[B.idx[i]].size, stats[i].n_assert, a});
     }
     tsm_host_free(B.arena);
   }
@@ -788,24 +826,54 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
   std::map<std::string, bool> seen;
   for (const FileEntry& f : a) { auto it = bm.find(f.rel); pairs.push_back({f.rel, &f, it == bm.end() ? nullptr : it->second}); seen[f.rel] = true; }
   for (const FileEntry& f : b) if (!seen.count(f.rel)) pairs.push_back({f.rel, nullptr, &f});
+  // git's numstat reports no line counts for binary files: a pair is skipped when either side has a NUL byte in its first 8000
+  {
+    auto binary = [](const FileEntry* f) {
+      if (!f || f->abs.empty() || f->size == 0) return false;
+      char buf[8000];
+      const int fd = open(f->abs.c_str(), O_RDONLY);
+      if (fd < 0) return false;
+      const ssize_t r = read(fd, buf, sizeof buf);
+      close(fd);
+      return r > 0 && memchr(buf, 0, (size_t)r) != nullptr;
+    };
+    std::vector<Pair> text;
+    size_t skipped = 0;
+    for (const Pair& p : pairs) { if (binary(p.o) || binary(p.n)) ++skipped; else text.push_back(p); }
+    if (skipped) fprintf(stderr, "tosem-scan: %zu binary file(s) skipped\n", skipped);
+    pairs.swap(text);
+  }
   auto pack = [&](bool old_side, Batch& B, std::vector<FileEntry>& tmp) {
     for (const Pair& p : pairs) { const FileEntry* f = old_side ? p.o : p.n; tmp.push_back(f ? *f : FileEntry{p.rel, "", 0, 0, 0}); }
-    B.first = 0; B.count = tmp.size();
-    B.len.resize(B.count); B.off.resize(B.count + 1); B.ext.assign(B.count, 0); B.grp.assign(B.count, 0);
-    for (size_t i = 0; i < B.count; ++i) B.len[i] = (int32_t)tmp[i].size;
-    B.bytes = tsm_layout(B.len.data(), (int32_t)B.count, B.off.data());
+    const size_t n = tmp.size();
+    B.idx.resize(n);
+    for (size_t i = 0; i < n; ++i) B.idx[i] = (uint32_t)i;
+    B.len.resize(n); B.off.resize(n + 1); B.ext.assign(n, 0); B.grp.assign(n, 0);
+    for (size_t i = 0; i < n; ++i) B.len[i] = (int32_t)tmp[i].size;
+    B.bytes = tsm_layout(B.len.data(), (int32_t)n, B.off.data());
     if (B.bytes < 0) die("tree does not fit one int32-indexed arena; diff it per sub-directory");
     B.arena = (uint8_t*)tsm_host_alloc(std::max<int64_t>(B.bytes, 128));
     if (!B.arena) die("pinned arena allocation failed");
     memset(B.arena, 0, (size_t)std::max<int64_t>(B.bytes, 128));
-    for (size_t i = 0; i < B.count; ++i) if (!tmp[i].abs.empty()) { std::ifstream in(tmp[i].abs, std::ios::binary); in.read((char*)B.arena + B.off[i], B.len[i]); }
+    for (size_t i = 0; i < n; ++i) {
+      if (tmp[i].abs.empty() || B.len[i] == 0) continue;
+      const int fd = open(tmp[i].abs.c_str(), O_RDONLY);
+      int64_t got = 0;
+      while (fd >= 0 && got < B.len[i]) {
+        const ssize_t r = read(fd, B.arena + B.off[i] + got, (size_t)(B.len[i] - got));
+        if (r <= 0) break;
+        got += r;
+      }
+      if (fd >= 0) close(fd);
+      if (got != B.len[i]) die("short read: " + tmp[i].abs);
+    }
   };
   Batch A, N; std::vector<FileEntry> ta, tn;
   pack(true, A, ta); pack(false, N, tn);
   tsm_ctx* ctx = nullptr;
   ck(tsm_create(&ctx, 0, 1 << 20, 16, 1, 0), "tsm_create");
-  tsm_corpus ca{A.arena, A.off.data(), A.len.data(), A.ext.data(), A.grp.data(), (int32_t)A.count, 1};
-  tsm_corpus cn{N.arena, N.off.data(), N.len.data(), N.ext.data(), N.grp.data(), (int32_t)N.count, 1};
+  tsm_corpus ca{A.arena, A.off.data(), A.len.data(), A.ext.data(), A.grp.data(), (int32_t)A.count(), 1};
+  tsm_corpus cn{N.arena, N.off.data(), N.len.data(), N.ext.data(), N.grp.data(), (int32_t)N.count(), 1};
   // ext tags of both sides feed the assertion-line classification of the changed lines
   for (size_t i = 0; i < pairs.size(); ++i) { A.ext[i] = (uint8_t)ext_tag(pairs[i].rel); N.ext[i] = A.ext[i]; }
   std::vector<int64_t> added(pairs.size()), removed(pairs.size());

@@ -280,12 +280,13 @@ void gen_pair(uint64_t seed, int64_t index, int32_t cap, double lambda, int ext,
 }
 }  // namespace
 
-extern "C" int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
-                                  double lambda, int32_t* len_old, int32_t* len_new, uint8_t* ext) {
+extern "C" int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, const int32_t* index, int32_t first_index, int32_t index_stride,
+                                  int32_t cap, double lambda, int32_t* len_old, int32_t* len_new, uint8_t* ext) {
   if (n_pairs < 0 || !len_old || !len_new || !ext || first_index < 0 || index_stride < 1 || cap < 128 || lambda < 0) return TSM_E_ARG;
   std::string o, n;
   for (int32_t i = 0; i < n_pairs; ++i) {
-    const int64_t logical = (int64_t)first_index + (int64_t)i * index_stride;
+    const int64_t logical = index ? (int64_t)index[i] : (int64_t)first_index + (int64_t)i * index_stride;
+    if (logical < 0) return TSM_E_ARG;
     ext[i] = (uint8_t)gen_ext(seed, logical);
     gen_pair(seed, logical, cap, lambda, ext[i], o, n);
     len_old[i] = (int32_t)o.size();
@@ -294,15 +295,15 @@ extern "C" int tsm_gen_pair_sizes(uint64_t seed, int32_t n_pairs, int32_t first_
   return TSM_OK;
 }
 
-extern "C" int tsm_gen_pair_fill(uint64_t seed, int32_t n_pairs, int32_t first_index, int32_t index_stride, int32_t cap,
-                                 double lambda, const uint8_t* ext, const int32_t* off_old, const int32_t* len_old,
+extern "C" int tsm_gen_pair_fill(uint64_t seed, int32_t n_pairs, const int32_t* index, int32_t first_index, int32_t index_stride,
+                                 int32_t cap, double lambda, const uint8_t* ext, const int32_t* off_old, const int32_t* len_old,
                                  uint8_t* arena_old, const int32_t* off_new, const int32_t* len_new, uint8_t* arena_new) {
   if (n_pairs < 0 || !ext || !off_old || !len_old || !arena_old || !off_new || !len_new || !arena_new || first_index < 0 ||
       index_stride < 1 || cap < 128)
     return TSM_E_ARG;
   std::string o, n;
   for (int32_t i = 0; i < n_pairs; ++i) {
-    const int64_t logical = (int64_t)first_index + (int64_t)i * index_stride;
+    const int64_t logical = index ? (int64_t)index[i] : (int64_t)first_index + (int64_t)i * index_stride;
     gen_pair(seed, logical, cap, lambda, ext[i], o, n);
     if ((int64_t)o.size() != len_old[i] || (int64_t)n.size() != len_new[i]) return TSM_E_ARG;   // sizes must come from tsm_gen_pair_sizes
     memcpy(arena_old + off_old[i], o.data(), o.size());

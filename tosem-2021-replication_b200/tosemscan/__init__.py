@@ -31,7 +31,7 @@ DIFF_DETAIL = np.dtype([("hunks_add", "<i8"), ("hunks_del", "<i8"), ("hunks_mod"
 # every symbol include/tosemscan.h declares (tests check the library exports exactly these)
 SYMBOLS = ["tsm_abi_version", "tsm_strerror", "tsm_category_name", "tsm_create", "tsm_destroy", "tsm_scan",
            "tsm_upload", "tsm_scan_resident", "tsm_download", "tsm_device_counts", "tsm_last_launch_count", "tsm_last_kernel_ms", "tsm_kernel_ms_stats",
-           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_statements", "tsm_line_hashes", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
+           "tsm_diff_pairs", "tsm_diff_pairs_detail", "tsm_statements", "tsm_line_hashes", "tsm_diff_upload", "tsm_diff_resident", "tsm_diff_last_ms", "tsm_reduce", "tsm_host_alloc", "tsm_host_free", "tsm_layout", "tsm_gen_sizes",
            "tsm_gen_fill", "tsm_gen_edit", "tsm_gen_pair_sizes", "tsm_gen_pair_fill"]
 
 
@@ -117,10 +117,16 @@ def lib():
         L.tsm_gen_edit.restype = C.c_int64
         L.tsm_gen_edit.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int64]
         L.tsm_gen_pair_sizes.restype = C.c_int
-        L.tsm_gen_pair_sizes.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+        L.tsm_gen_pair_sizes.argtypes = [C.c_uint64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.tsm_gen_pair_fill.restype = C.c_int
-        L.tsm_gen_pair_fill.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 7
+        L.tsm_gen_pair_fill.argtypes = [C.c_uint64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 7
+        L.tsm_diff_upload.restype = C.c_int
+        L.tsm_diff_upload.argtypes = [C.c_void_p, C.POINTER(_Corpus), C.POINTER(_Corpus), C.c_void_p]
+        L.tsm_diff_resident.restype = C.c_int
+        L.tsm_diff_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tsm_diff_last_ms.restype = C.c_int
+        L.tsm_diff_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
         _lib = L
     return _lib
 
@@ -248,41 +254,59 @@ def gen_corpus(seed, n_files, size_law=0, fixed_size=4096, first_index=0, index_
     return Corpus(arena, off, length, ext, grp, n_groups, keep)
 
 
-def gen_pairs(seed, n_pairs, cap=65536, lam=6.0, first_index=0, index_stride=1, pinned=True, threads=None):
-    """BASELINE config C5: (olds, news) corpora of n_pairs revision pairs, generated in C++."""
+def gen_pair_sizes(seed, n_pairs, cap=65536, lam=6.0, index=None, first_index=0, index_stride=1, threads=None):
+    """(len_old, len_new, ext) of the logical pairs index[...] (or first_index + i*stride) of BASELINE config C5."""
     L = lib()
-    lo, ln = np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.int32)
-    ext = np.zeros(n_pairs, np.uint8)
-    nthr = max(1, min(threads or (os.cpu_count() or 1), 64, (n_pairs + 255) // 256))
-    bounds = [n_pairs * t // nthr for t in range(nthr + 1)]
-
-    def run(fn):
-        if nthr == 1:
-            rcs = [fn(0)]
-        else:
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(nthr) as ex:
-                rcs = list(ex.map(fn, range(nthr)))
-        if any(rcs):
-            raise TsmError([r for r in rcs if r][0], "tsm_gen_pair_*")
+    idx = None if index is None else np.ascontiguousarray(index, np.int32)
+    n = n_pairs if idx is None else len(idx)
+    lo, ln, ext = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    nthr = max(1, min(threads or (os.cpu_count() or 1), 64, (n + 255) // 256))
+    bounds = [n * t // nthr for t in range(nthr + 1)]
 
     def sizes(t):
         a, b = bounds[t], bounds[t + 1]
-        return 0 if a == b else L.tsm_gen_pair_sizes(seed, b - a, first_index + a * index_stride, index_stride, cap, float(lam),
-                                                     _p(lo[a:b]), _p(ln[a:b]), _p(ext[a:b]))
-    run(sizes)
-    oo, on = np.zeros(n_pairs + 1, np.int32), np.zeros(n_pairs + 1, np.int32)
-    to, tn = L.tsm_layout(_p(lo), n_pairs, _p(oo)), L.tsm_layout(_p(ln), n_pairs, _p(on))
+        if a == b:
+            return 0
+        return L.tsm_gen_pair_sizes(seed, b - a, None if idx is None else _p(idx[a:b]), first_index + a * index_stride, index_stride,
+                                    cap, float(lam), _p(lo[a:b]), _p(ln[a:b]), _p(ext[a:b]))
+    _run_threads(sizes, nthr, "tsm_gen_pair_sizes")
+    return lo, ln, ext
+
+
+def _run_threads(fn, nthr, what):
+    if nthr == 1:
+        rcs = [fn(0)]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nthr) as ex:
+            rcs = list(ex.map(fn, range(nthr)))
+    if any(rcs):
+        raise TsmError([r for r in rcs if r][0], what)
+
+
+def gen_pairs(seed, n_pairs, cap=65536, lam=6.0, first_index=0, index_stride=1, pinned=True, threads=None, index=None, sizes=None):
+    """BASELINE config C5: (olds, news) corpora of revision pairs, generated in C++.  `index` picks
+    logical pairs by number (a rank's share of a size-balanced deal); `sizes` = gen_pair_sizes of the same pairs, if known."""
+    L = lib()
+    idx = None if index is None else np.ascontiguousarray(index, np.int32)
+    n = n_pairs if idx is None else len(idx)
+    lo, ln, ext = sizes if sizes is not None else gen_pair_sizes(seed, n, cap, lam, idx, first_index, index_stride, threads)
+    oo, on = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32)
+    to, tn = L.tsm_layout(_p(lo), n, _p(oo)), L.tsm_layout(_p(ln), n, _p(on))
     if to < 0 or tn < 0:
         raise ValueError("pairs do not fit an int32-indexed arena")
     ao, ko = host_buffer(to, pinned)
     an, kn = host_buffer(tn, pinned)
+    nthr = max(1, min(threads or (os.cpu_count() or 1), 64, (n + 255) // 256))
+    bounds = [n * t // nthr for t in range(nthr + 1)]
 
     def fill(t):
         a, b = bounds[t], bounds[t + 1]
-        return 0 if a == b else L.tsm_gen_pair_fill(seed, b - a, first_index + a * index_stride, index_stride, cap, float(lam),
-                                                    _p(ext[a:b]), _p(oo[a:b + 1]), _p(lo[a:b]), _p(ao), _p(on[a:b + 1]), _p(ln[a:b]), _p(an))
-    run(fill)
+        if a == b:
+            return 0
+        return L.tsm_gen_pair_fill(seed, b - a, None if idx is None else _p(idx[a:b]), first_index + a * index_stride, index_stride,
+                                   cap, float(lam), _p(ext[a:b]), _p(oo[a:b + 1]), _p(lo[a:b]), _p(ao), _p(on[a:b + 1]), _p(ln[a:b]), _p(an))
+    _run_threads(fill, nthr, "tsm_gen_pair_fill")
     return Corpus(ao, oo, lo, ext, None, 1, ko), Corpus(an, on, ln, ext.copy(), None, 1, kn)
 
 
@@ -460,3 +484,26 @@ class Scanner:
         if rc:
             raise TsmError(rc, "tsm_diff_pairs_detail")
         return added, removed, det[:n]
+
+    def diff_upload(self, olds, news, stream=None):
+        """Both sides of the pairs to HBM, kept by the ctx (tsm_diff_upload)."""
+        a, b = olds.c_struct(), news.c_struct()
+        rc = lib().tsm_diff_upload(self._ctx, C.byref(a), C.byref(b), stream)
+        if rc:
+            raise TsmError(rc, "tsm_diff_upload")
+        self._pairs = olds.n_files
+        self._diff_out = (np.zeros(self._pairs, np.int64), np.zeros(self._pairs, np.int64), np.zeros(max(self._pairs, 1), DIFF_DETAIL))
+
+    def diff_resident(self, detail=True, stream=None):
+        """The diff kernels over the resident sides; returns (added, removed[, detail]) - buffers reused across calls."""
+        added, removed, det = self._diff_out
+        rc = lib().tsm_diff_resident(self._ctx, _p(added), _p(removed), _p(det) if detail else None, stream)
+        if rc:
+            raise TsmError(rc, "tsm_diff_resident")
+        return (added, removed, det[:self._pairs]) if detail else (added, removed)
+
+    def diff_last_ms(self):
+        """Device time of the last diff call: [k_scan over both sides, k_myers, k_myers_trace] in ms."""
+        ms = (C.c_float * 3)()
+        lib().tsm_diff_last_ms(self._ctx, C.byref(ms))
+        return [float(x) for x in ms]
