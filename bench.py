@@ -67,7 +67,7 @@ def config_json(args, n, extra):
     c = CONFIGS[args.config]
     out = {"workload": "%s: %s (seed 0x%X, SURVEY.md section 8d)" % (args.config, c["what"], c["seed"]),
            "sharding": "round-robin by file index, no data-path collective" if c["kind"] == "scan"
-           else "pairs sorted by size, dealt round-robin (LPT), no data-path collective",
+           else "pairs sorted by size, dealt to the ranks in alternating direction (equal byte totals), no data-path collective",
            "collective": ("one allreduce(SUM) of the int64 [n_groups+1][128]+4 count table per step, overlapped with the next step's scan"
                           if c["kind"] == "scan" else "one allreduce(SUM) of the 7 churn totals per step") if n > 1 else "none",
            "l2": "input per GPU exceeds the 126 MB L2, no explicit flush"}
@@ -168,7 +168,10 @@ def diff_shard(ts, args, rank, n, pinned=True):
     total = max(n, int(c["total"] * args.scale))
     lo, ln, ext = ts.gen_pair_sizes(c["seed"], total)
     order = np.argsort(-(lo.astype(np.int64) + ln), kind="stable")
-    mine = np.sort(order[rank::n]).astype(np.int32)
+    pos = np.arange(total)
+    lane = pos % n
+    owner = np.where((pos // n) % 2 == 0, lane, n - 1 - lane)      # dealt in alternating direction: equal byte totals per rank
+    mine = np.sort(order[owner == rank]).astype(np.int32)
     a, b = ts.gen_pairs(c["seed"], 0, index=mine, sizes=(lo[mine], ln[mine], ext[mine]), pinned=pinned)
     return a, b, total, int(lo.astype(np.int64).sum() + ln.astype(np.int64).sum())
 

@@ -40,6 +40,8 @@ enum { TSM_EXT_OTHER = 0, TSM_EXT_PY = 1, TSM_EXT_CC = 2, TSM_EXT_CPP = 3, TSM_E
 /* scan flags */
 #define TSM_SCAN_ASSERT_EVENTS 1u  /* produce assertion events (raw scan rows need them) */
 #define TSM_SCAN_HEADER_EVENTS 2u  /* produce header events (method column needs them) */
+#define TSM_SCAN_REV_B 8u          /* the later revision of the lost tool (docs/SPEC.md section 4b; golden G1: ML-Testing-v1.xlsx!DeepSpeech):
+                                      also triggers on _CHECK / TESTEQUAL / FAIL, full statements for BOOST_CHECK( / NTA_CHECK( / Java */
 #define TSM_SCAN_LINE_HASHES 4u    /* internal to tsm_line_hashes / tsm_diff_pairs*: per-line records; ignored by tsm_scan* */
 
 /* Per-file record; replaces the per-file summary stage (S6: `total assert` of

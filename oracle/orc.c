@@ -239,6 +239,70 @@ uint32_t orc_method_string(int ext, const uint8_t* line, uint32_t len, uint8_t* 
   return o < cap ? o : cap;
 }
 
+/* ---------------------------------------------------------------- SPEC section 4b: the later revision of the lost tool ("Rev B")
+ * Golden G1: Important-files/ML-Testing-v1.xlsx!DeepSpeech vs src/DeepSpeech/v0.9.3 (the one version-matched count
+ * golden): rows `BOOST_CHECK_EQUAL` x 1, 1, 2, 2 of native_client/kenlm/util/bit_packing_test.cc:18,26,35,38;
+ * `BOOST_CHECK(!left.full);` (full statement) of lm/partial_test.cc; `assert (audioFormat == 1); // 1 is PCM` (java). */
+int orc_is_assert_line_b(const uint8_t* line, uint32_t len) {
+  return orc_is_assert_line(line, len) || contains_cs(line, len, "_CHECK") || contains_cs(line, len, "TESTEQUAL") ||
+         contains_cs(line, len, "FAIL");
+}
+
+static int ident_is(const uint8_t* L, uint32_t ln, const char* name) { return strlen(name) == ln && memcmp(L, name, ln) == 0; }
+
+/* Statement of Rev B: Rev A's T, except the whole stripped line for java files and for the callees BOOST_CHECK / NTA_CHECK. */
+void orc_statement_b(int ext, const uint8_t* line, uint32_t len, uint32_t* stmt_off, uint32_t* stmt_len) {
+  uint32_t so, sl;
+  orc_statement(line, len, &so, &sl);
+  uint32_t i = sl;
+  while (i > 0 && is_ident(line[so + i - 1])) --i;
+  const uint8_t* L = line + so + i;
+  const uint32_t ln = sl - i;
+  if (ext == 4 || ident_is(L, ln, "BOOST_CHECK") || ident_is(L, ln, "NTA_CHECK")) {
+    uint32_t b, e;
+    strip(line, len, &b, &e);
+    so = b; sl = e - b;
+  }
+  *stmt_off = so; *stmt_len = sl;
+}
+
+/* Category of Rev B from Rev A's statement T (at line + so, length sl): rule 1b BOOST_CHECK_EQUAL -> assertEqual; rule 2b
+ * the bare forms - T == "assert" followed by '(' (java `assert (x == 1);`), callee BOOST_CHECK / NTA_CHECK - by the
+ * operators of the text behind the '(': leading '!' -> assertFalse, then the operator list of rule 2; nothing found:
+ * assertTrue for assert, '' for the two macros.  Everything else: Rev A. */
+int orc_classify_b(const uint8_t* line, uint32_t len, uint32_t so, uint32_t sl, uint32_t* ident_off, uint32_t* ident_len) {
+  const uint8_t* t = line + so;
+  uint32_t i = sl;
+  while (i > 0 && is_ident(t[i - 1])) --i;
+  const uint8_t* L = t + i;
+  const uint32_t ln = sl - i;
+  if (ident_is(L, ln, "BOOST_CHECK_EQUAL")) { if (ident_off) *ident_off = i; if (ident_len) *ident_len = ln; return C_EQ; }
+  const int macro = ident_is(L, ln, "BOOST_CHECK") || ident_is(L, ln, "NTA_CHECK");
+  const int bare = sl == 6 && memcmp(t, "assert", 6) == 0;
+  uint32_t p = so + sl;                                   /* first byte behind T: blanks, then '(' ? */
+  while (p < len && is_w(line[p])) ++p;
+  if ((macro || bare) && p < len && line[p] == '(') {
+    if (ident_off) *ident_off = i;
+    if (ident_len) *ident_len = ln;
+    uint32_t b, e;
+    strip(line, len, &b, &e);
+    const uint8_t* x = line + p + 1;
+    uint32_t n = e > p + 1 ? e - (p + 1) : 0;
+    while (n && is_w(*x)) { ++x; --n; }
+    if (n && x[0] == '!' && !(n > 1 && x[1] == '=')) return C_FALSE;
+    if ((contains_cs(x, n, " not ") && contains_cs(x, n, " in ")) || contains_cs(x, n, " is not ")) return C_FALSE;
+    if (contains_cs(x, n, "True")) return C_TRUE;
+    if (contains_cs(x, n, "==")) return C_EQ;
+    if (contains_cs(x, n, "!=")) return C_NE;
+    if (contains_cs(x, n, "<=")) return C_LE;
+    if (contains_cs(x, n, ">=")) return C_GE;
+    if (contains_cs(x, n, "<")) return C_LT;
+    if (contains_cs(x, n, ">")) return C_GT;
+    return macro ? C_EMPTY : C_TRUE;
+  }
+  return orc_classify(t, sl, ident_off, ident_len);
+}
+
 /* ---------------------------------------------------------------- full scan */
 int orc_scan(const uint8_t* arena, const int32_t* off, const int32_t* len, const uint8_t* ext,
              const uint16_t* grp, int32_t n_files, int32_t n_groups,
@@ -246,6 +310,17 @@ int orc_scan(const uint8_t* arena, const int32_t* off, const int32_t* len, const
              orc_assert_event* aev, int64_t aev_cap, int64_t* n_aev,
              orc_header_event* hev, int64_t hev_cap, int64_t* n_hev,
              uint64_t* line_hash, int64_t* line_base) {
+  return orc_scan_ex(arena, off, len, ext, grp, n_files, n_groups, stats, group_counts, global_counts, aev, aev_cap, n_aev,
+                     hev, hev_cap, n_hev, line_hash, line_base, 0);
+}
+
+int orc_scan_ex(const uint8_t* arena, const int32_t* off, const int32_t* len, const uint8_t* ext,
+             const uint16_t* grp, int32_t n_files, int32_t n_groups,
+             orc_file_stat* stats, int64_t* group_counts, int64_t* global_counts,
+             orc_assert_event* aev, int64_t aev_cap, int64_t* n_aev,
+             orc_header_event* hev, int64_t hev_cap, int64_t* n_hev,
+             uint64_t* line_hash, int64_t* line_base, uint32_t flags) {
+  const int rev_b = (flags & ORC_REV_B) != 0;
   int64_t na = 0, nh = 0, nl = 0;
   if (group_counts) memset(group_counts, 0, sizeof(int64_t) * (size_t)n_groups * ORC_K);
   if (global_counts) memset(global_counts, 0, sizeof(int64_t) * ORC_K);
@@ -279,10 +354,15 @@ int orc_scan(const uint8_t* arena, const int32_t* off, const int32_t* len, const
           }
           ++nh;
         }
-        if (orc_is_assert_line(line, ll)) {
+        if (rev_b ? orc_is_assert_line_b(line, ll) : orc_is_assert_line(line, ll)) {
           uint32_t so, sl, io, il;
           orc_statement(line, ll, &so, &sl);
-          int cat = orc_classify(line + so, sl, &io, &il);
+          int cat = rev_b ? orc_classify_b(line, ll, so, sl, &io, &il) : orc_classify(line + so, sl, &io, &il);
+          if (rev_b) {                                     /* the event carries the Rev-B statement; ident stays Rev A's L */
+            const uint32_t so_a = so;
+            orc_statement_b(x, line, ll, &so, &sl);
+            io += so_a - so;
+          }
           st.n_assert++;
           if (group_counts) group_counts[(size_t)(grp ? grp[f] : 0) * ORC_K + cat]++;
           if (global_counts) global_counts[cat]++;

@@ -72,6 +72,19 @@ int orc_diff_pairs_detail(const uint8_t* arena_old, const int32_t* off_old, cons
                           const uint8_t* arena_new, const int32_t* off_new, const int32_t* len_new, const uint8_t* ext_new,
                           int32_t n_pairs, int64_t* added, int64_t* removed, orc_diff_detail* detail);
 
+/* SPEC section 4b (Rev B, golden G1): trigger, statement and category of the later revision of the lost tool; orc_scan_ex
+ * with ORC_REV_B runs the full scan with them (orc_scan == orc_scan_ex with flags 0). */
+#define ORC_REV_B 8u
+int orc_is_assert_line_b(const uint8_t* line, uint32_t len);
+void orc_statement_b(int ext, const uint8_t* line, uint32_t len, uint32_t* stmt_off, uint32_t* stmt_len);
+int orc_classify_b(const uint8_t* line, uint32_t len, uint32_t so, uint32_t sl, uint32_t* ident_off, uint32_t* ident_len);
+int orc_scan_ex(const uint8_t* arena, const int32_t* off, const int32_t* len, const uint8_t* ext,
+                const uint16_t* grp, int32_t n_files, int32_t n_groups,
+                orc_file_stat* stats, int64_t* group_counts, int64_t* global_counts,
+                orc_assert_event* aev, int64_t aev_cap, int64_t* n_aev,
+                orc_header_event* hev, int64_t hev_cap, int64_t* n_hev,
+                uint64_t* line_hash, int64_t* line_base, uint32_t flags);
+
 /* SPEC section 10: per-line statement kinds (0 blank, 1 first line of a statement, 2 continuation).  Fills
  * line_base[n_files+1]; line_end / line_kind hold up to cap lines (file-relative end offset of every line =
  * position of its LF or the file size).  Returns the total number of lines, or -1. */

@@ -129,7 +129,9 @@ TOKENS = [b"assert", b"ASSERT_", b"Assert", b"assert ", b"EXPECT_", b"EXPECT_EQ"
           b"assertEqual", b"assertTrue", b"assert_", b"assert_called_with", b"assertFoo", b" not ", b" in ", b" is not ",
           b"True", b"==", b"!=", b"<=", b">=", b"<", b">", b"not ", b" ", b"  ", b"\t", b"\r", b"x", b"y", b"_", b".", b",",
           b"EQ", b"NE", b"NEAR", b"FLOAT_EQ", b"DOUBLE_EQ", b"THROW", b"STREQ", b"//", b"#", b'"', b"asser", b"ssert",
-          b"EXPECT", b"tes", b"clas", b"voi", b"de", b"\x00", b"\xc3\xa9", b"0", b"9", b"assertassert", b"testtest"]
+          b"EXPECT", b"tes", b"clas", b"voi", b"de", b"\x00", b"\xc3\xa9", b"0", b"9", b"assertassert", b"testtest",
+          b"BOOST_CHECK", b"BOOST_CHECK_EQUAL", b"BOOST_CHECK(", b"NTA_CHECK(", b"TESTEQUAL", b"FAIL", b"_CHECK", b"_CHEC", b"TESTEQUA",
+          b"!", b"(!", b"assert (", b"F", b"TEST_"]
 
 
 def fuzz_file(rng: random.Random, size: int, nl_rate=0.08, long_lines=False) -> bytes:
@@ -181,3 +183,33 @@ def load_fixture(path):
     files = [blob[e - s:e].tobytes() for s, e in zip(size, ends)]
     grps = d["grp"].astype(np.uint16)
     return files, d["ext"].astype(np.uint8), grps, int(grps.max()) + 1 if len(grps) else 1
+
+
+def score_g1(golden, names, files, events):
+    """Golden G1 (ML-Testing-v1.xlsx!DeepSpeech rows of the bundled files): how many sheet statements the Rev-B events
+    reproduce, and how much of their counts.  events: assertion events of a scan over `files`."""
+    import collections
+    by_file = collections.defaultdict(collections.Counter)
+    for e in events:
+        f = files[int(e["file"])]
+        by_file[int(e["file"])][f[int(e["stmt_off"]):int(e["stmt_off"]) + int(e["stmt_len"])].decode("latin-1")] += 1
+    idx = {n: i for i, n in enumerate(names)}
+    stm, cnt, per_file = [0, 0], [0, 0], {}
+    for name, want in golden.items():
+        got = by_file[idx[name]]
+        fs = fc = 0
+        for st, (c, _) in want.items():
+            stm[1] += 1
+            cnt[1] += c
+            if got.get(st):
+                stm[0] += 1
+                cnt[0] += min(c, got[st])
+                fs += 1
+                fc += min(c, got[st])
+        per_file[name] = ([fs, len(want)], [fc, sum(c for c, _ in want.values())])
+    return stm, cnt, per_file
+
+
+def load_fixture_names(path):
+    d = np.load(path)
+    return bytes(d["names"]).decode().split("\n")

@@ -57,6 +57,8 @@ def lib():
         L.orc_scan.restype = C.c_int
         L.orc_scan.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 3 + \
             [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_scan_ex.restype = C.c_int
+        L.orc_scan_ex.argtypes = L.orc_scan.argtypes + [C.c_uint32]
         L.orc_lcs.restype = C.c_int64
         L.orc_lcs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         L.orc_diff_pairs.restype = C.c_int
@@ -140,7 +142,7 @@ def method_string(ext: int, line: bytes) -> bytes:
     return out[:n].tobytes()
 
 
-def scan(arena, off, length, ext, grp, n_groups=1, events=True, line_hashes=False):
+def scan(arena, off, length, ext, grp, n_groups=1, events=True, line_hashes=False, rev_b=False):
     """Run the oracle over a packed corpus.  Returns a dict of numpy arrays."""
     n = len(length)
     arena = np.ascontiguousarray(arena, np.uint8)
@@ -154,8 +156,9 @@ def scan(arena, off, length, ext, grp, n_groups=1, events=True, line_hashes=Fals
     na, nh = C.c_int64(), C.c_int64()
     L = lib()
     # first pass counts events, second fills
-    rc = L.orc_scan(_p(arena), _p(off), _p(length), _p(ext), _p(grp), n, n_groups, _p(stats), _p(gc),
-                    _p(glob), None, 0, C.byref(na), None, 0, C.byref(nh), None, None)
+    fl = 8 if rev_b else 0
+    rc = L.orc_scan_ex(_p(arena), _p(off), _p(length), _p(ext), _p(grp), n, n_groups, _p(stats), _p(gc),
+                       _p(glob), None, 0, C.byref(na), None, 0, C.byref(nh), None, None, fl)
     if rc != 0:
         raise ValueError("orc_scan: malformed corpus")
     out = {"stats": stats, "group_counts": gc, "global_counts": glob}
@@ -165,8 +168,8 @@ def scan(arena, off, length, ext, grp, n_groups=1, events=True, line_hashes=Fals
         nl = int(stats["n_lines"].astype(np.int64).sum())
         lh = np.zeros(max(nl, 1), np.uint64) if line_hashes else None
         lb = np.zeros(n + 1, np.int64) if line_hashes else None
-        L.orc_scan(_p(arena), _p(off), _p(length), _p(ext), _p(grp), n, n_groups, _p(stats), _p(gc),
-                   _p(glob), _p(aev), aev.size, C.byref(na), _p(hev), hev.size, C.byref(nh), _p(lh), _p(lb))
+        L.orc_scan_ex(_p(arena), _p(off), _p(length), _p(ext), _p(grp), n, n_groups, _p(stats), _p(gc),
+                      _p(glob), _p(aev), aev.size, C.byref(na), _p(hev), hev.size, C.byref(nh), _p(lh), _p(lb), fl)
         out["assert_events"] = aev[:na.value]
         out["header_events"] = hev[:nh.value]
         if line_hashes:

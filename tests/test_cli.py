@@ -269,7 +269,10 @@ def test_scan_two_gpus_matches_one(tmp_path):
         assert out.returncode == 0, out.stderr
         outs.append((out.stdout, open(rows_p, "rb").read(), out.stderr.strip().split("\n")[-1]))
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
-    assert outs[0][2].replace("on 1 GPU(s)", "") == outs[1][2].replace("on 2 GPU(s)", "")
+    totals = [o[2].split(" on ")[0] for o in outs]           # "lines=.. assertion_lines=.. headers=.. fixture_headers=.."
+    assert totals[0] == totals[1] and "on 2 GPU(s)" in outs[1][2]
+    lo, hi = (int(x) for x in outs[1][2].split("shares ")[1].split(" bytes")[0].split(".."))
+    assert hi - lo <= (1 << 20) + 128                        # LPT: the shares differ by less than the largest file
 
 
 @pytest.mark.gpu

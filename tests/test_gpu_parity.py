@@ -309,3 +309,43 @@ def test_line_records_and_ngrams(scanner):
     check_line_records(scanner, ts.gen_corpus(0x7053454D0004, 300, 1, pinned=False), ngram=2)
     gb, gh, ge, gf = scanner.line_hashes(ts.pack([], []))
     assert gb.tolist() == [0] and len(gh) == 0
+
+
+def test_rev_b_mode_matches_the_oracle(scanner):
+    """TSM_SCAN_REV_B (docs/SPEC.md section 4b): second automaton word for the extra triggers, full statements, Rev-B
+    categories - every output against the oracle's Rev-B mode."""
+    fl = FLAGS | ts.SCAN_REV_B
+    def check(c):
+        want = orc.scan(c.arena, c.off, c.len, c.ext, c.grp, c.n_groups, rev_b=True)
+        got = scanner.scan(c, fl)
+        for f in ("n_lines", "n_assert", "n_headers", "n_fixture", "digest"):
+            bad = np.nonzero(got["stats"][f] != want["stats"][f])[0]
+            assert bad.size == 0, (f, bad[:10], got["stats"][bad[:5]], want["stats"][bad[:5]])
+        assert np.array_equal(got["group_counts"], want["group_counts"])
+        for k in ("assert_events", "header_events"):
+            a, b = got[k], want[k]
+            assert len(a) == len(b), (k, len(a), len(b))
+            for f in a.dtype.names:
+                bad = np.nonzero(a[f] != b[f])[0]
+                assert bad.size == 0, (k, f, a[bad[:5]], b[bad[:5]])
+        return got
+    body = (b"BOOST_AUTO_TEST_CASE(ZeroBit57) {\n  BOOST_CHECK_EQUAL(0xFF, x);\n  BOOST_CHECK(!left.full);\n  BOOST_CHECK(a == b); // c\n"
+            b"  NTA_CHECK(x > 3) << \"m\";\n  TESTEQUAL(a, b);\n  FAIL();\n  SLOPPY_CHECK_CLOSE(a, b);\n  assert (n == 1); // java style\n}\n")
+    files = [body, body * 300, b"x" * 4090 + b"_CHECK(\n" + body, b"FAIL", b"_CHEC\nK", b"y" * 8188 + b"TESTEQUAL(q)\n"]
+    files += [b"#" * pad + b"\n" + b"a_CHECK\nFAIL\n" * 1200 for pad in (0, 3, 7, 129)]
+    check(ts.pack(files, [2, 3, 2, 1, 2, 4, 2, 1, 4, 6]))
+    for seed in (71, 72):
+        f2, e2, g2 = cu.fuzz_corpus(seed, 300, 12000, long_lines=seed == 72)
+        check(ts.pack(f2, e2, g2, 5))
+    # golden G1 from the GPU's own events (the 26 bundled DeepSpeech files of the C1 fixture)
+    import json, os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    golden = json.load(open(os.path.join(gold, "g1_deepspeech.json")))
+    names = cu.load_fixture_names(os.path.join(gold, "c1_testfiles.npz"))
+    allf, exts, _, _ = cu.load_fixture(os.path.join(gold, "c1_testfiles.npz"))
+    keep = [i for i, n in enumerate(names) if n in golden]
+    sub = [allf[i] for i in keep]
+    got = check(ts.pack(sub, exts[keep]))
+    stm, cnt, per_file = cu.score_g1(golden, [names[i] for i in keep], sub, got["assert_events"])
+    assert stm == [72, 79] and cnt == [326, 427]
+    assert per_file["DeepSpeech/v0.9.3/native_client/kenlm/util/bit_packing_test.cc"] == ([1, 1], [6, 6])

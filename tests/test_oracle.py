@@ -323,3 +323,35 @@ def test_c1_fixture_reproduces_the_committed_summary():
     assert hz["fixture"]["files"] == 1779 and hz["hazard_fixture"]["non_utf8"] == 1 and hz["hazard_fixture"]["crlf_files"] == 5
     hfiles, _, _, _ = cu.load_fixture(os.path.join(GOLD, "c1_hazard_files.npz"))
     assert max(len(f) for f in hfiles) == 2501857 and sum(1 for f in hfiles if f and not f.endswith(b"\n")) == 115
+
+
+def test_rev_b_rules_and_golden_g1():
+    """docs/SPEC.md section 4b: the later revision of the lost tool, scored against the one version-matched count golden
+    (ML-Testing-v1.xlsx!DeepSpeech vs src/DeepSpeech/v0.9.3; the sheet rows ship as tests/golden/g1_deepspeech.json)."""
+    assert orc.lib().orc_is_assert_line_b(b"  BOOST_CHECK_EQUAL(a, b);", 26) and not orc.is_assert_line(b"  BOOST_CHECK_EQUAL(a, b);")
+    for line, ext, stmt, cat in [(b"  BOOST_CHECK_EQUAL(0xFF, x);", 2, b"BOOST_CHECK_EQUAL", "assertEqual"),
+                                 (b"  BOOST_CHECK(!left.full);", 2, b"BOOST_CHECK(!left.full);", "assertFalse"),
+                                 (b"  BOOST_CHECK(ref_state == test_state);", 2, b"BOOST_CHECK(ref_state == test_state);", "assertEqual"),
+                                 (b"  BOOST_CHECK(base.left.full);", 2, b"BOOST_CHECK(base.left.full);", ""),
+                                 (b"    assert (bufferSize > 0);", 4, b"assert (bufferSize > 0);", "assertGreater"),
+                                 (b"  assert(x);", 2, b"assert", "assertTrue"),
+                                 (b"  BOOST_CHECK_CLOSE(a, b, 0.1);", 2, b"BOOST_CHECK_CLOSE", ""),
+                                 (b"        self.assertEqual(a, b)", 1, b"self.assertEqual", "assertEqual")]:
+        arena, off, ln = orc.pack([line])
+        ev = orc.scan(arena, off, ln, np.array([ext], np.uint8), np.zeros(1, np.uint16), 1, rev_b=True)["assert_events"]
+        assert len(ev) == 1, line
+        e = ev[0]
+        assert line[e["stmt_off"]:e["stmt_off"] + e["stmt_len"]] == stmt and orc.category_name(int(e["cat"])) == cat, (line, e)
+    golden = json.load(open(os.path.join(GOLD, "g1_deepspeech.json")))
+    names = cu.load_fixture_names(os.path.join(GOLD, "c1_testfiles.npz"))
+    files, exts, grps, n_groups = cu.load_fixture(os.path.join(GOLD, "c1_testfiles.npz"))
+    keep = [i for i, n in enumerate(names) if n in golden]
+    assert len(keep) == 26
+    sub = [files[i] for i in keep]
+    arena, off, ln = orc.pack(sub)
+    ev = orc.scan(arena, off, ln, exts[keep], np.zeros(len(keep), np.uint16), 1, rev_b=True)["assert_events"]
+    stm, cnt, per_file = cu.score_g1(golden, [names[i] for i in keep], sub, ev)
+    assert stm == [72, 79] and cnt == [326, 427], (stm, cnt)              # canonical Rev A: 15 / 79 and 34 / 427 (ledger)
+    assert per_file["DeepSpeech/v0.9.3/native_client/kenlm/util/bit_packing_test.cc"] == ([1, 1], [6, 6])   # BOOST_CHECK_EQUAL x 1, 1, 2, 2
+    led = json.load(open(os.path.join(GOLD, "ledger.json")))["G1"]["rev_b"]
+    assert led["sheet_statements_found"] == stm and led["assertion_count_recall"] == cnt

@@ -13,6 +13,7 @@ Outputs (all committed, all small):
   tests/golden/c1_summary.json              oracle totals over the bundled corpus src/ (config C1)
   tests/golden/c1_testfiles.npz             the C1 test files themselves (real bytes for the GPU box)
   tests/golden/c1_hazard_files.npz          the hazard files of SURVEY.md section 8d outside that subset
+  tests/golden/g1_deepspeech.json           G1: the rows (statement -> count, category) of ML-Testing-v1.xlsx!DeepSpeech for the bundled files
   tests/golden/ledger.json                  reproduction rates of every golden (the parity ledger)
 
 xlsx files are read with zipfile + ElementTree (no openpyxl in the image).
@@ -182,12 +183,51 @@ def ledger_g1(v1, ledger):
             if g:
                 stm_hit += 1
                 cnt_hit += min(c, g)
-    ledger["G1"] = {"source": "ML-Testing-v1.xlsx!DeepSpeech (Rev-B sheet) vs src/DeepSpeech/v0.9.3",
+    # ---- the same sheet scored with the Rev-B mode of the oracle (docs/SPEC.md section 4b), and the sheet rows of the bundled
+    #      files as a fixture (tests/golden/g1_deepspeech.json) so that the GPU box can score the CUDA path against G1
+    fixture, b_stm = {}, [0, 0]
+    b_cnt, b_cat = [0, 0], [0, 0]
+    cats = collections.defaultdict(dict)
+    for _, r in v1["DeepSpeech"][1:]:
+        if len(r) >= 7:
+            cats[r[0]][r[4]] = r[6]
+    per_file = {}
+    for f, want in sorted(by.items()):
+        p = os.path.join(root, f)
+        if not os.path.exists(p):
+            continue
+        data = open(p, "rb").read()
+        ext = EXT_TAG.get(f.rsplit(".", 1)[-1], 0)
+        arena, off, ln = orc.pack([data])
+        res = orc.scan(arena, off, ln, np.array([ext], np.uint8), np.zeros(1, np.uint16), 1, rev_b=True)
+        got, gcat = collections.Counter(), {}
+        for e in res["assert_events"]:
+            st = data[e["stmt_off"]:e["stmt_off"] + e["stmt_len"]].decode("latin-1")
+            got[st] += 1
+            gcat[st] = orc.category_name(int(e["cat"])) if e["cat"] != 127 else data[e["ident_off"]:e["ident_off"] + e["ident_len"]].decode("latin-1")
+        fixture["DeepSpeech/v0.9.3/" + f] = {st: [c, cats[f][st]] for st, c in want.items()}
+        fs = fc = 0
+        for st, c in want.items():
+            b_stm[1] += 1
+            b_cnt[1] += c
+            if got.get(st):
+                b_stm[0] += 1
+                b_cnt[0] += min(c, got[st])
+                fs += 1
+                fc += min(c, got[st])
+                b_cat[1] += 1
+                b_cat[0] += gcat[st] == cats[f][st]
+        per_file[f] = {"statements": [fs, len(want)], "counts": [fc, sum(want.values())]}
+    json.dump(fixture, open(os.path.join(OUT, "g1_deepspeech.json"), "w"), indent=0, sort_keys=True)
+    assert per_file["native_client/kenlm/util/bit_packing_test.cc"] == {"statements": [1, 1], "counts": [6, 6]}
+    ledger["G1"] = {"rev_b": {"rule": "docs/SPEC.md section 4b", "sheet_statements_found": b_stm, "assertion_count_recall": b_cnt,
+                              "category_agreement_on_found_statements": b_cat, "per_file": per_file},
+                    "source": "ML-Testing-v1.xlsx!DeepSpeech (Rev-B sheet) vs src/DeepSpeech/v0.9.3",
                     "files_in_bundle": [files, len(by)],
                     "sheet_statements_found_as_truncated_or_full_line": [stm_hit, stm_tot],
                     "assertion_count_recall": [cnt_hit, cnt_tot],
-                    "note": "Rev B also triggers on BOOST_CHECK*/NTA_CHECK/TESTEQUAL/FAIL; canonical Rev A does not"}
-    print("G1", stm_hit, stm_tot, cnt_hit, cnt_tot)
+                    "note": "the two lists above are canonical Rev A scored on the Rev-B sheet; Rev B also triggers on _CHECK / TESTEQUAL / FAIL"}
+    print("G1 rev A", stm_hit, stm_tot, cnt_hit, cnt_tot, "| rev B", b_stm, b_cnt, "category", b_cat)
 
 
 # Error_Type values merged into one strategy row.  Not written down anywhere in the package: recovered by exhaustive

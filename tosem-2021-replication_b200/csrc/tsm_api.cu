@@ -163,6 +163,14 @@ static void build_lut(uint32_t* lut) {                   // the automaton table 
     }
 }
 
+static void build_lut_b(uint32_t* lut) {                 // Rev-B triggers (tsm_scan_walk.cuh, docs/SPEC.md section 4b)
+  struct Pat { const char* s; int first; };
+  static const Pat pats[] = {{"_CHECK", 0}, {"TESTEQUAL", 6}, {"FAIL", 15}};
+  memset(lut, 0, 256 * sizeof(uint32_t));
+  for (const Pat& p : pats)
+    for (int k = 0; p.s[k]; ++k) lut[(unsigned char)p.s[k]] |= 1u << (p.first + k);
+}
+
 static void build_elut(uint32_t* lut) {                  // operator patterns of SPEC section 6 rule 2
   struct Pat { const char* s; int first; };
   static const Pat pats[] = {{" not ", 0}, {" in ", 5}, {" is not ", 9}, {"True", 17}, {"==", 21}, {"!=", 23},
@@ -246,15 +254,18 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
     static const uint8_t slot[TSM_CAT_SLOTS] = TSM_CAT_SLOT_INIT;
     static const uint16_t offs[TSM_CAT_NAMED + 1] = TSM_CAT_OFF_INIT;
     static const char blob[] = TSM_CAT_BLOB_INIT;
-    uint32_t elut[256];
+    uint32_t elut[256], lutb[256];
     build_elut(elut);
+    build_lut_b(lutb);
     if (cudaMemcpyToSymbol(c_lut, lut, sizeof lut) != cudaSuccess ||
         cudaMemcpyToSymbol(c_elut, elut, sizeof elut) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_slot, slot, sizeof slot) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_off, offs, sizeof offs) != cudaSuccess ||
         cudaMemcpyToSymbol(c_cat_blob, blob, TSM_CAT_BLOB_LEN + 1) != cudaSuccess ||
         cudaMemset(c->d_arena, 0, (size_t)c->max_arena + 4096) != cudaSuccess ||
-        cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess)
+        cudaMemcpyToSymbol(c_lut_b, lutb, sizeof lutb) != cudaSuccess ||
+        cudaFuncSetAttribute(k_scan_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_scan_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess)
       rc = TSM_E_CUDA;
   }
   if (rc != TSM_OK) {
@@ -374,7 +385,8 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       k_plan<<<(f1 - f0 + 255) / 256, 256, 0, st>>>(p);
       CU(cudaGetLastError());
       if (s == 0 && n_slabs == 1) CU(cudaEventRecord(ev[1], st));
-      k_scan<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+      if (flags & TSM_SCAN_REV_B) k_scan_t<true><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+      else k_scan_t<false><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
       CU(cudaGetLastError());
     }
     if (n_slabs > 1) CU(cudaEventRecord(ev[1], st));      // per-kernel split is only meaningful for one slab
@@ -402,7 +414,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
 
 extern "C" int tsm_scan_resident(tsm_ctx* c, uint32_t flags, void* stream) {
   if (!c) return TSM_E_ARG;
-  flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS;
+  flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS | TSM_SCAN_REV_B;
   if (!c->resident) return TSM_E_STATE;
   CU(cudaSetDevice(c->device));
   return launch_scan(c, flags, (cudaStream_t)stream, nullptr);
@@ -479,7 +491,7 @@ extern "C" int tsm_scan(tsm_ctx* c, const tsm_corpus* k, tsm_result* r, uint32_t
   if (!c || !r) return TSM_E_ARG;
   int rc = check_corpus(c, k);
   if (rc != TSM_OK) return rc;
-  flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS;
+  flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS | TSM_SCAN_REV_B;
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t n = k->n_files;
@@ -632,7 +644,7 @@ int side_records(tsm_ctx* c, HostSide& h, cudaStream_t st, float* scan_ms) {
     CU(cudaMemsetAsync(h.zero.p, 0, zero_bytes, st));
     k_plan_det<<<(n + 1 + 255) / 256, 256, 0, st>>>(p, h.unit_first.as<unsigned long long>());
     CU(cudaEventRecord(c->diff_ev[0], st));
-    k_scan<<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+    k_scan_t<false><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
     CU(cudaEventRecord(c->diff_ev[1], st));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&hc, p.ctrl, sizeof hc, cudaMemcpyDeviceToHost, st));

@@ -15,6 +15,7 @@
 namespace tsm {
 
 __constant__ uint32_t c_lut[256];                       // automaton table (tsm_device.cuh; built by tsm_create)
+__constant__ uint32_t c_lut_b[256];                     // Rev-B trigger table (tsm_scan_walk.cuh)
 __constant__ uint32_t c_elut[256];                      // bare-assert operator automaton (k_classify)
 // category tables: read once per block of k_classify into shared memory (coalesced, hence plain device memory)
 __device__ uint8_t c_cat_slot[TSM_CAT_SLOTS];            // perfect hash slot -> category id
@@ -349,8 +350,9 @@ __device__ __forceinline__ int stem_lookup(FileBytes& rd, uint32_t s, uint32_t n
 // operator patterns (table built in tsm_api.cu), 8 bytes per step:
 //  " not " 0-4 | " in " 5-8 | " is not " 9-16 | "True" 17-20 | "==" 21-22 | "!=" 23-24 | "<=" 25-26 |
 //  ">=" 27-28 | "<" 29 | ">" 30   (final bits 4, 8, 16, 20, 22, 24, 26, 28, 29, 30)
-__device__ __forceinline__ int bare_assert_category(FileBytes& rd, uint32_t e0, uint32_t en, const uint32_t* elut) {
-  if (en >= 4 && (uint32_t)rd.get8(e0) == 0x20746F6Eu) return 2;        // "not "
+__device__ __forceinline__ int bare_assert_category(FileBytes& rd, uint32_t e0, uint32_t en, const uint32_t* elut, int deflt = 3,
+                                                    bool not_prefix = true) {
+  if (not_prefix && en >= 4 && (uint32_t)rd.get8(e0) == 0x20746F6Eu) return 2;        // "not "
   uint32_t D = 0, A = 0;
   for (uint32_t a = 0; a < en; a += 8) {                 // bytes behind the end become zeros (match nothing)
     unsigned long long w = rd.get8(e0 + a);
@@ -369,7 +371,15 @@ __device__ __forceinline__ int bare_assert_category(FileBytes& rd, uint32_t e0, 
   if (A & (1u << 28)) return 6;                          // >=
   if (A & (1u << 29)) return 7;                          // <
   if (A & (1u << 30)) return 5;                          // >
-  return 3;
+  return deflt;
+}
+
+// Is the identifier [s, s + n) of the file the name `name` (Rev-B rules, docs/SPEC.md section 4b; rare path)?
+__device__ __noinline__ bool ident_eq(FileBytes& rd, uint32_t s, uint32_t n, const char* name, uint32_t len) {
+  if (n != len) return false;
+  for (uint32_t k = 0; k < len; ++k)
+    if (rd.get(s + k) != (uint8_t)name[k]) return false;
+  return true;
 }
 
 constexpr uint32_t BQ_CAP = 1024;                        // bare-assert expressions a block of k_classify defers (16 B each)
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     }
   };
   const uint32_t n = min(p.ctrl->n_cand, p.cand_cap);
-  const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0;
+  const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0, revb = (p.flags & TSM_SCAN_REV_B) != 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long cd = p.cand[i];
     const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
@@ -430,22 +440,44 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     while (last > t0 && (cls[rd.get(last - 1)] & CC_W)) --last;
     uint32_t Ls = last;
     while (Ls > t0 && (cls[rd.get(Ls - 1)] & CC_IDENT)) --Ls;
-    const uint32_t tlen = last - t0, Ln = last - Ls;
+    uint32_t tlen = last - t0;                           // (Rev B may lengthen the statement of the event; the rules see Rev A's)
+    const uint32_t tlen_a = tlen, Ln = last - Ls;
     // ---- category (SPEC section 6), first match wins
     int cat = 0;
     bool done = false;
     uint32_t def_e0 = 0, def_en = 0;                     // def_en != 0: category decided by the deferred operator pass
+    if (revb) {                                          // ---- Rev B (SPEC section 4b): one more stem, the bare forms by their operators, full statements
+      const bool macro = ident_eq(rd, Ls, Ln, "BOOST_CHECK", 11) || ident_eq(rd, Ls, Ln, "NTA_CHECK", 9);
+      const bool bare6 = tlen == 6 && low_bytes(rd.get8(t0), 6) == 0x747265737361ull;
+      const bool full = macro || p.ext[f] == TSM_EXT_JAVA;
+      uint32_t fe = last;                                // end of the stripped line
+      if (full || ((macro || bare6) && stop < size && rd.get(stop) == '(')) {
+        uint32_t le = stop;
+        while (le < size && rd.get(le) != '\n') ++le;
+        fe = le;
+        while (fe > t0 && (cls[rd.get(fe - 1)] & CC_W)) --fe;
+      }
+      if (ident_eq(rd, Ls, Ln, "BOOST_CHECK_EQUAL", 17)) { cat = 1; done = true; }
+      else if ((macro || bare6) && stop < size && rd.get(stop) == '(') {
+        uint32_t x = stop + 1;
+        while (x < fe && (cls[rd.get(x)] & CC_W)) ++x;
+        if (x < fe && rd.get(x) == '!' && !(x + 1 < fe && rd.get(x + 1) == '=')) cat = 4;
+        else cat = bare_assert_category(rd, x, fe > x ? fe - x : 0u, elut, macro ? 0 : 3, false);
+        done = true;
+      }
+      if (full) tlen = fe - t0;                          // the event carries the Rev-B statement (the rules above used Rev A's T)
+    }
     if (Ln >= 7) {                                       // rule 1: EXPECT_x / ASSERT_x
       const unsigned long long h7 = low_bytes(rd.get8(Ls), 7);
       if (h7 == 0x5F544345505845ull || h7 == 0x5F545245535341ull) { cat = stem_lookup(rd, Ls + 7, Ln - 7); done = true; }
     }
-    if (!done && tlen >= 6) {                            // rule 2: T == "assert" or T starts with "assert "
+    if (!done && tlen_a >= 6) {                          // rule 2: T == "assert" or T starts with "assert "
       const unsigned long long h = rd.get8(t0);
       const bool a6 = low_bytes(h, 6) == 0x747265737361ull;
-      if (a6 && tlen == 6) { cat = 3; done = true; }
-      else if (a6 && tlen >= 8 && ((h >> 48) & 0xFF) == 0x20) {
+      if (a6 && tlen_a == 6) { cat = 3; done = true; }
+      else if (a6 && tlen_a >= 8 && ((h >> 48) & 0xFF) == 0x20) {
         done = true;
-        def_e0 = t0 + 7; def_en = tlen - 7;              // e = T[7:]: the operator pass runs later, with every lane busy
+        def_e0 = t0 + 7; def_en = tlen_a - 7;            // e = T[7:]: the operator pass runs later, with every lane busy
       }
     }
     if (!done && Ln >= 6) {                              // rules 3-5 on L

@@ -54,7 +54,8 @@ constexpr uint32_t O2_CTL = O2_Q + Q2_CAP * 2;           // u32 queue length, pa
 constexpr uint32_t WARP_SMEM2 = ((O2_CTL + 16 + 127) / 128) * 128;
 // per CTA in front of the warps: automaton table (1 KB), per-language masks + the opaque 4 (128 B), rotations of '\n' (61 x 8 B)
 constexpr uint32_t O2_T0A = LUT_BYTES;
-constexpr uint32_t CTA_BYTES2 = LUT_BYTES + 512;
+constexpr uint32_t O2_LUTB = LUT_BYTES + 512;            // Rev-B trigger table (TSM_SCAN_REV_B): 256 x u32
+constexpr uint32_t CTA_BYTES2 = LUT_BYTES + 512 + 1024;
 constexpr uint32_t SCAN2_SMEM = CTA_BYTES2 + SCAN2_WARPS * WARP_SMEM2;
 static_assert(O2_RW % 8 == 0 && O2_WENT % 8 == 0 && O2_LTAB % 2 == 0 && O2_BASE % 8 == 0 && O2_Q % 4 == 0 && O2_CTL % 8 == 0, "alignment");
 static_assert(SCAN2_CTAS_PER_SM * SCAN2_SMEM <= 232448, "shared memory per SM");
@@ -62,37 +63,58 @@ static_assert(SCAN2_CTAS_PER_SM * SCAN2_SMEM <= 232448, "shared memory per SM");
 // OR is the line's), 14 = the word is mixed, 15 = no newline: the unterminated last line of a file
 constexpr uint32_t LR_POS = 0x1FFFu, LR_FIRST = 0x2000u, LR_MIXED = 0x4000u, LR_VIRT = 0x8000u;
 
+// Rev-B triggers (docs/SPEC.md section 4b; second automaton word, only in the TSM_SCAN_REV_B instantiation):
+//   bits 0..5 `_CHECK`   bits 6..14 `TESTEQUAL`   bits 15..18 `FAIL`
+constexpr uint32_t B2_FIRST = (1u << 0) | (1u << 6) | (1u << 15), B2_FIN = (1u << 5) | (1u << 14) | (1u << 18);
+constexpr uint32_t REVB_BIT = 1u;                        // in the stored ORs: bit 0 (a non-final state of `assert`) = "a Rev-B trigger ended"
+
 // Table entry of byte `idx`.  The address is formed by an integer multiply-add whose factor (4) the compiler
 // cannot see: IMAD runs on the FMA pipe, the LEA it replaces on the ALU pipe.
 #ifndef TSM_PIPE_BALANCE
 #define TSM_PIPE_BALANCE 1
 #endif
-__device__ __forceinline__ uint32_t lut_at(uint32_t idx, uint32_t four) {
+template <bool REVB>
+__device__ __forceinline__ void lut_at(uint32_t idx, uint32_t four, uint32_t& v, uint32_t& v2) {
 #if TSM_PIPE_BALANCE
-  uint32_t addr, v;
+  uint32_t addr;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(idx), "r"(four), "r"(smem_u32(scan_lut())));
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
+  if (REVB) asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v2) : "r"(addr), "n"(O2_LUTB));
 #else
   (void)four;
-  return scan_lut()[idx];
+  v = scan_lut()[idx];
+  if (REVB) v2 = scan_lut()[O2_LUTB / 4 + idx];
 #endif
 }
 __device__ __forceinline__ uint32_t opaque_four() { return scan_lut()[256 + 12]; }   // written by the kernel prologue from a launch parameter
 
+struct Auto { uint32_t D, D2; };                         // automaton state (D2: the Rev-B word, unused otherwise)
+
+// One automaton step; returns the states that count for the OR of a line (Rev-B: bit 0 = a Rev-B trigger ended).
+template <bool REVB>
+__device__ __forceinline__ uint32_t step1(Auto& a, uint32_t byte, uint32_t four) {
+  uint32_t m, m2 = 0;
+  lut_at<REVB>(byte, four, m, m2);
+  a.D = ((a.D + a.D) | B_FIRST) & m;
+  if (!REVB) return a.D;
+  a.D2 = ((a.D2 + a.D2) | B2_FIRST) & m2;
+  return (a.D & ~REVB_BIT) | ((a.D2 & B2_FIN) ? REVB_BIT : 0u);
+}
+
 // Eight automaton steps over one 8-byte word; A collects every state of the word.
-__device__ __forceinline__ void step8b(unsigned long long w, uint32_t& D, uint32_t& A, uint32_t four) {
+template <bool REVB>
+__device__ __forceinline__ void step8b(unsigned long long w, Auto& a, uint32_t& A, uint32_t four) {
   const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  uint32_t A2 = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | B_FIRST) & lut_at(__byte_perm(lo, 0, 0x4440 + k), four);
-    A |= D;
+  for (int k = 0; k < 8; ++k) {
+    uint32_t m, m2 = 0;
+    lut_at<REVB>(__byte_perm(k < 4 ? lo : hi, 0, 0x4440 + (k & 3)), four, m, m2);
+    a.D = ((a.D + a.D) | B_FIRST) & m;
+    A |= a.D;
+    if (REVB) { a.D2 = ((a.D2 + a.D2) | B2_FIRST) & m2; A2 |= a.D2; }
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    D = ((D + D) | B_FIRST) & lut_at(__byte_perm(hi, 0, 0x4440 + k), four);
-    A |= D;
-  }
+  if (REVB) A = (A & ~REVB_BIT) | ((A2 & B2_FIN) ? REVB_BIT : 0u);
 }
 
 __device__ __forceinline__ uint32_t nl8_of(unsigned long long w) {       // bit b = byte b of w is '\n'
@@ -109,16 +131,17 @@ struct WalkOut { uint32_t nlw, tail; };                  // bit k: word k of the
 // lengths are; the bytes outside the chunk's staged range are zeros).  Per word: 8 automaton steps, the
 // Mersenne-61 running prefix R_k = R_{k-1} * 2^-64 + w_k, one store of the running OR.  Then one warp scan
 // turns the stripe totals into the absolute hash prefix at every stripe start.
+template <bool REVB>
 __device__ __noinline__ WalkOut walk2(uint8_t* wb, uint32_t fin, int lane) {
   const uint32_t pos0 = (uint32_t)lane * STRIPE;
   const uint8_t* sp = wb + pos0;
   uint32_t* ar = reinterpret_cast<uint32_t*>(wb + O2_ARUN) + (uint32_t)lane * 17u;
   unsigned long long* rw = reinterpret_cast<unsigned long long*>(wb + O2_RW) + (uint32_t)lane * RW2_PER_STRIPE;
   const uint32_t four = opaque_four();
-  uint32_t D = 0;
-  if (lane) {                                            // state in front of the stripe (no pattern is longer than 7 bytes)
-    uint32_t A = 0;
-    step8b(*reinterpret_cast<const unsigned long long*>(sp - 8), D, A, four);
+  Auto au{0u, 0u};
+  if (lane) {                                            // state in front of the stripe: no state looks back more than 8 bytes
+    uint32_t A = 0;                                      // (the longest pattern, Rev B's TESTEQUAL, has 9)
+    step8b<REVB>(*reinterpret_cast<const unsigned long long*>(sp - 8), au, A, four);
   }
   unsigned long long R = 0;
   uint32_t run = 0, nlr = 0;                             // nlr: newline-word bits, the newest word in bit 0
@@ -129,7 +152,7 @@ __device__ __noinline__ WalkOut walk2(uint8_t* wb, uint32_t fin, int lane) {
       if (g == 4 && k) break;
       const unsigned long long w = *reinterpret_cast<const unsigned long long*>(sp + 32u * g + 8u * k);
       uint32_t A = 0;
-      step8b(w, D, A, four);
+      step8b<REVB>(w, au, A, four);
       R = ror3_61(R) + fold61(w);                        // lazily reduced: stays below 2^63
       if (((k + 1u) & ((1u << RW2_SHIFT) - 1u)) == 0u && g < 4u) rw[(4u * g + k) >> RW2_SHIFT] = R;   // (not behind the 17th word)
       ar[4u * g + k] = run;
@@ -160,19 +183,21 @@ __device__ __noinline__ WalkOut walk2(uint8_t* wb, uint32_t fin, int lane) {
 // A mixed word (newline + pattern end), byte by byte: the states in front of its first newline belong to the
 // line that ends there (word entry i), the states behind its last newline to the line that ends at the next
 // entry.  Lines inside the word are walked by the finish pass itself (LR_MIXED asks for it).
+template <bool REVB>
 __device__ __noinline__ void resolve_mixed(uint8_t* wb, uint32_t g, uint32_t i, uint32_t n_went) {
-  const uint32_t* lut = scan_lut();
-  uint32_t D = 0, A = 0;
-  step8b(*reinterpret_cast<const unsigned long long*>(wb + 8u * g - 8u), D, A, opaque_four());   // g >= 2: the first 16 bytes are zeros
+  const uint32_t four = opaque_four();
+  Auto au{0u, 0u};
+  uint32_t A = 0;
+  step8b<REVB>(*reinterpret_cast<const unsigned long long*>(wb + 8u * g - 8u), au, A, four);   // g >= 2: the first 16 bytes are zeros
   unsigned long long w = *reinterpret_cast<const unsigned long long*>(wb + 8u * g);
   uint32_t pre = 0, post = 0, seen = 0;
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
-    D = ((D + D) | B_FIRST) & lut[(uint32_t)w & 0xFFu];
-    const uint32_t m = (uint32_t)((int32_t)D >> 31);     // all ones at a newline
-    pre |= D & ~seen;
+    const uint32_t d = step1<REVB>(au, (uint32_t)w & 0xFFu, four);
+    const uint32_t m = (uint32_t)((int32_t)au.D >> 31);  // all ones at a newline
+    pre |= d & ~seen;
     seen |= m;
-    post = (post | D) & ~m;
+    post = (post | d) & ~m;
     w >>= 8;
   }
   uint32_t* arun = reinterpret_cast<uint32_t*>(wb + O2_ARUN);
@@ -208,9 +233,10 @@ __device__ __noinline__ bool starts_with8(SmemByte lb, uint32_t s, uint32_t e, u
 }
 
 // Flags of a finished line (SPEC sections 4 / 5) from the OR of its automaton states; adds it to the per-file counters.
+template <bool REVB>
 __device__ __forceinline__ uint32_t line_flags2(uint32_t s, uint32_t e, uint32_t A, uint32_t g1, uint32_t g2, int ext, SmemByte lb, Accum& ac) {
   if (ext == 0) return 0;
-  uint32_t fl = (A & (AF_ASSERT | AF_EXPECT)) ? LF_CAND : 0;
+  uint32_t fl = (A & (AF_ASSERT | AF_EXPECT | (REVB ? REVB_BIT : 0u))) ? LF_CAND : 0;
   bool hdr;
   if (ext == TSM_EXT_PY) {
     hdr = (A & g1) != 0;
@@ -225,6 +251,19 @@ __device__ __forceinline__ uint32_t line_flags2(uint32_t s, uint32_t e, uint32_t
   return fl;
 }
 
+// Does the line [s, e) of a file in HBM hold a Rev-B trigger (docs/SPEC.md section 4b)?  Slow path of long lines only.
+__device__ __noinline__ bool revb_trigger_gmem(const uint8_t* g, uint32_t s, uint32_t e) {
+  const char* const pats[3] = {"_CHECK", "TESTEQUAL", "FAIL"};
+  const uint32_t lens[3] = {6, 9, 4};
+  for (int t = 0; t < 3; ++t)
+    for (uint32_t i = s; i + lens[t] <= e; ++i) {
+      uint32_t k = 0;
+      while (k < lens[t] && __ldg(g + i + k) == (uint8_t)pats[t][k]) ++k;
+      if (k == lens[t]) return true;
+    }
+  return false;
+}
+
 struct FinishState {                                     // carried from one window of line records to the next
   uint32_t prev_last;                                    // newline in front of the next line
   unsigned long long prevP;                              // hash prefix of the bytes [0, prev_last]
@@ -236,6 +275,7 @@ struct FinishState {                                     // carried from one win
 // newline in front of it, which is the neighbour lane's.  A line belongs to the chunk its first byte lies in
 // (start < lim).  The starts of the assertion lines are compacted (u16 each) over the records already consumed
 // and go to the global candidate list at the end of the window.
+template <bool REVB>
 __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, const uint32_t* lc, uint32_t n, uint32_t lim,
                                            bool skip_first, uint32_t f, uint32_t cb, int ext, int lane, Accum& ac, FinishState& fs) {
   uint16_t* ltab = reinterpret_cast<uint16_t*>(wb + O2_LTAB);
@@ -296,11 +336,11 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
       uint32_t A = 0;
       if (rec & LR_FIRST) A = arun[isv ? SLOT_TAIL : g];
       else if (rec & LR_MIXED) {                         // a line inside a mixed word: its own states
-        const uint32_t* lut = scan_lut();
-        uint32_t D = 0;
-        for (uint32_t q = s; q < e; ++q) { D = ((D + D) | B_FIRST) & lut[lb(q)]; A |= D; }
+        Auto au{0u, 0u};
+        const uint32_t four = opaque_four();
+        for (uint32_t q = s; q < e; ++q) A |= step1<REVB>(au, lb(q), four);
       }
-      fl = line_flags2(s, e, A, g1, g2, ext, lb, a);
+      fl = line_flags2<REVB>(s, e, A, g1, g2, ext, lb, a);
       if (want_hev && (fl & LF_HDR)) emit_header(p, f, cb + s - PRE, e - s, fl);
     }
     if (want_lh) {                                       // the line's record, in line order inside the chunk's region
@@ -334,6 +374,7 @@ __device__ __noinline__ void finish_lines2(const ScanParams& p, uint8_t* wb, con
   fs.lh_done = lh_done;
 }
 
+template <bool REVB>
 __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32_t* lc, uint8_t* wb, uint32_t uslot, uint32_t f,
                                                uint32_t cb, uint32_t fo, uint32_t size, int ext, int lane) {
   const uint32_t ce = min(cb + CH, size);
@@ -353,7 +394,7 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   }
   if (lane == 0) *reinterpret_cast<uint32_t*>(wb + O2_CTL) = 0u;
   __syncwarp();
-  const WalkOut wo = walk2(wb, lc[0], lane);
+  const WalkOut wo = walk2<REVB>(wb, lc[0], lane);
   // ---- newline words behind the owned bytes: only the first one matters (it ends the last owned line)
   const uint32_t w0 = 17u * (uint32_t)lane, lim_w = (lim + 7u) >> 3;
   const uint32_t ownbits = lim_w <= w0 ? 0u : (lim_w - w0 >= 17u ? 0x1FFFFu : (1u << (lim_w - w0)) - 1u);
@@ -397,7 +438,7 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
         const uint32_t m = __shfl_sync(0xffffffffu, kept, (int)l), eb = __shfl_sync(0xffffffffu, ebase, (int)l);
         const bool act = t < nq_all && ((m >> k) & 1u);
         const uint32_t i = eb + __popc(m & ((1u << k) - 1u));
-        if (act) resolve_mixed(wb, g, i, n_went);
+        if (act) resolve_mixed<REVB>(wb, g, i, n_went);
         __syncwarp();
         if (act) went[i] |= 0x8000u;
         __syncwarp();
@@ -405,7 +446,7 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
     } else if (lc[0]) {                                  // queue overflow: take every newline word as mixed
       for (uint32_t base = 0; base < n_went; base += 32) {
         const uint32_t i = base + (uint32_t)lane;
-        if (i < n_went) resolve_mixed(wb, (uint32_t)went[i] & 0x3FFu, i, n_went);
+        if (i < n_went) resolve_mixed<REVB>(wb, (uint32_t)went[i] & 0x3FFu, i, n_went);
         __syncwarp();
         if (i < n_went) went[i] |= 0x8000u;
         __syncwarp();
@@ -457,7 +498,7 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
     n_rec += __shfl_sync(0xffffffffu, in2, 31);
     __syncwarp();
     if (n_rec + 256u > LCAP && base + 32u < n_went) {    // the next round may not fit: finish what is there
-      finish_lines2(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
+      finish_lines2<REVB>(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
       n_rec = 0;
     }
   }
@@ -470,11 +511,21 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
     } else tail_long = true;
   }
   __syncwarp();
-  if (n_rec) finish_lines2(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
+  if (n_rec) finish_lines2<REVB>(p, wb, lc, n_rec, lim, skip_first, f, cb, ext, lane, ac, fs);
   if (tail_long && lane == 0) {
     const unsigned long long d0 = ac.digest;
     uint32_t fl = 0;
-    const uint32_t e = long_line(p, scan_lut(), B_FIRST, f, fo, size, ext, cb + tail_start - PRE, ac, &fl);
+    const uint32_t ls = cb + tail_start - PRE;
+    const uint32_t e = long_line(p, scan_lut(), B_FIRST, f, fo, size, ext, ls, ac, &fl);
+    if (REVB && ext != 0 && !(fl & LF_CAND) && revb_trigger_gmem(p.arena + fo, ls, e)) {   // Rev-B triggers of a long line: plain search in HBM
+      fl |= LF_CAND;
+      ac.asserts++;
+      if (p.cand_cap) {
+        const uint32_t slot = atomicAdd(&p.ctrl->n_cand, 1u);
+        if (slot < p.cand_cap) p.cand[slot] = ((unsigned long long)f << 32) | ls;
+        else p.ctrl->overflow = 1;
+      }
+    }
     if (want_lh) {                                       // the chunk's last line
       const uint32_t slot = fs.lh_base + fs.lh_done;
       if (slot < p.lh_cap) { p.lh_hash[slot] = ac.digest - d0; p.lh_end[slot] = e; p.lh_flag[slot] = (uint8_t)(fl & LF_CAND); }
@@ -508,17 +559,19 @@ __device__ __forceinline__ void process_chunk2(const ScanParams& p, const uint32
   }
 }
 
-__global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan(ScanParams p) {
+template <bool REVB>
+__global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan_t(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t* lut_all = reinterpret_cast<uint32_t*>(smem);  // [0,256) the automaton table, then 3 x 4 per-language masks, the opaque 4
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[i] = c_lut[i];
   if (threadIdx.x < 12) {                                // per language (PY, C family, none): pattern ends that count, then the header groups
     const int t = threadIdx.x, lang = t >> 2, q = t & 3;
     const uint32_t g1 = lang == 0 ? PY_G1 : CJ_G1, g2 = lang == 0 ? PY_G2 : CJ_G2;
-    const uint32_t v = q == 0 ? (AF_ASSERT | AF_EXPECT | g1 | g2 | B_F) : (q == 1 ? g1 : (q == 2 ? g2 : 0u));
+    const uint32_t v = q == 0 ? (AF_ASSERT | AF_EXPECT | g1 | g2 | B_F | (REVB ? REVB_BIT : 0u)) : (q == 1 ? g1 : (q == 2 ? g2 : 0u));
     lut_all[256 + t] = lang == 2 ? 0u : v;
   }
   if (threadIdx.x == 12) lut_all[256 + 12] = p.four;
+  if (REVB) for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_all[O2_LUTB / 4 + i] = c_lut_b[i];
   if (threadIdx.x >= 32 && threadIdx.x < 32 + 61)        // rotations of the newline byte: 0x0A * 2^r mod 2^61-1
     reinterpret_cast<unsigned long long*>(smem + O2_T0A)[threadIdx.x - 32] = rotl61(0x0Aull, threadIdx.x - 32);
   __syncthreads();
@@ -546,10 +599,14 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, SCAN2_CTAS_PER_SM) k_scan(Sc
     while (!mbar_try_wait(bar, phase)) {}
     phase ^= 1;
     const uint32_t lang = cur.ext == 0 ? 2u : (cur.ext == TSM_EXT_PY ? 0u : 1u);
-    process_chunk2(p, lut_all + 256u + 4u * lang, wb, p.unit_base + cur.u, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
+    process_chunk2<REVB>(p, lut_all + 256u + 4u * lang, wb, p.unit_base + cur.u, cur.f, cur.cb, cur.fo, cur.size, cur.ext, lane);
     __syncwarp();
     cur = nxt;
   }
 }
+
+// The two instantiations: canonical Rev A (the hot path, what bench.py times) and Rev B (TSM_SCAN_REV_B).
+template __global__ void k_scan_t<false>(ScanParams);
+template __global__ void k_scan_t<true>(ScanParams);
 
 }  // namespace tsm

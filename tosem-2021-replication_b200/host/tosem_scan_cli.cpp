@@ -279,7 +279,7 @@ static void render_file(const FileEntry& f, int64_t id, const uint8_t* base, int
 }
 
 static int cmd_scan(const std::vector<std::string>& roots, const std::string& rows_path, const std::string& summary_path,
-                    int gpus, bool all_files, int64_t batch_bytes) {
+                    int gpus, bool all_files, int64_t batch_bytes, bool rev_b) {
   std::vector<FileEntry> files;
   for (size_t g = 0; g < roots.size(); ++g) walk(roots[g], (int)g, all_files, files);
   const int n_groups = (int)std::max<size_t>(roots.size(), 1);
@@ -287,8 +287,8 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device (there is no CPU fallback)");
   gpus = std::max(1, std::min(gpus, ndev));
-  // ---- shares of the GPUs: files sorted by size, descending, dealt round-robin (LPT), so that
-  //      every GPU gets the same byte total whatever the size law is; then, per GPU, batches of at most
+  // ---- shares of the GPUs: files sorted by size, descending, each to the GPU with the least bytes
+  //      so far (LPT), so that every GPU gets the same byte total whatever the size law is; then, per GPU, batches of at most
   //      --batch-bytes of arena (and 1M files) in walk order
   std::vector<std::vector<Batch>> share((size_t)gpus);
   {
@@ -299,7 +299,13 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
     }
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return files[x].size > files[y].size; });
     std::vector<std::vector<uint32_t>> mine((size_t)gpus);
-    for (size_t k = 0; k < order.size(); ++k) mine[k % (size_t)gpus].push_back(order[k]);
+    std::vector<int64_t> load((size_t)gpus, 0);            // greedy LPT: the next largest file goes to the lightest GPU
+    for (uint32_t i : order) {
+      size_t g = 0;
+      for (size_t k = 1; k < (size_t)gpus; ++k) if (load[k] < load[g]) g = k;
+      mine[g].push_back(i);
+      load[g] += files[i].size + 128;
+    }
     for (int g = 0; g < gpus; ++g) {
       std::sort(mine[(size_t)g].begin(), mine[(size_t)g].end());
       int64_t cur = 0;
@@ -372,7 +378,7 @@ static int cmd_scan(const std::vector<std::string>& roots, const std::string& ro
       tsm_result r{};
       r.stats = stats.data(); r.group_counts = group_counts.data();
       r.aev = aev.data(); r.aev_cap = cap; r.hev = hev.data(); r.hev_cap = cap;
-      ck(tsm_scan(ctx, &c, &r, TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS, st), "tsm_scan");
+      ck(tsm_scan(ctx, &c, &r, TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS | (rev_b ? TSM_SCAN_REV_B : 0u), st), "tsm_scan");
       aev.resize((size_t)r.n_aev); hev.resize((size_t)r.n_hev);
       void* dptr = nullptr; int64_t n64 = 0;
       ck(tsm_device_counts(ctx, &dptr, &n64), "tsm_device_counts");
@@ -900,7 +906,7 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
 
 static void usage() {
   fprintf(stderr,
-          "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]\n"
+          "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N] [--rev-b]\n"
           "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
@@ -913,15 +919,16 @@ int main(int argc, char** argv) {
   const std::string cmd = argv[1];
   std::vector<std::string> pos;
   std::map<std::string, std::string> opt;
-  bool all_files = false;
+  bool all_files = false, rev_b = false;
   for (int i = 2; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--all-files") all_files = true;
+    else if (a == "--rev-b") rev_b = true;
     else if (a.rfind("--", 0) == 0) { if (i + 1 >= argc) die("missing value for " + a); opt[a] = argv[++i]; }
     else pos.push_back(a);
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
-                                        opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30)); }
+                                        opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30), rev_b); }
   if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"]); }
   if (cmd == "releases") { if (pos.empty()) die("releases needs <root>=<tag>..."); return cmd_releases(pos, opt["--out"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }

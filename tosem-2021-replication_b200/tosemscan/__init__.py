@@ -18,6 +18,7 @@ ALIGN = 128
 EXT = {"py": 1, "cc": 2, "cpp": 3, "java": 4, "c": 5, "h": 6}
 SCAN_ASSERT_EVENTS = 1
 SCAN_HEADER_EVENTS = 2
+SCAN_REV_B = 8            # docs/SPEC.md section 4b (golden G1)
 
 FILE_STAT = np.dtype([("n_lines", "<u4"), ("n_assert", "<u4"), ("n_headers", "<u4"),
                       ("n_fixture", "<u4"), ("digest", "<u8")])
