@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Small scan + diff + reduce under compute-sanitizer (run: compute-sanitizer --tool memcheck python tools/sanitize_smoke.py)."""
+"""Small scan (Rev A and Rev B) + line records + diff + statements + reduce under compute-sanitizer (run: compute-sanitizer --tool memcheck python tools/sanitize_smoke.py)."""
 import os
 import sys
 
@@ -19,7 +19,10 @@ c = ts.gen_corpus(3, 300, 1, n_groups=4, pinned=False)
 r3 = s.scan(c, 0)
 a = ts.pack([b"a\nb\nc\n", b"x\n" * 50, b""], [1, 1, 1])
 b = ts.pack([b"a\nc\nd\n", b"y\n" * 40, b"q\n"], [1, 1, 1])
-print(s.diff_pairs(a, b))
+print(s.diff_pairs(a, b, detail=True))
+print([x[:4] for x in s.line_hashes(ts.pack(files[:40], exts[:40]), ngram=3)])
+r4 = s.scan(ts.pack(files, exts, grps, 5), 3 | ts.SCAN_REV_B)
+print(s.statements(c)[0][-1])
 fl = (np.random.default_rng(1).random((500, 7)) < 0.3).astype(np.uint8)
 print(s.reduce(fl, np.arange(500) % 3, np.arange(500) % 41, 3, 41)[1])
 print("totals", r["totals"], r2["totals"], r3["totals"])

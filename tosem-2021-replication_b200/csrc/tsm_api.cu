@@ -265,7 +265,7 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
         cudaMemset(c->d_arena, 0, (size_t)c->max_arena + 4096) != cudaSuccess ||
         cudaMemcpyToSymbol(c_lut_b, lutb, sizeof lutb) != cudaSuccess ||
         cudaFuncSetAttribute(k_scan_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_scan_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(k_scan_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM_B) != cudaSuccess)
       rc = TSM_E_CUDA;
   }
   if (rc != TSM_OK) {
@@ -385,7 +385,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       k_plan<<<(f1 - f0 + 255) / 256, 256, 0, st>>>(p);
       CU(cudaGetLastError());
       if (s == 0 && n_slabs == 1) CU(cudaEventRecord(ev[1], st));
-      if (flags & TSM_SCAN_REV_B) k_scan_t<true><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+      if (flags & TSM_SCAN_REV_B) k_scan_t<true><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM_B, st>>>(p);
       else k_scan_t<false><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
       CU(cudaGetLastError());
     }
@@ -394,11 +394,12 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
     if (c->cls_smem != hist) {                           // one resident wave of k_classify (grid-stride inside): measured
       int per_sm = 0;                                    // -7 % on C2 against 8 blocks per SM, equal on C4
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify, 256, hist) != cudaSuccess || per_sm < 1) per_sm = 4;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify_t<false>, 256, hist) != cudaSuccess || per_sm < 1) per_sm = 4;
       c->cls_grid = c->sms * per_sm;
       c->cls_smem = hist;
     }
-    k_classify<<<c->cls_grid, 256, hist, st>>>(p);
+    if (flags & TSM_SCAN_REV_B) k_classify_t<true><<<c->cls_grid, 256, hist, st>>>(p);
+    else k_classify_t<false><<<c->cls_grid, 256, hist, st>>>(p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev[3], st));
     CU(cudaEventRecord(ev[4], st));                           // (slot of the former k_totals, now fused into k_classify)

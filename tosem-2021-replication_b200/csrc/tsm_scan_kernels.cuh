@@ -384,7 +384,8 @@ __device__ __noinline__ bool ident_eq(FileBytes& rd, uint32_t s, uint32_t n, con
 
 constexpr uint32_t BQ_CAP = 1024;                        // bare-assert expressions a block of k_classify defers (16 B each)
 
-__global__ void __launch_bounds__(256) k_classify(ScanParams p) {
+template <bool REVB>
+__global__ void __launch_bounds__(256) k_classify_t(ScanParams p) {
   extern __shared__ __align__(16) uint32_t csm[];        // byte classes, operator table, category tables, deferral queue, [n_groups][K] histogram
   uint32_t* cls = csm;
   uint32_t* elut = csm + 256;
@@ -415,7 +416,8 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     }
   };
   const uint32_t n = min(p.ctrl->n_cand, p.cand_cap);
-  const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0, revb = (p.flags & TSM_SCAN_REV_B) != 0;
+  const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0;
+  constexpr bool revb = REVB;                            // (two instantiations: the Rev-B rules stay out of the canonical kernel)
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long cd = p.cand[i];
     const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
@@ -581,5 +583,8 @@ __global__ void __launch_bounds__(256) k_classify(ScanParams p) {
     }
   }
 }
+
+template __global__ void k_classify_t<false>(ScanParams);
+template __global__ void k_classify_t<true>(ScanParams);
 
 }  // namespace tsm

@@ -54,11 +54,12 @@ constexpr uint32_t O2_CTL = O2_Q + Q2_CAP * 2;           // u32 queue length, pa
 constexpr uint32_t WARP_SMEM2 = ((O2_CTL + 16 + 127) / 128) * 128;
 // per CTA in front of the warps: automaton table (1 KB), per-language masks + the opaque 4 (128 B), rotations of '\n' (61 x 8 B)
 constexpr uint32_t O2_T0A = LUT_BYTES;
-constexpr uint32_t O2_LUTB = LUT_BYTES + 512;            // Rev-B trigger table (TSM_SCAN_REV_B): 256 x u32
-constexpr uint32_t CTA_BYTES2 = LUT_BYTES + 512 + 1024;
+constexpr uint32_t CTA_BYTES2 = LUT_BYTES + 512;
 constexpr uint32_t SCAN2_SMEM = CTA_BYTES2 + SCAN2_WARPS * WARP_SMEM2;
+constexpr uint32_t O2_LUTB = SCAN2_SMEM;                 // Rev-B trigger table (only the TSM_SCAN_REV_B instantiation): 256 x u32 behind the warps
+constexpr uint32_t SCAN2_SMEM_B = SCAN2_SMEM + 1024;
 static_assert(O2_RW % 8 == 0 && O2_WENT % 8 == 0 && O2_LTAB % 2 == 0 && O2_BASE % 8 == 0 && O2_Q % 4 == 0 && O2_CTL % 8 == 0, "alignment");
-static_assert(SCAN2_CTAS_PER_SM * SCAN2_SMEM <= 232448, "shared memory per SM");
+static_assert(SCAN2_CTAS_PER_SM * (SCAN2_SMEM_B + 1024) <= 233472, "shared memory per SM (228 KB, 1 KB reserved per CTA)");
 // line record: bits 0..12 position of the line's end in the buffer, 13 = first newline of its word (the word's stored
 // OR is the line's), 14 = the word is mixed, 15 = no newline: the unterminated last line of a file
 constexpr uint32_t LR_POS = 0x1FFFu, LR_FIRST = 0x2000u, LR_MIXED = 0x4000u, LR_VIRT = 0x8000u;
