@@ -33,7 +33,7 @@ namespace tsm {
 #define TSM_RW2_SHIFT 2
 #endif
 #ifndef TSM_WALK_UNROLL
-#define TSM_WALK_UNROLL 1
+#define TSM_WALK_UNROLL 2
 #endif
 constexpr int SCAN2_WARPS = TSM_SCAN2_WARPS, SCAN2_CTAS_PER_SM = TSM_SCAN2_CTAS, WALK_UNROLL = TSM_WALK_UNROLL;
 
