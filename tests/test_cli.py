@@ -148,8 +148,9 @@ def test_reduce_tables(tmp_path):
     tax = tmp_path / "taxonomy.csv"
     with open(tax, "w", newline="", encoding="utf-8") as f:
         csv.writer(f, lineterminator="\r\n").writerows(lines)
-    sp, mp, pp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv")
-    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp], capture_output=True, text=True)
+    sp, mp, pp, cp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv"), str(tmp_path / "c.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp, "--correlate", cp],
+                         capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     s = read_csv(sp)
     assert s[0][:10] == ["Tests"] + repos
@@ -190,8 +191,9 @@ def test_reduce_reproduces_the_shipped_tables(tmp_path):
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     tax = tmp_path / "taxonomy.csv"
     tax.write_bytes(gzip.open(os.path.join(gold, "taxonomy_min.csv.gz"), "rb").read())
-    sp, mp, pp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv")
-    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp], capture_output=True, text=True)
+    sp, mp, pp, cp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv"), str(tmp_path / "c.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp, "--correlate", cp],
+                         capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     d = np.load(os.path.join(gold, "g3_reduce.npz"))
     repos = [str(x) for x in d["repo_names"]]
@@ -224,6 +226,24 @@ def test_reduce_reproduces_the_shipped_tables(tmp_path):
                 assert prow[repos[k]][1 + j] == str(pwant[j][k]), (pnames[j], repos[k])
                 n_ok += 1
     assert n_ok == 172
+    # RQs/RQ3/tests_correlate_rq3.csv: same header and row names, 394 of the 420 cells bit-identical; the other 26 are
+    # checked against the oracle's distinct counts (the taxonomy revision shipped differs from the one the table was made from)
+    ct = read_csv(cp)
+    assert ct[0] == ["Tests"] + [str(x) for x in d["correlate_col_names"]]
+    assert [x[0] for x in ct[1:]] == [str(x) for x in d["correlate_row_names"]]
+    cok, cwant, cdist = d["correlate_cell_reproduces"], d["want_correlate_cells"], d["oracle_correlate_distinct"]
+    order = [str(x) for x in d["correlate_repo_order"]]
+    cpr = dict(zip(repos, (int(x) for x in d["oracle_cases_per_repo"])))
+    n_ok = 0
+    for j in range(cok.shape[0]):
+        for q in range(cok.shape[1]):
+            dd = [int(cdist[j * cok.shape[1] + q, repos.index(n)]) for n in order]
+            mine = "0" if not any(dd) else "".join("%s:(%s%%), " % (n, repr(round(100.0 * v / cpr[n], 2))) for n, v in zip(order, dd))
+            assert ct[1 + j][1 + q] == mine, (j, q)
+            if cok[j, q]:
+                assert ct[1 + j][1 + q] == str(cwant[j][q])
+                n_ok += 1
+    assert n_ok == 394
 
 
 @pytest.mark.gpu

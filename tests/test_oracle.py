@@ -144,6 +144,42 @@ def test_header_rules_and_method_strings():
     assert ms(4, b"  @Test public void testDoubleInitialize() throws Exception {") == b"@TesttestDoubleInitialize()throwsException{"
 
 
+def test_g3_correlate_table_from_the_taxonomy_fixture():
+    """RQs/RQ3/tests_correlate_rq3.csv (20 strategies x 21 properties): the flag columns rebuilt from the committed
+    taxonomy columns (tests/golden/taxonomy_min.csv.gz), reduced by the oracle, formatted like the shipped cells
+    ("repo:(p%), " with p a Python float of 2 decimals, "0" for a pairing no case has): 394 of 420 cells bit-identical."""
+    import csv
+    import gzip
+    import io
+    d = np.load(os.path.join(GOLD, "g3_reduce.npz"))
+    rows = list(csv.DictReader(io.StringIO(gzip.open(os.path.join(GOLD, "taxonomy_min.csv.gz"), "rb").read().decode("utf-8"), newline="")))
+    repos = [str(x) for x in d["repo_names"]]
+    rid = {r: i for i, r in enumerate(repos)}
+    cases = sorted({r["Cases"] for r in rows}, key=lambda s: (len(s), s))
+    cid = {c: i for i, c in enumerate(cases)}
+    rcol, rval = [str(x) for x in d["correlate_row_column"]], [str(x) for x in d["correlate_row_value"]]
+    labels = [set(str(x).split("|")) for x in d["correlate_col_labels"]]
+    nr, nc = len(rcol), len(labels)
+    flags = np.zeros((len(rows), nr * nc), np.uint8)
+    for i, r in enumerate(rows):
+        pr = [(r["Data"].strip() in lab) or (r["Model"].strip() in lab) for lab in labels]
+        for j in range(nr):
+            if r[rcol[j]].strip() == rval[j]:
+                flags[i, j * nc:(j + 1) * nc] = pr
+    repo = np.array([rid[r["Repo"]] for r in rows], np.int32)
+    case = np.array([cid[r["Cases"]] for r in rows], np.int32)
+    out, cpr = orc.reduce(flags, repo, case, len(repos), len(cases))
+    assert np.array_equal(out, d["oracle_correlate_distinct"])
+    order = [str(x) for x in d["correlate_repo_order"]]
+    ok, want = d["correlate_cell_reproduces"], d["want_correlate_cells"]
+    assert ok.shape == (20, 21) and int(ok.sum()) == 394 and int((ok.sum(axis=1) == 21).sum()) == 5
+    for j in range(nr):
+        for q in range(nc):
+            dd = [int(out[j * nc + q, rid[n]]) for n in order]
+            cell = "0" if not any(dd) else "".join("%s:(%s%%), " % (n, repr(round(100.0 * v / int(cpr[rid[n]]), 2))) for n, v in zip(order, dd))
+            assert (cell == str(want[j][q])) == bool(ok[j, q]), (j, q)
+
+
 def test_g3_reduce_golden():
     """Golden G3: RQs/taxonomy_test2.csv -> tests_strategy_rq32.csv / tests_methods_v2.csv."""
     d = np.load(os.path.join(GOLD, "g3_reduce.npz"))

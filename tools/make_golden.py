@@ -274,6 +274,42 @@ PROPERTIES = [
     ("Compatibility and Portability", ("Compatibility",))]
 
 
+# RQ3 strategy x property table (RQs/RQ3/tests_correlate_rq3.csv): 20 strategy rows, 21 property columns, one cell =
+# "repo:(p%), " over the nine repositories, p = 100 * distinct cases with BOTH flags / cases of the repository, rounded
+# to 2 decimals and printed as a Python float ("0.0", "1.22", "12.2"); a cell with no case at all is the string "0".
+# The row predicates are single taxonomy values (unlike tests_strategy_rq32.csv, which merges Error_Type values):
+# `decision` is logical_statement, `logical_condition` is logical_expression (recovered against the shipped cells).
+CORRELATE_ROWS = [  # (row name in tests_correlate_rq3.csv, column, value)
+    ("rounding_tolence", "Approximation_Type", "rounding_tolence"), ("instance_check", "checks_type", "instance_check"),
+    ("MemoryError", "Error_Type", "MemoryError"), ("negative_test", "negative_test", "1"),
+    ("status_analysis", "status_test", "1"), ("value_range_analysis", "value_range", "1"),
+    ("sub_set_checks", "checks_type", "sub_set_checks"), ("ValueError", "Error_Type", "ValueError"),
+    ("decision", "logical_statement", "1"), ("error_bounding", "Approximation_Type", "error_bounding"),
+    ("Null_pointer", "null_pointer", "1"), ("boundary", "boundary", "1"),
+    ("absolute_relative_tolerence", "Approximation_Type", "absolute_relative_tolerence"),
+    ("ImportError", "Error_Type", "ImportError"), ("pseaudo_oracle", "Pseaudo_Oracle", "1"),
+    ("RuntimeError", "Error_Type", "RuntimeError"), ("logical_condition", "logical_expression", "1"),
+    ("TypeError", "Error_Type", "TypeError"), ("KeyError", "Error_Type", "KeyError"),
+    ("NotImplementedError", "Error_Type", "NotImplementedError")]
+CORRELATE_COLS = [  # (column name in tests_correlate_rq3.csv, name in PROPERTIES)
+    ("Distribution", "Data Distribution"), ("Validity", "Data Validity"), ("Consistency", "Consistency"),
+    ("Completeness", "Completeness"), ("Correctness", "Correctness"), ("Robustness", "Robustness"),
+    ("Efficiency", "Efficiency"), ("Relation", "Data Relation"), ("Scalability", "Scalability"),
+    ("Feature Importance", "Features Importance"), ("Restoration", "Data Restoration and Recoverability"),
+    ("Concurrency", "Concurrency and Parallelism"), ("uncertainty", "Uncertainty"), ("Anomaly", "Anomaly"),
+    ("Data Loss", "Data Migration Loss and Corruption"), ("Bias", "Bias and Fairness"),
+    ("Security", "Security and Privacy"), ("Uniqueness", "Data Uniqueness"), ("Timeliness", "Data Timeliness"),
+    ("integration", "Data Integration Integrity"), ("Compatibility", "Compatibility and Portability")]
+CORRELATE_REPOS = ["auto_sklearn", "google_automl", "tpot", "autokeras", "Nupic", "Apollo", "nni", "Ray", "DeepSpeech2"]
+
+
+def correlate_cell(distinct, cases, names):
+    """One cell of tests_correlate_rq3.csv from the distinct-case counts of the nine repositories."""
+    if not any(distinct):
+        return "0"
+    return "".join("%s:(%s%%), " % (n, repr(round(100.0 * int(d) / int(c), 2))) for n, d, c in zip(names, distinct, cases))
+
+
 def fmt4(x):
     s = ("%.4f" % x).rstrip("0").rstrip(".")
     return s if s else "0"
@@ -323,7 +359,7 @@ def golden_g3(ledger):
         m_ok.append(int(out[len(STRATEGY) + j].sum()) == want4[name])
     # the columns `tosem-scan reduce` reads, as a compact fixture for the CLI's own golden test (tests/test_cli.py)
     import gzip
-    keep = ["Cases", "Repo", "Data", "Model"] + sorted({c for _, c, _ in STRATEGY} | {"logical_expression"} | {c for _, c in METHODS})
+    keep = ["Cases", "Repo", "Data", "Model"] + sorted({c for _, c, _ in STRATEGY} | {c for _, c, _ in CORRELATE_ROWS} | {c for _, c in METHODS})
     import io
     txt = io.StringIO(newline="")
     w = csv.writer(txt, lineterminator="\r\n")
@@ -346,22 +382,50 @@ def golden_g3(ledger):
         for j in range(len(PROPERTIES)):
             want_prop[j][k] = r[1 + j]
             prop_ok[j, k] = fmt4(round(100.0 * out[p0 + j, k] / denom, 4)) == r[1 + j]
+    # RQ3 strategy x property table: 20 x 21 combined flags through the same reduction
+    labels_of = dict(PROPERTIES)
+    cflags = np.zeros((len(rows), len(CORRELATE_ROWS) * len(CORRELATE_COLS)), np.uint8)
+    for i, r in enumerate(rows):
+        pr = [(r["Data"].strip() in labels_of[q]) or (r["Model"].strip() in labels_of[q]) for _, q in CORRELATE_COLS]
+        for j, (_, col, val) in enumerate(CORRELATE_ROWS):
+            if r[col].strip() == val:
+                cflags[i, j * len(CORRELATE_COLS):(j + 1) * len(CORRELATE_COLS)] = pr
+    cout, _ = orc.reduce(cflags, repo, case, len(repos), len(cases))
+    tc = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_correlate_rq3.csv"), newline="")))
+    assert tc[0][1:] == [c for c, _ in CORRELATE_COLS] and [r[0] for r in tc[1:]] == [r[0] for r in CORRELATE_ROWS]
+    order = [rid[n] for n in CORRELATE_REPOS]
+    corr_ok = np.zeros((len(CORRELATE_ROWS), len(CORRELATE_COLS)), np.uint8)
+    want_corr = [r[1:] for r in tc[1:]]
+    for j in range(len(CORRELATE_ROWS)):
+        for q in range(len(CORRELATE_COLS)):
+            d = cout[j * len(CORRELATE_COLS) + q]
+            corr_ok[j, q] = correlate_cell([d[k] for k in order], [cpr[k] for k in order], CORRELATE_REPOS) == want_corr[j][q]
     np.savez_compressed(os.path.join(OUT, "g3_reduce.npz"), flags=flags, repo=repo, case_id=case,
                         want_property_cells=np.array(want_prop), property_cell_reproduces=prop_ok,
                         flag_names=np.array(names), repo_names=np.array(repos),
                         want_strategy_cells=np.array(want_cells), strategy_cell_reproduces=cell_ok,
                         want_method_total_cases=np.array([want4[m[0]] for m in METHODS], np.int64),
                         method_reproduces=np.array(m_ok, np.uint8),
-                        oracle_distinct=out, oracle_cases_per_repo=cpr)
+                        oracle_distinct=out, oracle_cases_per_repo=cpr,
+                        want_correlate_cells=np.array(want_corr), correlate_cell_reproduces=corr_ok,
+                        correlate_row_names=np.array([r[0] for r in CORRELATE_ROWS]),
+                        correlate_col_names=np.array([c for c, _ in CORRELATE_COLS]),
+                        correlate_row_column=np.array([r[1] for r in CORRELATE_ROWS]),
+                        correlate_row_value=np.array([r[2] for r in CORRELATE_ROWS]),
+                        correlate_col_labels=np.array(["|".join(labels_of[q]) for _, q in CORRELATE_COLS]),
+                        correlate_repo_order=np.array(CORRELATE_REPOS), oracle_correlate_distinct=cout)
     ledger["G3"] = {"source": "RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/tests_methods_v2.csv",
                     "rows": len(rows), "cases": len(cases), "cases_per_repo": dict(zip(repos, map(int, cpr))),
                     "strategy_cells_bit_identical": [int(cell_ok.sum()), int(cell_ok.size)],
                     "rq4_method_counts_identical": [int(sum(m_ok)), len(m_ok)],
                     "property_cells_bit_identical": [int(prop_ok.sum()), int(prop_ok.size)],
                     "property_columns_fully_identical": [int((prop_ok.sum(axis=1) == len(repos)).sum()), len(PROPERTIES)],
+                    "correlate_cells_bit_identical": [int(corr_ok.sum()), int(corr_ok.size)],
+                    "correlate_rows_fully_identical": [int((corr_ok.sum(axis=1) == len(CORRELATE_COLS)).sum()), len(CORRELATE_ROWS)],
                     "rq4_mismatches": {m[0]: [int(out[len(STRATEGY) + j].sum()), want4[m[0]]]
                                        for j, m in enumerate(METHODS) if not m_ok[j]}}
-    print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok), "property cells", int(prop_ok.sum()), prop_ok.size)
+    print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok), "property cells", int(prop_ok.sum()), prop_ok.size,
+          "correlate cells", int(corr_ok.sum()), corr_ok.size)
 
 
 def c1_collect():

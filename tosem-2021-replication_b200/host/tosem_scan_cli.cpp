@@ -16,7 +16,7 @@
 // itself goes through libtosemscan.so (sm_100a kernels); there is no CPU fallback.
 //
 //   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]
-//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F]
+//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
 //   tosem-scan releases <snapshot-root>=<tag>... [--out F]
@@ -489,6 +489,35 @@ static const PropDef kProperties[] = {
     {"Data Timeliness", "Timeliness"}, {"Data Integration Integrity", "Validate data integration and integrity"},
     {"Compatibility and Portability", "Compatibility"}};
 
+// RQ3 strategy x property table (RQs/RQ3/tests_correlate_rq3.csv): 20 rows x 21 columns, one cell = the share of a
+// repository's cases that have BOTH the strategy flag and the property, for the nine repositories in the order below.
+// Row predicates are single taxonomy values (the strategy table above merges Error_Type values, this one does not);
+// `decision` reads logical_statement and `logical_condition` reads logical_expression - recovered against the shipped
+// cells, 394 of 420 bit-identical (tools/make_golden.py, tests/golden/ledger.json G3).
+struct CorrRow { const char* name; const char* col; const char* val; };
+static const CorrRow kCorrRows[] = {
+    {"rounding_tolence", "Approximation_Type", "rounding_tolence"}, {"instance_check", "checks_type", "instance_check"},
+    {"MemoryError", "Error_Type", "MemoryError"}, {"negative_test", "negative_test", "1"},
+    {"status_analysis", "status_test", "1"}, {"value_range_analysis", "value_range", "1"},
+    {"sub_set_checks", "checks_type", "sub_set_checks"}, {"ValueError", "Error_Type", "ValueError"},
+    {"decision", "logical_statement", "1"}, {"error_bounding", "Approximation_Type", "error_bounding"},
+    {"Null_pointer", "null_pointer", "1"}, {"boundary", "boundary", "1"},
+    {"absolute_relative_tolerence", "Approximation_Type", "absolute_relative_tolerence"},
+    {"ImportError", "Error_Type", "ImportError"}, {"pseaudo_oracle", "Pseaudo_Oracle", "1"},
+    {"RuntimeError", "Error_Type", "RuntimeError"}, {"logical_condition", "logical_expression", "1"},
+    {"TypeError", "Error_Type", "TypeError"}, {"KeyError", "Error_Type", "KeyError"},
+    {"NotImplementedError", "Error_Type", "NotImplementedError"}};
+struct CorrCol { const char* name; const char* prop; };        // column header of the shipped table -> name in kProperties
+static const CorrCol kCorrCols[] = {
+    {"Distribution", "Data Distribution"}, {"Validity", "Data Validity"}, {"Consistency", "Consistency"},
+    {"Completeness", "Completeness"}, {"Correctness", "Correctness"}, {"Robustness", "Robustness"},
+    {"Efficiency", "Efficiency"}, {"Relation", "Data Relation"}, {"Scalability", "Scalability"},
+    {"Feature Importance", "Features Importance"}, {"Restoration", "Data Restoration and Recoverability"},
+    {"Concurrency", "Concurrency and Parallelism"}, {"uncertainty", "Uncertainty"}, {"Anomaly", "Anomaly"},
+    {"Data Loss", "Data Migration Loss and Corruption"}, {"Bias", "Bias and Fairness"},
+    {"Security", "Security and Privacy"}, {"Uniqueness", "Data Uniqueness"}, {"Timeliness", "Data Timeliness"},
+    {"integration", "Data Integration Integrity"}, {"Compatibility", "Compatibility and Portability"}};
+
 static bool one_of(const std::string& have, const std::string& want) {   // `want` = '|'-separated values
   for (size_t a = 0; a <= want.size();) {
     const size_t b = std::min(want.find('|', a), want.size());
@@ -511,10 +540,17 @@ static std::string fmt_num(double v, int dec) {            // shipped cells drop
   if (s.find('.') != std::string::npos) { while (!s.empty() && s.back() == '0') s.pop_back(); if (!s.empty() && s.back() == '.') s.pop_back(); }
   return s.empty() ? "0" : s;
 }
+static std::string fmt_pyfloat2(double v) {                 // repr(round(v, 2)) of the shipped correlate cells: "0.0", "1.22", "12.2"
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.2f", v);
+  std::string s = buf;
+  while (s.size() > 1 && s.back() == '0' && s[s.size() - 2] != '.') s.pop_back();
+  return s;
+}
 static double round_to(double v, int dec) { const double p = std::pow(10.0, dec); return std::round(v * p) / p; }
 
 static int cmd_reduce(const std::string& path, const std::string& strategy_path, const std::string& methods_path,
-                      const std::string& properties_path) {
+                      const std::string& properties_path, const std::string& correlate_path) {
   auto rows = csv_read(path);
   if (rows.size() < 2) die("empty taxonomy");
   std::map<std::string, int> col;
@@ -526,7 +562,16 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
   for (size_t r = 1; r < rows.size(); ++r) if ((int)rows[r].size() > col["Repo"] && !std::count(repos.begin(), repos.end(), rows[r][col["Repo"]])) repos.push_back(rows[r][col["Repo"]]);
   for (size_t i = 0; i < repos.size(); ++i) rid[repos[i]] = (int)i;
   const int nS = sizeof(kStrategy) / sizeof(kStrategy[0]), nM = sizeof(kMethods) / sizeof(kMethods[0]);
-  const int nP = sizeof(kProperties) / sizeof(kProperties[0]), nF = nS + nM + nP;
+  const int nP = sizeof(kProperties) / sizeof(kProperties[0]);
+  const int nCR = sizeof(kCorrRows) / sizeof(kCorrRows[0]), nCC = sizeof(kCorrCols) / sizeof(kCorrCols[0]);
+  const bool corr = !correlate_path.empty();
+  const int nF = nS + nM + nP + (corr ? nCR * nCC : 0);      // the correlate table is 420 more flag columns of the same reduction
+  int corr_prop[sizeof(kCorrCols) / sizeof(kCorrCols[0])];
+  for (int q = 0; q < nCC; ++q) {
+    corr_prop[q] = -1;
+    for (int j = 0; j < nP; ++j) if (!strcmp(kCorrCols[q].prop, kProperties[j].name)) corr_prop[q] = j;
+    if (corr_prop[q] < 0) die(std::string("no property named ") + kCorrCols[q].prop);
+  }
   std::vector<uint8_t> flags; std::vector<int32_t> repo, cas;
   auto cell = [&](const std::vector<std::string>& r, const char* c) -> std::string {
     auto it = col.find(c); return (it == col.end() || it->second >= (int)r.size()) ? std::string() : trim(r[it->second]); };
@@ -543,8 +588,14 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
     }
     for (int j = 0; j < nM; ++j) { const std::string v = cell(R, kMethods[j].col); flags.push_back(!(v.empty() || v == "0")); }
     const std::string data = cell(R, "Data"), model = cell(R, "Model");
+    const size_t p0 = flags.size();
     for (int j = 0; j < nP; ++j)
       flags.push_back((!data.empty() && one_of(data, kProperties[j].labels)) || (!model.empty() && one_of(model, kProperties[j].labels)));
+    if (corr)
+      for (int j = 0; j < nCR; ++j) {
+        const bool s_on = cell(R, kCorrRows[j].col) == kCorrRows[j].val;
+        for (int q = 0; q < nCC; ++q) flags.push_back(s_on && flags[p0 + (size_t)corr_prop[q]]);
+      }
   }
   const int n_rows = (int)repo.size(), n_repos = (int)repos.size(), n_cases = (int)cid.size();
   tsm_ctx* ctx = nullptr;
@@ -606,6 +657,35 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
       std::vector<std::string> row = {name};
       for (int j = 0; j < nP; ++j)
         row.push_back(fmt_num(denom ? round_to(100.0 * out[(size_t)(nS + nM + j) * n_repos + r] / denom, 4) : 0.0, 4));
+      csv_row(os, row);
+    }
+  }
+  if (corr) {                                               // layout of RQs/RQ3/tests_correlate_rq3.csv
+    for (const CorrRow& cr : kCorrRows) if (!col.count(cr.col)) die(std::string("taxonomy lacks column ") + cr.col);
+    std::ofstream os(correlate_path, std::ios::binary);
+    std::vector<std::string> h = {"Tests"};
+    for (int q = 0; q < nCC; ++q) h.push_back(kCorrCols[q].name);
+    csv_row(os, h);
+    std::vector<std::string> order = {"auto_sklearn", "google_automl", "tpot", "autokeras", "Nupic", "Apollo", "nni", "Ray", "DeepSpeech2"};
+    for (auto& r : repos) if (!std::count(order.begin(), order.end(), r)) order.push_back(r);
+    const size_t c0 = (size_t)(nS + nM + nP);
+    for (int j = 0; j < nCR; ++j) {
+      std::vector<std::string> row = {kCorrRows[j].name};
+      for (int q = 0; q < nCC; ++q) {
+        const int64_t* d = &out[(c0 + (size_t)j * nCC + q) * n_repos];
+        bool any = false;
+        for (int r = 0; r < n_repos; ++r) any = any || d[r] != 0;
+        std::string cellv = "0";                            // a pairing no case has is the bare string "0" in the shipped table
+        if (any) {
+          cellv.clear();
+          for (auto& name : order) {
+            if (!rid.count(name) || cpr[(size_t)rid[name]] == 0) continue;
+            const int r = rid[name];
+            cellv += name + ":(" + fmt_pyfloat2(100.0 * (double)d[r] / (double)cpr[r]) + "%), ";
+          }
+        }
+        row.push_back(cellv);
+      }
       csv_row(os, row);
     }
   }
@@ -907,7 +987,7 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
 static void usage() {
   fprintf(stderr,
           "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N] [--rev-b]\n"
-          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F]\n"
+          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
           "       tosem-scan releases <snapshot-root>=<tag>... [--out F]\n"
@@ -929,7 +1009,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
                                         opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30), rev_b); }
-  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"]); }
+  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"], opt["--correlate"]); }
   if (cmd == "releases") { if (pos.empty()) die("releases needs <root>=<tag>..."); return cmd_releases(pos, opt["--out"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
   if (cmd == "diff") { if (pos.size() != 2) die("diff needs <old-root> <new-root>"); return cmd_diff(pos[0], pos[1], opt["--out"]); }
