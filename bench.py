@@ -541,13 +541,13 @@ def bench_diff(args, ts, torch, env):
            "roofline": {"bound": "hbm", "kernel": "k_scan (line records of both sides)", "achieved": achieved, "peak": env["peak"],
                         "unit": "GB/s", "frac": achieved / env["peak"], "traffic": None, "peak_source": env["peak_src"],
                         "algorithmic_bytes_per_launch": alg / 2,
-                        "kernel_ms": {"k_scan_both_sides": float(kern_ms[0]), "k_myers": float(kern_ms[1]), "k_myers_trace": float(kern_ms[2])},
+                        "kernel_ms": {"k_scan_both_sides": float(kern_ms[0]), "k_diff_small": float(kern_ms[1]), "k_myers_and_trace_of_the_left_over_pairs": float(kern_ms[2])},
                         "lcs_phase": {"note": "compute / latency bound on 8-byte line hashes, reported in pairs/s (SURVEY.md section 8d)",
                                       "pairs_per_s_kernels_only_this_gpu": a.n_files / (float(kern_ms.sum()) * 1e-3) if kern_ms.sum() > 0 else None}},
            "e2e": {"value": total_bytes * ke / e2e_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": int(a.off[-1]) + int(b.off[-1]) + 18 * a.n_files + 16,
                    "d2h_bytes_per_step": 56 * a.n_files + 16 * (a.n_files + 1), "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
                    "pairs_per_s": total_pairs * ke / e2e_s,
-                   "path": "tsm_diff_pairs_detail(pinned host arenas): H2D of both sides + k_scan x 2 + k_myers + k_myers_trace + D2H"},
+                   "path": "tsm_diff_pairs_detail(pinned host arenas): H2D of both sides + k_scan x 2 + k_diff_small (+ k_myers, k_myers_trace for the pairs it leaves over) + D2H"},
            "gpu_launches": launches, "clocks": clocks,
            "check": {"added": int(add.sum()), "removed": int(rem.sum()), "hunks": int(det["hunks_add"].sum() + det["hunks_del"].sum() + det["hunks_mod"].sum()),
                      "added_assert": int(det["added_assert"].sum()), "removed_assert": int(det["removed_assert"].sum())}}

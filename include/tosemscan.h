@@ -137,8 +137,11 @@ int tsm_diff_pairs_detail(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus
  *
  * Resident variant (bench.py's `value` for config C5): tsm_diff_upload copies both sides to HBM once and keeps them in
  * the ctx; every tsm_diff_resident call runs the kernels over them (k_scan over both sides for the line records,
- * k_myers, k_myers_trace when detail != NULL) and copies the per-pair results back.  tsm_diff_last_ms: device time
- * (CUDA events on the launching stream) of the last diff call: ms3 = { k_scan over both sides, k_myers, k_myers_trace }. */
+ * k_diff_small - search, rows of V and backtrack of a pair in shared memory, four launches for four sizes of pairs - then
+ * k_myers and, when detail != NULL, k_myers_trace for the pairs they leave over: distances above 127 lines, changed
+ * regions of more than 4 096 lines) and copies the
+ * per-pair results back.  tsm_diff_last_ms: device time (CUDA events on the launching stream) of the last diff call:
+ * ms3 = { k_scan over both sides, k_diff_small, k_myers + k_myers_trace of the left-over pairs }. */
 int tsm_diff_upload(tsm_ctx* ctx, const tsm_corpus* olds, const tsm_corpus* news, void* stream);
 int tsm_diff_resident(tsm_ctx* ctx, int64_t* added, int64_t* removed, tsm_diff_detail* detail, void* stream);
 int tsm_diff_last_ms(tsm_ctx* ctx, float* ms3);

@@ -148,9 +148,8 @@ def test_reduce_tables(tmp_path):
     tax = tmp_path / "taxonomy.csv"
     with open(tax, "w", newline="", encoding="utf-8") as f:
         csv.writer(f, lineterminator="\r\n").writerows(lines)
-    sp, mp, pp, cp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv"), str(tmp_path / "c.csv")
-    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp, "--correlate", cp],
-                         capture_output=True, text=True)
+    sp, mp, pp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     s = read_csv(sp)
     assert s[0][:10] == ["Tests"] + repos

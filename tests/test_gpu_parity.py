@@ -271,6 +271,44 @@ def test_diff_hunks_and_classification(scanner):
     check_diff_detail(scanner, o3, n3, [1] * 40)
 
 
+def test_diff_limits_of_the_one_launch_kernel(scanner):
+    """k_diff_small finishes a pair in the first of its four sizes that holds it (middle <= 512 lines and D <= 31,
+    1 024 / 63, 4 096 / 63, 4 096 / 127); everything else goes to k_myers / k_myers_trace.  Pairs on both sides of every limit, with
+    detail, against the oracle."""
+    def lines(tag, n):
+        return [b"%s%05d\n" % (tag, i) for i in range(n)]
+    olds, news, want_rem = [], [], []
+    for total, ds in ((250, (1, 15, 30, 31, 32, 33)), (500, (62, 63, 64, 65)), (1300, (31, 64, 126, 127, 128, 129, 200))):
+        for d in ds:                                        # d deletions spread over the file: D = d
+            o = lines(b"assert x", total)
+            keep = [l for i, l in enumerate(o) if not (i % (total // d) == 3 and i // (total // d) < d)]
+            assert len(o) - len(keep) == d
+            olds.append(b"".join(o)); news.append(b"".join(keep)); want_rem.append(d)
+    n_del = len(olds)
+    for d in (16, 31, 32, 64):                              # replacements: D = 2 d, hunks of kind mod
+        o = lines(b"y = ", 300)
+        n = list(o)
+        for j in range(d):
+            n[5 + 4 * j] = b"EXPECT_EQ(%d, q);\n" % j
+        olds.append(b"".join(o)); news.append(b"".join(n))
+    for total in (510, 512, 514, 1022, 1024, 1026, 4094, 4096, 4098, 6000):   # middle of `total` lines on both sides together, 2 edits at its ends
+        half = total // 2
+        o = [b"first old\n"] + lines(b"m", half - 2) + [b"last old\n"]
+        n = [b"first new\n"] + lines(b"m", total - half - 2) + [b"assert last_new\n"]
+        olds.append(b"head\n" * 40 + b"".join(o) + b"tail\n" * 40); news.append(b"head\n" * 40 + b"".join(n) + b"tail\n" * 40)
+    olds += [b"", b"a\n" * 3000, b"".join(lines(b"p", 40)), b"same\n" * 5000]
+    news += [b"b\n" * 2500, b"", b"".join(lines(b"q", 40)), b"same\n" * 5000]
+    exts = [1] * n_del + [2] * 4 + [1] * 14
+    add, rem, det = check_diff_detail(scanner, olds, news, exts)
+    assert [int(x) for x in rem[:n_del]] == want_rem and int(add[:n_del].sum()) == 0
+    assert [int(x) for x in det["hunks_mod"][n_del:n_del + 4]] == [16, 31, 32, 64] and int(det["added_assert"][n_del + 1]) == 31
+    assert (int(add[-4]), int(rem[-4])) == (2500, 0) and (int(add[-1]), int(rem[-1])) == (0, 0)
+    a = ts.pack(olds, exts)
+    b = ts.pack(news, exts)
+    add2, rem2 = scanner.diff_pairs(a, b)                   # and without detail (no rows kept)
+    assert np.array_equal(add2, add) and np.array_equal(rem2, rem)
+
+
 def test_statement_kinds(scanner):
     """SPEC section 10 line kinds: GPU (SWAR parenthesis counts + clamped warp scan) against the oracle."""
     corpora = []

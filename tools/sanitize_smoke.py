@@ -20,6 +20,9 @@ r3 = s.scan(c, 0)
 a = ts.pack([b"a\nb\nc\n", b"x\n" * 50, b""], [1, 1, 1])
 b = ts.pack([b"a\nc\nd\n", b"y\n" * 40, b"q\n"], [1, 1, 1])
 print(s.diff_pairs(a, b, detail=True))
+far_o = [b"".join(b"o%d\n" % i for i in range(60)), b"head\n" * 10 + b"".join(b"m%d\n" % i for i in range(2500)) + b"tail\n"]
+far_n = [b"".join(b"n%d\n" % i for i in range(50)), b"head\n" * 10 + b"x\n" + b"".join(b"m%d\n" % i for i in range(2500)) + b"y\ntail\n"]
+print(s.diff_pairs(ts.pack(far_o, [1, 1]), ts.pack(far_n, [1, 1]), detail=True))   # the left-over path: D > 31, middle > 4 096 lines
 print([x[:4] for x in s.line_hashes(ts.pack(files[:40], exts[:40]), ngram=3)])
 r4 = s.scan(ts.pack(files, exts, grps, 5), 3 | ts.SCAN_REV_B)
 print(s.statements(c)[0][-1])

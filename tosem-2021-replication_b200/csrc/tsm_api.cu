@@ -87,7 +87,8 @@ struct tsm_ctx {
   cudaStream_t copy_stream = nullptr;       // H2D of arena slabs, overlapped with the scan of earlier slabs
   cudaEvent_t slab_ev[64] = {};
   cudaEvent_t ready_ev = nullptr;
-  cudaEvent_t diff_ev[6] = {};             // around the kernels of the diff path (tsm_diff_last_ms)
+  cudaEvent_t diff_ev[8] = {};             // around the kernels of the diff path (tsm_diff_last_ms)
+  uint8_t* h_diff = nullptr;               // 256 B pinned: what the diff path reads back between its kernels (Ctrl x 2, line totals, todo count)
   float diff_ms[3] = {0, 0, 0};            // k_scan over both sides, k_myers, k_myers_trace of the last diff
   struct HostSidePair* res_pair = nullptr; // sides kept in HBM by tsm_diff_upload
   static constexpr int kMaxSlabs = 64;
@@ -195,6 +196,7 @@ extern "C" void tsm_destroy(tsm_ctx* c) {
   free_res_pair(c);
   cudaFree(c->d_cand); cudaFree(c->d_hev); cudaFree(c->d_aev);
   if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
+  if (c->h_diff) cudaFreeHost(c->h_diff);
   for (auto& set : c->ev) for (cudaEvent_t e : set) if (e) cudaEventDestroy(e);
   delete c;
 }
@@ -247,6 +249,7 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   A((void**)&c->d_stats, sizeof(tsm_file_stat) * (size_t)max_files);
   A((void**)&c->d_cand, sizeof(unsigned long long) * (size_t)c->max_events);
   if (rc == TSM_OK && cudaHostAlloc((void**)&c->h_ctrl, sizeof(Ctrl) + 64, cudaHostAllocDefault) != cudaSuccess) rc = TSM_E_CUDA;
+  if (rc == TSM_OK && cudaHostAlloc((void**)&c->h_diff, 256, cudaHostAllocDefault) != cudaSuccess) rc = TSM_E_CUDA;
   for (auto& set : c->ev) for (cudaEvent_t& e : set) if (rc == TSM_OK && cudaEventCreate(&e) != cudaSuccess) rc = TSM_E_CUDA;
   if (rc == TSM_OK) {
     uint32_t lut[256];
@@ -574,9 +577,14 @@ struct HostSide {                                         // device image of one
   int32_t n = 0; size_t ab = 0; uint32_t unit_cap = 0;
   DevBuf arena, off, len, ext, line_base, line_end, line_hash, line_flag;
   DevBuf unit_file, unit_begin, cnt, unit_first, bsum, zero, stats, unit_lines, unit_out, unit_line_base, s_hash, s_end, s_flag;
-  std::vector<unsigned long long> base;                   // host copy of line_base
+  std::vector<unsigned long long> base;                   // host copy of line_base (only when asked for)
+  uint32_t n_units = 0;                                   // (file, chunk) work units: sum of ceil(len / 4 KiB)
+  Ctrl hc{};                                              // read back behind the scan: capacity flags, lines written
+  unsigned long long total = 0;                           // lines of the side
+  Ctrl* pin_hc = nullptr; unsigned long long* pin_total = nullptr;   // where they land (pinned, in the ctx)
   DiffSide d{};
   int launches = 0;
+  void drop_staging() { s_hash.reset(); s_end.reset(); s_flag.reset(); }
 };
 
 // Exclusive scan of n u32 counts into n + 1 u64 (tsm_lines_kernels.cuh); bsum holds n / 1024 + 2 u64.
@@ -594,6 +602,10 @@ int side_upload(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
   h.n = n; h.ab = ab;
   h.unit_cap = (uint32_t)(ab / CH + (size_t)n + 1);
   const uint32_t unit_cap = h.unit_cap;
+  unsigned long long nu = 0;
+  for (int32_t i = 0; i < n; ++i) nu += ((unsigned long long)(uint32_t)k->len[i] + CH - 1) / CH;
+  if (nu > unit_cap) return TSM_E_LAYOUT;
+  h.n_units = (uint32_t)nu;
   if (!h.arena.alloc(ab + 4096) || !h.off.alloc(sizeof(int32_t) * ((size_t)n + 1)) || !h.len.alloc(sizeof(int32_t) * (size_t)n) ||
       !h.ext.alloc((size_t)n) || !h.unit_file.alloc(sizeof(uint32_t) * unit_cap) || !h.unit_begin.alloc(sizeof(uint32_t) * unit_cap) ||
       !h.cnt.alloc(sizeof(uint32_t) * (size_t)n) || !h.unit_first.alloc(sizeof(unsigned long long) * ((size_t)n + 1)) ||
@@ -611,83 +623,117 @@ int side_upload(const tsm_corpus* k, HostSide& h, cudaStream_t st) {
   return TSM_OK;
 }
 
-// One side's line records in file order (docs/SPEC.md sections 2-4) from the uploaded bytes: line_base[n+1], and per
-// line its hash, its end and whether it is an assertion line.  One pass of k_scan over the source
-// (TSM_SCAN_LINE_HASHES: every chunk writes the records of its own lines into a region of the staging arrays), one
-// exclusive scan of the lines per unit, one gather.  The staging arrays are sized for 8-byte lines; a corpus with
-// more lines than that is scanned a second time with the exact size (the first pass counted them).  scan_ms adds
-// the device time of the k_scan launches (CUDA events on st).
-int side_records(tsm_ctx* c, HostSide& h, cudaStream_t st, float* scan_ms) {
+// Line records in file order (docs/SPEC.md sections 2-4) of `ns` uploaded sides (the two sides of the revision pairs, or one
+// corpus): per side line_base[n+1], and per line its hash, its end and whether it is an assertion line.  One pass of
+// k_scan over the source (TSM_SCAN_LINE_HASHES: every chunk writes the records of its own lines into a region of the
+// staging arrays), one exclusive scan of the lines per unit, one gather.  The kernels of all sides are queued before the
+// host looks at anything: ONE synchronisation (capacity flags + line totals) per call instead of four per side.  The
+// staging arrays are sized for 8-byte lines; a side with more lines than that is scanned a second time with the exact
+// size (the first pass counted them).  scan_ms adds the device time of the k_scan launches (CUDA events on st).
+// host_base: also copy line_base to the host (HostSide::base).
+static int side_scan_pass(tsm_ctx* c, HostSide& h, ScanParams& p, size_t cap, int side, cudaStream_t st) {
+  const int ev = side ? 6 : 0;
+  h.pin_hc = reinterpret_cast<Ctrl*>(c->h_diff + 32 * side);            // pinned: the copies below do not stall the host
+  h.pin_total = reinterpret_cast<unsigned long long*>(c->h_diff + 64 + 8 * side);
   const int32_t n = h.n;
-  const size_t ab = h.ab;
-  const uint32_t unit_cap = h.unit_cap;
-  const size_t zero_bytes = 256 + sizeof(SlabCtl);
-  ScanParams p{};
-  p.arena = h.arena.as<uint8_t>(); p.off = h.off.as<int32_t>(); p.len = h.len.as<int32_t>(); p.ext = h.ext.as<uint8_t>();
-  p.grp = nullptr; p.n_files = n; p.n_groups = 1;
-  p.unit_file = h.unit_file.as<uint32_t>(); p.unit_begin = h.unit_begin.as<uint32_t>(); p.unit_cap = unit_cap;
-  p.ctrl = reinterpret_cast<Ctrl*>(h.zero.as<uint8_t>()); p.slab = reinterpret_cast<SlabCtl*>(h.zero.as<uint8_t>() + 256);
-  p.f_begin = 0; p.f_end = n; p.unit_base = 0;
-  p.stats = h.stats.as<tsm_file_stat>();
-  p.cand = nullptr; p.cand_cap = 0; p.hev = nullptr; p.hev_cap = 0; p.aev = nullptr; p.aev_cap = 0; p.counts = nullptr;
-  p.flags = TSM_SCAN_LINE_HASHES; p.four = 4;
-  p.unit_lines = h.unit_lines.as<uint32_t>(); p.unit_out = h.unit_out.as<uint32_t>();
-  // units in (file, chunk) order
-  k_file_units<<<(n + 255) / 256, 256, 0, st>>>(p.len, (uint32_t)n, h.cnt.as<uint32_t>());
-  xscan(h.cnt.as<uint32_t>(), (uint32_t)n, h.bsum.as<unsigned long long>(), h.unit_first.as<unsigned long long>(), st);
-  size_t cap = ab / 8 + 2 * (size_t)unit_cap + 64;
-  Ctrl hc{};
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if (cap > 0xFFFFFFF0ull) return TSM_E_CAPACITY;
-    if (!h.s_hash.alloc(sizeof(unsigned long long) * cap) || !h.s_end.alloc(sizeof(uint32_t) * cap) || !h.s_flag.alloc(cap)) return TSM_E_CUDA;
-    p.lh_hash = h.s_hash.as<unsigned long long>(); p.lh_end = h.s_end.as<uint32_t>(); p.lh_flag = h.s_flag.as<uint8_t>();
-    p.lh_cap = (uint32_t)cap;
-    CU(cudaMemsetAsync(h.zero.p, 0, zero_bytes, st));
-    k_plan_det<<<(n + 1 + 255) / 256, 256, 0, st>>>(p, h.unit_first.as<unsigned long long>());
-    CU(cudaEventRecord(c->diff_ev[0], st));
-    k_scan_t<false><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
-    CU(cudaEventRecord(c->diff_ev[1], st));
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(&hc, p.ctrl, sizeof hc, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (scan_ms) { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[0], c->diff_ev[1]) == cudaSuccess) *scan_ms += ms; }
-    h.launches += 6;
-    if (hc.overflow) return TSM_E_CAPACITY;
-    if (!hc.lh_overflow) break;
-    if (attempt == 1) return TSM_E_CAPACITY;
-    cap = (size_t)hc.n_lh + 64;                            // the first pass counted every region
-  }
-  SlabCtl hs{};
-  CU(cudaMemcpyAsync(&hs, p.slab, sizeof hs, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  const uint32_t n_units = hs.n_units;
-  xscan(p.unit_lines, n_units, h.bsum.as<unsigned long long>(), h.unit_line_base.as<unsigned long long>(), st);
-  unsigned long long total = 0;
-  CU(cudaMemcpyAsync(&total, h.unit_line_base.as<unsigned long long>() + n_units, sizeof total, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  if (!h.line_end.alloc(sizeof(uint32_t) * (size_t)total) || !h.line_hash.alloc(sizeof(unsigned long long) * (size_t)total) ||
-      !h.line_flag.alloc((size_t)total))
-    return TSM_E_CUDA;
-  if (n_units)
-    k_gather_lines<<<(n_units * 32 + 255) / 256, 256, 0, st>>>(p.unit_lines, p.unit_out, h.unit_line_base.as<unsigned long long>(), n_units,
-                                                                 p.lh_hash, p.lh_end, p.lh_flag, h.line_hash.as<unsigned long long>(),
-                                                                 h.line_end.as<uint32_t>(), h.line_flag.as<uint8_t>());
-  k_line_base<<<(n + 1 + 255) / 256, 256, 0, st>>>(h.unit_first.as<unsigned long long>(), h.unit_line_base.as<unsigned long long>(),
-                                                     (uint32_t)n, h.line_base.as<unsigned long long>());
+  if (cap > 0xFFFFFFF0ull) return TSM_E_CAPACITY;
+  if (!h.s_hash.alloc(sizeof(unsigned long long) * cap) || !h.s_end.alloc(sizeof(uint32_t) * cap) || !h.s_flag.alloc(cap)) return TSM_E_CUDA;
+  p.lh_hash = h.s_hash.as<unsigned long long>(); p.lh_end = h.s_end.as<uint32_t>(); p.lh_flag = h.s_flag.as<uint8_t>();
+  p.lh_cap = (uint32_t)cap;
+  CU(cudaMemsetAsync(h.zero.p, 0, 256 + sizeof(SlabCtl), st));
+  k_plan_det<<<(n + 1 + 255) / 256, 256, 0, st>>>(p, h.unit_first.as<unsigned long long>());
+  CU(cudaEventRecord(c->diff_ev[ev], st));
+  k_scan_t<false><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
+  CU(cudaEventRecord(c->diff_ev[ev + 1], st));
   CU(cudaGetLastError());
-  h.base.assign((size_t)n + 1, 0);
-  CU(cudaMemcpyAsync(h.base.data(), h.line_base.p, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  h.launches += 5;
-  h.s_hash.reset(); h.s_end.reset(); h.s_flag.reset();    // staging is done with
-  h.d.arena = h.arena.as<uint8_t>(); h.d.off = h.off.as<int32_t>(); h.d.len = h.len.as<int32_t>();
-  h.d.n_lines = nullptr;
-  h.d.line_base = h.line_base.as<unsigned long long>();
-  h.d.line_end = h.line_end.as<uint32_t>();
-  h.d.line_hash = h.line_hash.as<unsigned long long>();
-  h.d.ext = h.ext.as<uint8_t>();
-  h.d.line_flag = h.line_flag.as<uint8_t>();
+  // lines per unit -> first line of every unit (the unit count is known on the host: units are (file, chunk) in order)
+  xscan(p.unit_lines, h.n_units, h.bsum.as<unsigned long long>(), h.unit_line_base.as<unsigned long long>(), st);
+  CU(cudaMemcpyAsync(h.pin_hc, p.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h.pin_total, h.unit_line_base.as<unsigned long long>() + h.n_units, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  h.launches += 6;
   return TSM_OK;
+}
+
+int sides_records(tsm_ctx* c, HostSide* const* sides, int ns, cudaStream_t st, float* scan_ms, bool host_base) {
+  if (ns < 1 || ns > 2) return TSM_E_ARG;
+  ScanParams ps[2];
+  size_t caps[2];
+  for (int i = 0; i < ns; ++i) {
+    HostSide& h = *sides[i];
+    const int32_t n = h.n;
+    ScanParams& p = ps[i];
+    p = ScanParams{};
+    p.arena = h.arena.as<uint8_t>(); p.off = h.off.as<int32_t>(); p.len = h.len.as<int32_t>(); p.ext = h.ext.as<uint8_t>();
+    p.grp = nullptr; p.n_files = n; p.n_groups = 1;
+    p.unit_file = h.unit_file.as<uint32_t>(); p.unit_begin = h.unit_begin.as<uint32_t>(); p.unit_cap = h.unit_cap;
+    p.ctrl = reinterpret_cast<Ctrl*>(h.zero.as<uint8_t>()); p.slab = reinterpret_cast<SlabCtl*>(h.zero.as<uint8_t>() + 256);
+    p.f_begin = 0; p.f_end = n; p.unit_base = 0;
+    p.stats = h.stats.as<tsm_file_stat>();
+    p.cand = nullptr; p.cand_cap = 0; p.hev = nullptr; p.hev_cap = 0; p.aev = nullptr; p.aev_cap = 0; p.counts = nullptr;
+    p.flags = TSM_SCAN_LINE_HASHES; p.four = 4;
+    p.unit_lines = h.unit_lines.as<uint32_t>(); p.unit_out = h.unit_out.as<uint32_t>();
+    // units in (file, chunk) order
+    k_file_units<<<(n + 255) / 256, 256, 0, st>>>(p.len, (uint32_t)n, h.cnt.as<uint32_t>());
+    xscan(h.cnt.as<uint32_t>(), (uint32_t)n, h.bsum.as<unsigned long long>(), h.unit_first.as<unsigned long long>(), st);
+    caps[i] = h.ab / 8 + 2 * (size_t)h.unit_cap + 64;
+    const int rc = side_scan_pass(c, h, p, caps[i], i, st);
+    if (rc != TSM_OK) return rc;
+  }
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < ns; ++i) {
+    HostSide& h = *sides[i];
+    const int ev = i ? 6 : 0;
+    h.hc = *h.pin_hc; h.total = *h.pin_total;
+    if (scan_ms) { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[ev], c->diff_ev[ev + 1]) == cudaSuccess) *scan_ms += ms; }
+    if (h.hc.overflow) return TSM_E_CAPACITY;
+    if (h.hc.lh_overflow) {                                // more lines than the staging arrays hold: once more, exact size
+      const int rc = side_scan_pass(c, h, ps[i], (size_t)h.hc.n_lh + 64, i, st);
+      if (rc != TSM_OK) return rc;
+      CU(cudaStreamSynchronize(st));
+      h.hc = *h.pin_hc; h.total = *h.pin_total;
+      if (scan_ms) { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[ev], c->diff_ev[ev + 1]) == cudaSuccess) *scan_ms += ms; }
+      if (h.hc.overflow || h.hc.lh_overflow) return TSM_E_CAPACITY;
+    }
+  }
+  for (int i = 0; i < ns; ++i) {
+    HostSide& h = *sides[i];
+    const int32_t n = h.n;
+    const ScanParams& p = ps[i];
+    const unsigned long long total = h.total;
+    if (!h.line_end.alloc(sizeof(uint32_t) * (size_t)total) || !h.line_hash.alloc(sizeof(unsigned long long) * (size_t)total) ||
+        !h.line_flag.alloc((size_t)total))
+      return TSM_E_CUDA;
+    if (h.n_units)
+      k_gather_lines<<<(h.n_units * 32 + 255) / 256, 256, 0, st>>>(p.unit_lines, p.unit_out, h.unit_line_base.as<unsigned long long>(), h.n_units,
+                                                                     p.lh_hash, p.lh_end, p.lh_flag, h.line_hash.as<unsigned long long>(),
+                                                                     h.line_end.as<uint32_t>(), h.line_flag.as<uint8_t>());
+    k_line_base<<<(n + 1 + 255) / 256, 256, 0, st>>>(h.unit_first.as<unsigned long long>(), h.unit_line_base.as<unsigned long long>(),
+                                                       (uint32_t)n, h.line_base.as<unsigned long long>());
+    CU(cudaGetLastError());
+    h.launches += 5;
+    h.base.clear();
+    if (host_base) {
+      h.base.assign((size_t)n + 1, 0);
+      CU(cudaMemcpyAsync(h.base.data(), h.line_base.p, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    }
+    h.d.arena = h.arena.as<uint8_t>(); h.d.off = h.off.as<int32_t>(); h.d.len = h.len.as<int32_t>();
+    h.d.n_lines = nullptr;
+    h.d.line_base = h.line_base.as<unsigned long long>();
+    h.d.line_end = h.line_end.as<uint32_t>();
+    h.d.line_hash = h.line_hash.as<unsigned long long>();
+    h.d.ext = h.ext.as<uint8_t>();
+    h.d.line_flag = h.line_flag.as<uint8_t>();
+  }
+  if (host_base) {
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < ns; ++i) sides[i]->drop_staging();
+  }                                                        // (else the caller drops them behind its next synchronisation:
+  return TSM_OK;                                           //  the gather queued above still reads them)
+}
+
+int side_records(tsm_ctx* c, HostSide& h, cudaStream_t st, float* scan_ms) {
+  HostSide* one[1] = {&h};
+  return sides_records(c, one, 1, st, scan_ms, true);
 }
 }  // namespace
 
@@ -712,54 +758,112 @@ static int check_pair_layout(const tsm_corpus* olds, const tsm_corpus* news, boo
   return TSM_OK;
 }
 
-// The diff proper over two sides whose line records exist: k_myers (edit distance per pair), then for `detail`
-// k_myers_trace (the canonical script: hunks, changed assertion lines).  A pair whose distance D needs more
-// than TSM_DIFF_TRACE_MAX_INTS trace entries ((D+1)(D+2)/2) is not traced: it is reported as ONE hunk
-// (add / del / mod by its counts) with added_assert = removed_assert = -1 (tosemscan.h).
+// The diff proper over two sides whose line records exist.  k_diff_small finishes the common pairs (distance at most
+// 127 lines, middle of at most 4 096 lines) start to finish - search in registers, rows of V and backtrack in shared
+// memory - in four sizes (512 lines / D <= 31 at 32 pairs per SM, 1 024 / 63 at 12, 4 096 / 63 at 5, 4 096 / 127 at 3), each
+// fed on the device by the list the size before it leaves.  What all of them leave over (the `todo` list, normally empty) goes through k_myers (edit distance, V in global scratch) and, for `detail`,
+// k_myers_trace (rows of V in global memory sized from those distances, then the canonical script: hunks, changed
+// assertion lines).  A pair whose distance D needs more than TSM_DIFF_TRACE_MAX_INTS trace entries ((D+1)(D+2)/2) is
+// not traced: it is reported as ONE hunk (add / del / mod by its counts) with added_assert = removed_assert = -1
+// (tosemscan.h).  diff_ms[1] = k_diff_small, diff_ms[2] = the two kernels of the left-over pairs.
 static int diff_core(tsm_ctx* c, HostSide& A, HostSide& B, int32_t n, int64_t* added, int64_t* removed,
                      tsm_diff_detail* detail, cudaStream_t st) {
-  std::vector<unsigned long long> vbase((size_t)n + 1, 0);
-  for (int32_t i = 0; i < n; ++i)
-    vbase[(size_t)i + 1] = vbase[(size_t)i] + 2 * ((A.base[(size_t)i + 1] - A.base[(size_t)i]) + (B.base[(size_t)i + 1] - B.base[(size_t)i])) + 3;
-  DevBuf d_vbase, d_v, d_add, d_rem;
-  if (!d_vbase.alloc(sizeof(unsigned long long) * ((size_t)n + 1)) || !d_v.alloc(sizeof(int32_t) * (size_t)vbase[(size_t)n]) ||
-      !d_add.alloc(sizeof(long long) * (size_t)n) || !d_rem.alloc(sizeof(long long) * (size_t)n))
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  DevBuf d_add, d_rem, d_detail, d_todo1, d_todo2, d_todo3, d_todo, d_ntodo;
+  if (!d_add.alloc(sizeof(long long) * (size_t)n) || !d_rem.alloc(sizeof(long long) * (size_t)n) ||
+      !d_todo1.alloc(sizeof(int32_t) * (size_t)n) || !d_todo2.alloc(sizeof(int32_t) * (size_t)n) || !d_todo3.alloc(sizeof(int32_t) * (size_t)n) || !d_todo.alloc(sizeof(int32_t) * (size_t)n) ||
+      !d_ntodo.alloc(64) || (detail && !d_detail.alloc(sizeof(tsm_diff_detail) * (size_t)n)))
     return TSM_E_CUDA;
-  CU(cudaMemcpyAsync(d_vbase.p, vbase.data(), sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  constexpr uint32_t kSmem1 = DS1_WARPS * ds_warp_bytes(DS1_HCAP, DS1_DCAP), kSmem2 = DS2_WARPS * ds_warp_bytes(DS2_HCAP, DS2_DCAP),
+                     kSmem3 = DS3_WARPS * ds_warp_bytes(DS3_HCAP, DS3_DCAP), kSmem4 = DS4_WARPS * ds_warp_bytes(DS4_HCAP, DS4_DCAP);
+  static_assert(kSmem1 * 4 + 4 * 1024 <= 233472 && kSmem2 * 6 + 6 * 1024 <= 233472 && kSmem3 * 5 + 5 * 1024 <= 233472 &&
+                kSmem4 * 3 + 3 * 1024 <= 233472, "pairs per SM");
+  static bool smem_set = false;
+  if (!smem_set) {
+    CU(cudaFuncSetAttribute(k_diff_small<DS1_HCAP, DS1_DCAP, DS1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1));
+    CU(cudaFuncSetAttribute(k_diff_small<DS2_HCAP, DS2_DCAP, DS2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
+    CU(cudaFuncSetAttribute(k_diff_small<DS3_HCAP, DS3_DCAP, DS3_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3));
+    CU(cudaFuncSetAttribute(k_diff_small<DS4_HCAP, DS4_DCAP, DS4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem4));
+    smem_set = true;
+  }
+  CU(cudaMemsetAsync(d_ntodo.p, 0, 64, st));
+  uint32_t* cnt = d_ntodo.as<uint32_t>();                  // [0..3] pairs each size left over, [4..7] the sizes' work counters
+  const uint8_t* fa = detail ? A.d.line_flag : nullptr;
+  const uint8_t* fb = detail ? B.d.line_flag : nullptr;
+  tsm_diff_detail* d_det = detail ? d_detail.as<tsm_diff_detail>() : nullptr;
+  long long* da = d_add.as<long long>();
+  long long* dr = d_rem.as<long long>();
   CU(cudaEventRecord(c->diff_ev[2], st));
-  k_myers<<<(n * 32 + 127) / 128, 128, 0, st>>>(A.d.line_hash, A.d.line_base, B.d.line_hash, B.d.line_base, n,
-                                               d_v.as<int32_t>(), d_vbase.as<unsigned long long>(),
-                                               d_add.as<long long>(), d_rem.as<long long>());
+  k_diff_small<DS1_HCAP, DS1_DCAP, DS1_WARPS><<<std::min((n + DS1_WARPS - 1) / DS1_WARPS, c->sms * 4), DS1_WARPS * 32, kSmem1, st>>>(
+      A.d.line_hash, A.d.line_base, fa, B.d.line_hash, B.d.line_base, fb, nullptr, nullptr, n, cnt + 4, da, dr, d_det, d_todo1.as<int32_t>(), cnt + 0);
+  k_diff_small<DS2_HCAP, DS2_DCAP, DS2_WARPS><<<std::min((n + DS2_WARPS - 1) / DS2_WARPS, c->sms * 6), DS2_WARPS * 32, kSmem2, st>>>(
+      A.d.line_hash, A.d.line_base, fa, B.d.line_hash, B.d.line_base, fb, d_todo1.as<int32_t>(), cnt + 0, n, cnt + 5, da, dr, d_det, d_todo2.as<int32_t>(), cnt + 1);
+  k_diff_small<DS3_HCAP, DS3_DCAP, DS3_WARPS><<<std::min(n, c->sms * 5), DS3_WARPS * 32, kSmem3, st>>>(
+      A.d.line_hash, A.d.line_base, fa, B.d.line_hash, B.d.line_base, fb, d_todo2.as<int32_t>(), cnt + 1, n, cnt + 6, da, dr, d_det, d_todo3.as<int32_t>(), cnt + 2);
+  k_diff_small<DS4_HCAP, DS4_DCAP, DS4_WARPS><<<std::min(n, c->sms * 3), DS4_WARPS * 32, kSmem4, st>>>(
+      A.d.line_hash, A.d.line_base, fa, B.d.line_hash, B.d.line_base, fb, d_todo3.as<int32_t>(), cnt + 2, n, cnt + 7, da, dr, d_det, d_todo.as<int32_t>(), cnt + 3);
   CU(cudaEventRecord(c->diff_ev[3], st));
   CU(cudaGetLastError());
-  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  uint32_t* pin_nt = reinterpret_cast<uint32_t*>(c->h_diff + 80);
+  CU(cudaMemcpyAsync(pin_nt, cnt + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(added, d_add.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(removed, d_rem.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (detail) CU(cudaMemcpyAsync(detail, d_detail.p, sizeof(tsm_diff_detail) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  A.drop_staging(); B.drop_staging();
+  const uint32_t nt = *pin_nt;
+  { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[2], c->diff_ev[3]) == cudaSuccess) c->diff_ms[1] = ms; }
+  c->launches = A.launches + B.launches + 4;
+  c->diff_ms[2] = 0;
+  if (nt == 0) return TSM_OK;
+  // ---- the left-over pairs: long middles, far-apart revisions
+  std::vector<int32_t> todo(nt);
+  CU(cudaMemcpyAsync(todo.data(), d_todo.p, sizeof(int32_t) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+  for (HostSide* h : {&A, &B})
+    if (h->base.empty()) {
+      h->base.assign((size_t)n + 1, 0);
+      CU(cudaMemcpyAsync(h->base.data(), h->line_base.p, sizeof(unsigned long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    }
+  CU(cudaStreamSynchronize(st));
+  std::vector<unsigned long long> vbase((size_t)nt + 1, 0);
+  for (uint32_t s = 0; s < nt; ++s) {
+    const size_t i = (size_t)todo[s];
+    vbase[(size_t)s + 1] = vbase[s] + 2 * ((A.base[i + 1] - A.base[i]) + (B.base[i + 1] - B.base[i])) + 3;
+  }
+  DevBuf d_vbase, d_v;
+  if (!d_vbase.alloc(sizeof(unsigned long long) * ((size_t)nt + 1)) || !d_v.alloc(sizeof(int32_t) * (size_t)vbase[nt])) return TSM_E_CUDA;
+  CU(cudaMemcpyAsync(d_vbase.p, vbase.data(), sizeof(unsigned long long) * ((size_t)nt + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(c->diff_ev[4], st));
+  k_myers<<<(nt * 32 + 127) / 128, 128, 0, st>>>(A.d.line_hash, A.d.line_base, B.d.line_hash, B.d.line_base, (int32_t)nt,
+                                                d_v.as<int32_t>(), d_vbase.as<unsigned long long>(),
+                                                d_add.as<long long>(), d_rem.as<long long>(), d_todo.as<int32_t>());
+  CU(cudaEventRecord(c->diff_ev[5], st));
+  CU(cudaGetLastError());
   CU(cudaMemcpyAsync(added, d_add.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(removed, d_rem.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[2], c->diff_ev[3]) == cudaSuccess) c->diff_ms[1] = ms; }
-  c->launches = A.launches + B.launches + 1;
-  c->diff_ms[2] = 0;
+  { float ms = 0; if (cudaEventElapsedTime(&ms, c->diff_ev[4], c->diff_ev[5]) == cudaSuccess) c->diff_ms[2] += ms; }
+  c->launches++;
   if (!detail) return TSM_OK;
-  // ---- hunks: second search with the rows of V kept; rows sized from the distances just computed,
+  // ---- their hunks: second search with the rows of V kept; rows sized from the distances just computed,
   //      pairs processed in batches of at most 2^28 trace ints (1 GiB)
   d_v.reset();                                             // the first search's scratch is no longer needed
-  DevBuf d_detail, d_tbase;
-  if (!d_detail.alloc(sizeof(tsm_diff_detail) * (size_t)n) || !d_tbase.alloc(sizeof(unsigned long long) * ((size_t)n + 1)))
-    return TSM_E_CUDA;
-  CU(cudaMemsetAsync(d_detail.p, 0, sizeof(tsm_diff_detail) * (size_t)n, st));
-  std::vector<unsigned long long> tbase((size_t)n + 1, 0);
+  DevBuf d_tbase;
+  if (!d_tbase.alloc(sizeof(unsigned long long) * ((size_t)nt + 1))) return TSM_E_CUDA;
+  std::vector<unsigned long long> tbase((size_t)nt + 1, 0);
   std::vector<int32_t> untraced;
   const unsigned long long kBatch = TSM_DIFF_TRACE_MAX_INTS;
-  int32_t p0 = 0;
-  while (p0 < n) {
-    int32_t p1 = p0;
+  uint32_t p0 = 0;
+  while (p0 < nt) {
+    uint32_t p1 = p0;
     unsigned long long tot = 0;
-    while (p1 < n) {
-      const unsigned long long D = (unsigned long long)(added[p1] + removed[p1]);
+    while (p1 < nt) {
+      const int32_t i = todo[p1];
+      const unsigned long long D = (unsigned long long)(added[i] + removed[i]);
       unsigned long long need = (D + 1) * (D + 2) / 2;
-      if (need > kBatch) { untraced.push_back(p1); need = 1; }      // k_myers_trace skips it (row table of one int)
+      if (need > kBatch) { untraced.push_back(i); need = 1; }       // k_myers_trace skips it (row table of one int)
       if (p1 > p0 && tot + need > kBatch) break;
-      tbase[(size_t)p1] = tot;
+      tbase[p1] = tot;
       tot += need;
       ++p1;
     }
@@ -769,9 +873,9 @@ static int diff_core(tsm_ctx* c, HostSide& A, HostSide& B, int32_t n, int64_t* a
                        cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(c->diff_ev[4], st));
     k_myers_trace<<<((p1 - p0) * 32 + 127) / 128, 128, 0, st>>>(
-        A.d.line_hash, A.d.line_base, A.d.line_flag, B.d.line_hash, B.d.line_base, B.d.line_flag, p0, p1 - p0,
+        A.d.line_hash, A.d.line_base, A.d.line_flag, B.d.line_hash, B.d.line_base, B.d.line_flag, (int32_t)p0, (int32_t)(p1 - p0),
         d_trace.as<int32_t>(), d_tbase.as<unsigned long long>(), d_add.as<long long>(), d_rem.as<long long>(),
-        (long long)TSM_DIFF_TRACE_MAX_D, d_detail.as<tsm_diff_detail>());
+        (long long)TSM_DIFF_TRACE_MAX_D, d_detail.as<tsm_diff_detail>(), d_todo.as<int32_t>());
     CU(cudaEventRecord(c->diff_ev[5], st));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
@@ -804,8 +908,8 @@ extern "C" int tsm_diff_pairs_detail(tsm_ctx* c, const tsm_corpus* olds, const t
   c->diff_ms[0] = 0;
   rc = side_upload(olds, A, st);
   if (rc == TSM_OK) rc = side_upload(news, B, st);
-  if (rc == TSM_OK) rc = side_records(c, A, st, &c->diff_ms[0]);
-  if (rc == TSM_OK) rc = side_records(c, B, st, &c->diff_ms[0]);
+  HostSide* both[2] = {&A, &B};
+  if (rc == TSM_OK) rc = sides_records(c, both, 2, st, &c->diff_ms[0], false);
   if (rc != TSM_OK) return rc;
   return diff_core(c, A, B, n, added, removed, detail, st);
 }
@@ -841,8 +945,8 @@ extern "C" int tsm_diff_resident(tsm_ctx* c, int64_t* added, int64_t* removed, t
   HostSidePair& P = *c->res_pair;
   c->diff_ms[0] = 0;
   P.A.launches = P.B.launches = 0;
-  int rc = side_records(c, P.A, st, &c->diff_ms[0]);
-  if (rc == TSM_OK) rc = side_records(c, P.B, st, &c->diff_ms[0]);
+  HostSide* both[2] = {&P.A, &P.B};
+  int rc = sides_records(c, both, 2, st, &c->diff_ms[0], false);
   if (rc != TSM_OK) return rc;
   return diff_core(c, P.A, P.B, P.n, added, removed, detail, st);
 }

@@ -19,7 +19,8 @@
 //   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
-//   tosem-scan releases <snapshot-root>=<tag>... [--out F]
+//   tosem-scan releases <snapshot-root>=<tag>... [--out F]   |   releases --git <repository> [<revision>...] [--out F]
+//   tosem-scan history <git-repository> [--rev R] [--max-commits N] [--all-files] [--dry-run] [--out F]
 #include <algorithm>
 #include <atomic>
 #include <cctype>
@@ -34,6 +35,7 @@
 #include <fstream>
 #include <future>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -43,6 +45,7 @@
 #include <nccl.h>
 
 #include "../../include/tosemscan.h"
+#include "git_store.hpp"
 
 namespace fs = std::filesystem;
 
@@ -90,7 +93,10 @@ static std::vector<std::vector<std::string>> csv_read(const std::string& path) {
 }
 
 // ---------------------------------------------------------------------------------- S0-S2: walk and tag
-struct FileEntry { std::string rel, abs; int ext; int grp; int64_t size; };
+struct FileEntry {
+  std::string rel, abs; int ext; int grp; int64_t size;
+  std::shared_ptr<const std::vector<uint8_t>> blob;       // set instead of `abs` when the bytes come from a git object store
+};
 
 static int ext_tag(const std::string& rel) {               // S1
   const size_t d = rel.rfind('.');
@@ -142,7 +148,7 @@ static void walk(const std::string& root, int grp, bool all_files, std::vector<F
       if (lower(rel).find("test") == std::string::npos) continue;          // S0: path contains `test`
       if (ext == TSM_EXT_OTHER) continue;                                   // S1: no rows for other extensions
     }
-    out.push_back({rel, p.string(), ext, grp, (int64_t)fs::file_size(p)});
+    out.push_back({rel, p.string(), ext, grp, (int64_t)fs::file_size(p), nullptr});
   }
 }
 
@@ -211,6 +217,7 @@ static void load_batch(const std::vector<FileEntry>& files, Batch& b) {
   std::atomic<long> bad{-1};
   auto reader = [&](unsigned t) {
     for (size_t i = t; i < n && bad.load(std::memory_order_relaxed) < 0; i += nt) {
+      if (files[b.idx[i]].blob) { if (b.len[i]) memcpy(b.arena + b.off[i], files[b.idx[i]].blob->data(), (size_t)b.len[i]); continue; }
       const int fd = open(files[b.idx[i]].abs.c_str(), O_RDONLY);
       int64_t got = 0;
       while (fd >= 0 && got < b.len[i]) {
@@ -801,9 +808,7 @@ static int cmd_body(const std::vector<std::string>& roots, const std::string& ou
 struct SnapFile { std::string rel; uint64_t digest; int64_t size; uint32_t n_assert; std::string hist; };
 
 // Scan one snapshot: per selected test file its digest, assertion total and "n:category, ..." histogram.
-static std::vector<SnapFile> scan_snapshot(const std::string& root) {
-  std::vector<FileEntry> files;
-  walk(root, 0, false, files);
+static std::vector<SnapFile> scan_snapshot(const std::vector<FileEntry>& files) {
   std::vector<SnapFile> out;
   size_t first = 0;
   while (first < files.size()) {
@@ -843,15 +848,63 @@ static std::vector<SnapFile> scan_snapshot(const std::string& root) {
   return out;
 }
 
-static int cmd_releases(const std::vector<std::string>& specs, const std::string& out_path) {
+// The selected test files (S0 + S1) of one tree of a git repository, in the order `walk` gives for a checkout of it
+// (names sorted at every level, depth first); their bytes are inflated here and scanned like files read from disk.
+static void walk_git(gitstore::Store& gs, const gitstore::Oid& tree, const std::string& prefix, bool all_files, std::vector<FileEntry>& out) {
+  std::vector<gitstore::TreeEntry> es;
+  if (!gs.tree(tree, es)) die("unreadable tree " + tree.hex());
+  std::sort(es.begin(), es.end(), [](const gitstore::TreeEntry& a, const gitstore::TreeEntry& b) { return a.name < b.name; });
+  for (const gitstore::TreeEntry& e : es) {
+    const std::string rel = prefix + e.name;
+    if (e.is_tree()) { walk_git(gs, e.oid, rel + "/", all_files, out); continue; }
+    if (!e.is_blob()) continue;
+    const int ext = ext_tag(rel);
+    if (!all_files && (lower(rel).find("test") == std::string::npos || ext == TSM_EXT_OTHER)) continue;
+    gitstore::Object o;
+    if (!gs.read(e.oid, o) || o.type != gitstore::OBJ_BLOB) die("unreadable blob " + e.oid.hex());
+    if (o.data.size() > 0x7fff0000u) die("blob too large: " + rel);
+    FileEntry f{rel, "", ext, 0, (int64_t)o.data.size(), nullptr};
+    f.blob = std::make_shared<const std::vector<uint8_t>>(std::move(o.data));
+    out.push_back(std::move(f));
+  }
+}
+
+// specs: <snapshot-root>=<tag>...; or, with --git <repository>, revisions (tags, branches, object names) in release
+// order - none = every tag of the repository, oldest commit first.
+static int cmd_releases(const std::vector<std::string>& specs_in, const std::string& out_path, const std::string& git_repo) {
+  std::vector<std::string> specs = specs_in;
+  gitstore::Store gs;
+  if (!git_repo.empty()) {
+    std::string err;
+    if (!gs.open(git_repo, err)) die(err);
+    if (specs.empty()) {
+      std::vector<std::pair<long long, std::string>> byt;
+      for (const std::string& t : gs.tag_names()) {
+        gitstore::Oid id; gitstore::Commit c;
+        if (gs.resolve("refs/tags/" + t, id) && gs.commit(id, c)) byt.push_back({c.time, t});
+      }
+      std::sort(byt.begin(), byt.end());
+      for (auto& kv : byt) specs.push_back(kv.second);
+      if (specs.empty()) die("the repository has no tags; name the revisions");
+    }
+  }
   struct Identity { std::string name; std::vector<std::string> path; uint64_t digest; int64_t size; uint32_t n_assert; std::string hist; std::string cur; };
   std::vector<std::string> tags;
   std::vector<Identity> ids;
   for (size_t t = 0; t < specs.size(); ++t) {
-    const size_t eq = specs[t].rfind('=');
-    if (eq == std::string::npos) die("releases arguments are <snapshot-root>=<tag>");
-    tags.push_back(specs[t].substr(eq + 1));
-    const std::vector<SnapFile> snap = scan_snapshot(specs[t].substr(0, eq));
+    std::vector<FileEntry> files;
+    if (!git_repo.empty()) {
+      gitstore::Oid id; gitstore::Commit c;
+      if (!gs.resolve(specs[t], id) || !gs.commit(id, c)) die("cannot resolve revision " + specs[t]);
+      tags.push_back(specs[t]);
+      walk_git(gs, c.tree, "", false, files);
+    } else {
+      const size_t eq = specs[t].rfind('=');
+      if (eq == std::string::npos) die("releases arguments are <snapshot-root>=<tag>");
+      tags.push_back(specs[t].substr(eq + 1));
+      walk(specs[t].substr(0, eq), 0, false, files);
+    }
+    const std::vector<SnapFile> snap = scan_snapshot(files);
     std::vector<char> id_taken(ids.size(), 0), f_done(snap.size(), 0);
     auto base_of = [](const std::string& p) { const size_t s = p.rfind('/'); return s == std::string::npos ? p : p.substr(s + 1); };
     auto bind = [&](size_t fi, size_t id) {
@@ -930,7 +983,7 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
     pairs.swap(text);
   }
   auto pack = [&](bool old_side, Batch& B, std::vector<FileEntry>& tmp) {
-    for (const Pair& p : pairs) { const FileEntry* f = old_side ? p.o : p.n; tmp.push_back(f ? *f : FileEntry{p.rel, "", 0, 0, 0}); }
+    for (const Pair& p : pairs) { const FileEntry* f = old_side ? p.o : p.n; tmp.push_back(f ? *f : FileEntry{p.rel, "", 0, 0, 0, nullptr}); }
     const size_t n = tmp.size();
     B.idx.resize(n);
     for (size_t i = 0; i < n; ++i) B.idx[i] = (uint32_t)i;
@@ -984,13 +1037,168 @@ static int cmd_diff(const std::string& old_root, const std::string& new_root, co
   return 0;
 }
 
+// ---------------------------------------------------------------------------------- S8 on a real repository
+// `tosem-scan history <repo>`: the churn of the test files along the first-parent history of a revision, read straight
+// from the git object store (host/git_store.hpp: loose objects, packfiles, refs - no `git` process, no checkout).
+// Host: commit chain, tree diff by object name (only entries whose blob changed are opened), blob inflation into the
+// two pinned arenas.  GPU: line records of both sides + per-pair Myers + hunks + changed assertion lines
+// (tsm_diff_pairs_detail), one call per batch of at most ~512 MiB per side.  Rows: one per (commit, changed file).
+struct BlobChange { std::string path; gitstore::Oid o, n; bool has_o, has_n; };
+
+static void tree_diff(gitstore::Store& gs, const gitstore::Oid* a, const gitstore::Oid* b, const std::string& prefix,
+                      bool all_files, std::vector<BlobChange>& out) {
+  std::vector<gitstore::TreeEntry> ea, eb;
+  if (a && !gs.tree(*a, ea)) die("unreadable tree " + a->hex());
+  if (b && !gs.tree(*b, eb)) die("unreadable tree " + b->hex());
+  std::map<std::string, const gitstore::TreeEntry*> ma, mb;
+  for (auto& e : ea) ma[e.name] = &e;
+  for (auto& e : eb) mb[e.name] = &e;
+  std::vector<std::string> names;
+  for (auto& kv : ma) names.push_back(kv.first);
+  for (auto& kv : mb) if (!ma.count(kv.first)) names.push_back(kv.first);
+  std::sort(names.begin(), names.end());
+  for (const std::string& nm : names) {
+    const gitstore::TreeEntry* x = ma.count(nm) ? ma[nm] : nullptr;
+    const gitstore::TreeEntry* y = mb.count(nm) ? mb[nm] : nullptr;
+    if (x && y && x->oid == y->oid && x->is_tree() == y->is_tree()) continue;     // same object: nothing below it changed
+    const std::string path = prefix + nm;
+    const bool xt = x && x->is_tree(), yt = y && y->is_tree();
+    if (xt || yt) tree_diff(gs, xt ? &x->oid : nullptr, yt ? &y->oid : nullptr, path + "/", all_files, out);
+    const bool xb = x && x->is_blob(), yb = y && y->is_blob();                     // (symlinks and submodules are not files of the study)
+    if (!xb && !yb) continue;
+    if (!all_files && (lower(path).find("test") == std::string::npos || ext_tag(path) == TSM_EXT_OTHER)) continue;   // S0, S1
+    BlobChange c{path, {}, {}, xb, yb};
+    if (xb) c.o = x->oid;
+    if (yb) c.n = y->oid;
+    out.push_back(c);
+  }
+}
+
+// --dry-run: no GPU - the rows carry the object names, sizes and an FNV-1a checksum of both blobs instead of the counts
+// (what the CPU tests compare with `git diff-tree` / `git cat-file`).
+static int cmd_history(const std::string& repo, const std::string& rev, int64_t max_commits, bool all_files, const std::string& out_path,
+                       bool dry_run) {
+  gitstore::Store gs;
+  std::string err;
+  if (!gs.open(repo, err)) die(err);
+  gitstore::Oid head;
+  if (!gs.resolve(rev, head)) die("cannot resolve revision " + rev);
+  struct Step { gitstore::Oid id; gitstore::Commit c; };
+  std::vector<Step> chain;
+  for (gitstore::Oid id = head; max_commits <= 0 || (int64_t)chain.size() < max_commits;) {
+    Step st{id, {}};
+    if (!gs.commit(id, st.c)) die("unreadable commit " + id.hex());
+    chain.push_back(st);
+    if (st.c.parents.empty()) break;
+    id = st.c.parents[0];
+  }
+  std::reverse(chain.begin(), chain.end());                 // oldest first
+  struct Row { size_t step; BlobChange ch; };
+  std::vector<Row> rows;
+  for (size_t i = 0; i < chain.size(); ++i) {
+    gitstore::Commit parent;
+    const bool has_parent = !chain[i].c.parents.empty();
+    if (has_parent && !gs.commit(chain[i].c.parents[0], parent)) die("unreadable commit " + chain[i].c.parents[0].hex());
+    if (has_parent && parent.tree == chain[i].c.tree) continue;
+    std::vector<BlobChange> ch;
+    tree_diff(gs, has_parent ? &parent.tree : nullptr, &chain[i].c.tree, "", all_files, ch);
+    for (auto& c : ch) rows.push_back({i, c});
+  }
+  std::ofstream os;
+  if (!out_path.empty()) {
+    os.open(out_path, std::ios::binary);
+    if (dry_run) csv_row(os, {"commit", "parent", "time", "fileName", "old_blob", "new_blob", "old_size", "new_size", "old_fnv", "new_fnv"});
+    else csv_row(os, {"commit", "parent", "time", "fileName", "cloc", "added", "removed", "hunks_add", "hunks_del", "hunks_mod", "added_assert", "removed_assert"});
+  }
+  tsm_ctx* ctx = nullptr;
+  if (!dry_run) ck(tsm_create(&ctx, 0, 1 << 20, 16, 1, 0), "tsm_create");
+  std::vector<int64_t> per_add(chain.size(), 0), per_rem(chain.size(), 0), per_files(chain.size(), 0);
+  int64_t binaries = 0, pairs_done = 0;
+  const int64_t kBatch = 512ll << 20;
+  size_t r0 = 0;
+  while (r0 < rows.size()) {
+    // inflate blobs until a side of the batch is full
+    std::vector<std::vector<uint8_t>> bo, bn;
+    std::vector<size_t> idx;
+    int64_t so = 0, sn = 0;
+    size_t r1 = r0;
+    for (; r1 < rows.size() && so < kBatch && sn < kBatch; ++r1) {
+      const BlobChange& c = rows[r1].ch;
+      gitstore::Object x, y;
+      if (c.has_o && (!gs.read(c.o, x) || x.type != gitstore::OBJ_BLOB)) die("unreadable blob " + c.o.hex());
+      if (c.has_n && (!gs.read(c.n, y) || y.type != gitstore::OBJ_BLOB)) die("unreadable blob " + c.n.hex());
+      auto binary = [](const std::vector<uint8_t>& v) { return !v.empty() && memchr(v.data(), 0, std::min<size_t>(v.size(), 8000)) != nullptr; };
+      if (dry_run) {
+        auto fnv = [](const std::vector<uint8_t>& v) { uint64_t h = 0xcbf29ce484222325ull; for (uint8_t b : v) h = (h ^ b) * 0x100000001b3ull; char buf[24]; snprintf(buf, sizeof buf, "%016llx", (unsigned long long)h); return std::string(buf); };
+        const Step& st = chain[rows[r1].step];
+        if (os.is_open())
+          csv_row(os, {st.id.hex(), st.c.parents.empty() ? "" : st.c.parents[0].hex(), std::to_string(st.c.time), c.path, c.has_o ? c.o.hex() : "", c.has_n ? c.n.hex() : "",
+                       std::to_string(x.data.size()), std::to_string(y.data.size()), fnv(x.data), fnv(y.data)});
+        per_files[rows[r1].step]++;
+        continue;
+      }
+      if (binary(x.data) || binary(y.data)) { ++binaries; continue; }              // like git's numstat: no line counts for binary files
+      if (x.data.size() > 0x7fff0000u || y.data.size() > 0x7fff0000u) die("blob too large: " + c.path);
+      so += (int64_t)x.data.size() + 256; sn += (int64_t)y.data.size() + 256;
+      bo.push_back(std::move(x.data)); bn.push_back(std::move(y.data)); idx.push_back(r1);
+    }
+    const size_t n = idx.size();
+    if (n) {
+      Batch A, N;
+      auto pack = [&](Batch& B, const std::vector<std::vector<uint8_t>>& blobs) {
+        B.len.resize(n); B.off.resize(n + 1); B.ext.assign(n, 0); B.grp.assign(n, 0);
+        for (size_t i = 0; i < n; ++i) B.len[i] = (int32_t)blobs[i].size();
+        B.bytes = tsm_layout(B.len.data(), (int32_t)n, B.off.data());
+        if (B.bytes < 0) die("batch does not fit one int32-indexed arena");
+        B.arena = (uint8_t*)tsm_host_alloc(std::max<int64_t>(B.bytes, 128));
+        if (!B.arena) die("pinned arena allocation failed");
+        memset(B.arena, 0, (size_t)std::max<int64_t>(B.bytes, 128));
+        for (size_t i = 0; i < n; ++i) if (B.len[i]) memcpy(B.arena + B.off[i], blobs[i].data(), blobs[i].size());
+      };
+      pack(A, bo); pack(N, bn);
+      for (size_t i = 0; i < n; ++i) { A.ext[i] = (uint8_t)ext_tag(rows[idx[i]].ch.path); N.ext[i] = A.ext[i]; }
+      tsm_corpus ca{A.arena, A.off.data(), A.len.data(), A.ext.data(), A.grp.data(), (int32_t)n, 1};
+      tsm_corpus cn{N.arena, N.off.data(), N.len.data(), N.ext.data(), N.grp.data(), (int32_t)n, 1};
+      std::vector<int64_t> added(n), removed(n);
+      std::vector<tsm_diff_detail> det(n);
+      ck(tsm_diff_pairs_detail(ctx, &ca, &cn, added.data(), removed.data(), det.data(), nullptr), "tsm_diff_pairs_detail");
+      for (size_t i = 0; i < n; ++i) {
+        const Row& r = rows[idx[i]];
+        per_add[r.step] += added[i]; per_rem[r.step] += removed[i]; per_files[r.step]++;
+        if (os.is_open()) {
+          const Step& st = chain[r.step];
+          csv_row(os, {st.id.hex(), st.c.parents.empty() ? "" : st.c.parents[0].hex(), std::to_string(st.c.time), r.ch.path,
+                       std::to_string(added[i] + removed[i]), std::to_string(added[i]), std::to_string(removed[i]),
+                       std::to_string(det[i].hunks_add), std::to_string(det[i].hunks_del), std::to_string(det[i].hunks_mod),
+                       std::to_string(det[i].added_assert), std::to_string(det[i].removed_assert)});
+        }
+      }
+      pairs_done += (int64_t)n;
+      tsm_host_free(A.arena); tsm_host_free(N.arena);
+    }
+    r0 = r1;
+  }
+  if (ctx) tsm_destroy(ctx);
+  printf("commit,files,cloc,added,removed\r\n");
+  int64_t ta = 0, tr = 0;
+  for (size_t i = 0; i < chain.size(); ++i) {
+    ta += per_add[i]; tr += per_rem[i];
+    printf("%s,%lld,%lld,%lld,%lld\r\n", chain[i].id.hex().c_str(), (long long)per_files[i], (long long)(per_add[i] + per_rem[i]),
+           (long long)per_add[i], (long long)per_rem[i]);
+  }
+  fprintf(stderr, "tosem-scan: history of %s: %zu commits, %lld changed files diffed on the GPU, %lld binary skipped, cloc %lld (+%lld -%lld)\n",
+          rev.c_str(), chain.size(), (long long)pairs_done, (long long)binaries, (long long)(ta + tr), (long long)ta, (long long)tr);
+  return 0;
+}
+
 static void usage() {
   fprintf(stderr,
           "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N] [--rev-b]\n"
           "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
-          "       tosem-scan releases <snapshot-root>=<tag>... [--out F]\n"
+          "       tosem-scan releases <snapshot-root>=<tag>... [--out F]   |   releases --git <repository> [<revision>...] [--out F]\n"
+          "       tosem-scan history <git-repository> [--rev R] [--max-commits N] [--all-files] [--dry-run] [--out F]\n"
           "Scans run on the GPU through libtosemscan.so (sm_100a); there is no CPU fallback.\n");
 }
 
@@ -999,19 +1207,22 @@ int main(int argc, char** argv) {
   const std::string cmd = argv[1];
   std::vector<std::string> pos;
   std::map<std::string, std::string> opt;
-  bool all_files = false, rev_b = false;
+  bool all_files = false, rev_b = false, dry_run = false;
   for (int i = 2; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--all-files") all_files = true;
     else if (a == "--rev-b") rev_b = true;
+    else if (a == "--dry-run") dry_run = true;
     else if (a.rfind("--", 0) == 0) { if (i + 1 >= argc) die("missing value for " + a); opt[a] = argv[++i]; }
     else pos.push_back(a);
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
                                         opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30), rev_b); }
   if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"], opt["--correlate"]); }
-  if (cmd == "releases") { if (pos.empty()) die("releases needs <root>=<tag>..."); return cmd_releases(pos, opt["--out"]); }
+  if (cmd == "releases") { if (pos.empty() && !opt.count("--git")) die("releases needs <root>=<tag>... or --git <repository>"); return cmd_releases(pos, opt["--out"], opt["--git"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
+  if (cmd == "history") { if (pos.size() != 1) die("history needs the repository"); return cmd_history(pos[0], opt.count("--rev") ? opt["--rev"] : "HEAD",
+                                                  opt.count("--max-commits") ? atoll(opt["--max-commits"].c_str()) : 0, all_files, opt["--out"], dry_run); }
   if (cmd == "diff") { if (pos.size() != 2) die("diff needs <old-root> <new-root>"); return cmd_diff(pos[0], pos[1], opt["--out"]); }
   usage();
   return 2;

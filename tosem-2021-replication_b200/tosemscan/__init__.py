@@ -493,7 +493,11 @@ class Scanner:
         if rc:
             raise TsmError(rc, "tsm_diff_upload")
         self._pairs = olds.n_files
-        self._diff_out = (np.zeros(self._pairs, np.int64), np.zeros(self._pairs, np.int64), np.zeros(max(self._pairs, 1), DIFF_DETAIL))
+        n = max(self._pairs, 1)                              # results land in pinned memory: D2H at the PCIe rate, no staging copy
+        bufs = [host_buffer(n * 8), host_buffer(n * 8), host_buffer(n * DIFF_DETAIL.itemsize)]
+        self._diff_pins = [b[1] for b in bufs]
+        self._diff_out = (bufs[0][0][:self._pairs * 8].view(np.int64), bufs[1][0][:self._pairs * 8].view(np.int64),
+                          bufs[2][0][:n * DIFF_DETAIL.itemsize].view(DIFF_DETAIL))
 
     def diff_resident(self, detail=True, stream=None):
         """The diff kernels over the resident sides; returns (added, removed[, detail]) - buffers reused across calls."""
@@ -504,7 +508,7 @@ class Scanner:
         return (added, removed, det[:self._pairs]) if detail else (added, removed)
 
     def diff_last_ms(self):
-        """Device time of the last diff call: [k_scan over both sides, k_myers, k_myers_trace] in ms."""
+        """Device time of the last diff call: [k_scan over both sides, k_diff_small, k_myers + k_myers_trace of the pairs it left over] in ms."""
         ms = (C.c_float * 3)()
         lib().tsm_diff_last_ms(self._ctx, C.byref(ms))
         return [float(x) for x in ms]
