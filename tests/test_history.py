@@ -179,3 +179,30 @@ def test_history_churn_matches_git_numstat(repo, tmp_path):
     for c in chain:
         mine = [v for (cc, _), v in got.items() if cc == c]
         assert [int(v) for v in tot[c]] == [len(mine), sum(a + d for a, d in mine), sum(a for a, _ in mine), sum(d for _, d in mine)]
+
+
+@pytest.mark.gpu
+def test_release_matrix_from_tags_equals_the_matrix_of_checkouts(repo, tmp_path):
+    """`releases --git` reads the trees of the tags from the object store; the matrix must equal the one `releases`
+    builds from work trees of the same revisions (SPEC section 11 is unchanged: only where the bytes come from differs)."""
+    roots = []
+    for tag in ("v1", "v2", "HEAD"):
+        d = tmp_path / ("co_" + tag)
+        os.makedirs(d)
+        tar = git(repo, "archive", "--format=tar", tag, text=False)
+        subprocess.run(["tar", "-x", "-C", str(d)], input=tar, check=True)
+        roots.append("%s=%s" % (d, tag))
+    a, b = tmp_path / "from_dirs.csv", tmp_path / "from_git.csv"
+    r1 = subprocess.run([CLI, "releases"] + roots + ["--out", str(a)], capture_output=True, text=True)
+    r2 = subprocess.run([CLI, "releases", "--git", str(repo), "v1", "v2", "HEAD", "--out", str(b)], capture_output=True, text=True)
+    assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
+    assert open(a, "rb").read() == open(b, "rb").read() and r1.stdout == r2.stdout
+    rows = list(csv.reader(open(b, newline="")))
+    assert rows[0][:2] == ["Id", "FileName"] and rows[0][2:5] == ["v1", "v2", "HEAD"]
+    by = {x[1]: x for x in rows[1:]}
+    assert by["tests/test_gone.py"][2:5] == ["tests/test_gone.py", "", ""]              # deleted after v1
+    assert by["tests/new_test.cc"][2:5] == ["", "tests/new_test.cc", "tests/new_test.cc"] and by["tests/new_test.cc"][5] == "3"
+    # no revisions named: every tag, oldest first
+    r3 = subprocess.run([CLI, "releases", "--git", str(repo), "--out", str(tmp_path / "tags.csv")], capture_output=True, text=True)
+    assert r3.returncode == 0, r3.stderr
+    assert next(csv.reader(open(tmp_path / "tags.csv", newline="")))[2:4] == ["v1", "v2"]

@@ -384,8 +384,11 @@ __device__ __noinline__ bool ident_eq(FileBytes& rd, uint32_t s, uint32_t n, con
 
 constexpr uint32_t BQ_CAP = 1024;                        // bare-assert expressions a block of k_classify defers (16 B each)
 
+#ifndef TSM_CLS_MINB
+#define TSM_CLS_MINB 1
+#endif
 template <bool REVB>
-__global__ void __launch_bounds__(256) k_classify_t(ScanParams p) {
+__global__ void __launch_bounds__(256, TSM_CLS_MINB) k_classify_t(ScanParams p) {
   extern __shared__ __align__(16) uint32_t csm[];        // byte classes, operator table, category tables, deferral queue, [n_groups][K] histogram
   uint32_t* cls = csm;
   uint32_t* elut = csm + 256;
