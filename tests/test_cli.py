@@ -191,8 +191,9 @@ def test_reduce_reproduces_the_shipped_tables(tmp_path):
     tax = tmp_path / "taxonomy.csv"
     tax.write_bytes(gzip.open(os.path.join(gold, "taxonomy_min.csv.gz"), "rb").read())
     sp, mp, pp, cp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv"), str(tmp_path / "c.csv")
-    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp, "--correlate", cp],
-                         capture_output=True, text=True)
+    ctex, ccnt = str(tmp_path / "ctex.csv"), str(tmp_path / "ccnt.csv")
+    out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp, "--correlate", cp,
+                          "--correlate-tex", ctex, "--correlate-counts", ccnt], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     d = np.load(os.path.join(gold, "g3_reduce.npz"))
     repos = [str(x) for x in d["repo_names"]]
@@ -243,6 +244,23 @@ def test_reduce_reproduces_the_shipped_tables(tmp_path):
                 assert ct[1 + j][1 + q] == str(cwant[j][q])
                 n_ok += 1
     assert n_ok == 394
+    # the same counts in the LaTeX layout (tests_correlate_rq4.csv) and as totals over the repositories (tests_combined_correlate_rq3.csv)
+    tt, tn = read_csv(ctex), read_csv(ccnt)
+    assert tt[0] == ct[0] and tn[0] == ct[0]
+    tok, twant, nok, nwant = d["correlate_tex_cell_reproduces"], d["want_correlate_tex_cells"], d["correlate_count_cell_reproduces"], d["want_correlate_count_cells"]
+    n_tex = n_cnt = 0
+    for j in range(cok.shape[0]):
+        for q in range(cok.shape[1]):
+            dd = [int(cdist[j * cok.shape[1] + q, repos.index(n)]) for n in order]
+            assert tn[1 + j][1 + q] == str(sum(dd))
+            assert (tt[1 + j][1 + q] == "0") == (sum(dd) == 0)
+            if tok[j, q]:
+                assert tt[1 + j][1 + q] == str(twant[j][q]), (j, q)
+                n_tex += 1
+            if nok[j, q]:
+                assert tn[1 + j][1 + q] == str(nwant[j][q]), (j, q)
+                n_cnt += 1
+    assert (n_tex, n_cnt) == (394, 382)
 
 
 @pytest.mark.gpu

@@ -136,6 +136,24 @@ def test_resident_rescans_are_identical_and_launch_count(scanner):
     assert len(ms) == 4 and all(m >= 0 for m in ms)
 
 
+def test_host_path_with_pinned_index_and_reused_result_buffers(scanner):
+    """The path bench.py's e2e times: a pinned corpus pins its index arrays too, scan(reuse=True) returns views of
+    pinned buffers the Scanner keeps - same numbers as the plain call, the buffers are overwritten by the next call."""
+    a = ts.gen_corpus(11, 1200, 1, n_groups=5)                # pinned arena (a GPU is present)
+    b = ts.gen_corpus(12, 1200, 1, n_groups=5)
+    assert a._keep is not None and len(a._index_pins) == 4 and a.off.dtype == np.int32 and a.grp.dtype == np.uint16
+    plain_a, plain_b = scanner.scan(a, 0), scanner.scan(b, 0)
+    ra = scanner.scan(a, 0, reuse=True)
+    keep = {k: ra[k].copy() for k in ("stats", "group_counts", "global_counts")}
+    rb = scanner.scan(b, 0, reuse=True)
+    assert rb["stats"] is ra["stats"]                         # the same buffer, now holding b's records
+    for k in keep:
+        assert np.array_equal(keep[k], plain_a[k]) and np.array_equal(rb[k], plain_b[k])
+    assert np.array_equal(ra["totals"], plain_a["totals"]) and np.array_equal(rb["totals"], plain_b["totals"])
+    want = orc.scan(a.arena, a.off, a.len, a.ext, a.grp, 5, events=False)
+    assert np.array_equal(keep["stats"], want["stats"])
+
+
 def test_shards_add_up_to_the_whole(scanner):
     """Size-independent property used at full scale: counts of round-robin shards sum to the whole."""
     n, w = 4000, 4

@@ -178,6 +178,11 @@ def test_g3_correlate_table_from_the_taxonomy_fixture():
             dd = [int(out[j * nc + q, rid[n]]) for n in order]
             cell = "0" if not any(dd) else "".join("%s:(%s%%), " % (n, repr(round(100.0 * v / int(cpr[rid[n]]), 2))) for n, v in zip(order, dd))
             assert (cell == str(want[j][q])) == bool(ok[j, q]), (j, q)
+            # the two other shipped layouts of the same counts (tests_correlate_rq4.csv, tests_combined_correlate_rq3.csv)
+            tex = "".join("$%s:%s\\%%$, " % (n, repr(round(100.0 * v / int(cpr[rid[n]]), 2))) for n, v in zip(order, dd) if v) or "0"
+            assert (tex == str(d["want_correlate_tex_cells"][j][q])) == bool(d["correlate_tex_cell_reproduces"][j, q]), (j, q)
+            assert (str(sum(dd)) == str(d["want_correlate_count_cells"][j][q])) == bool(d["correlate_count_cell_reproduces"][j, q]), (j, q)
+    assert int(d["correlate_tex_cell_reproduces"].sum()) == 394 and int(d["correlate_count_cell_reproduces"].sum()) == 382
 
 
 def test_g3_reduce_golden():

@@ -400,6 +400,19 @@ def golden_g3(ledger):
         for q in range(len(CORRELATE_COLS)):
             d = cout[j * len(CORRELATE_COLS) + q]
             corr_ok[j, q] = correlate_cell([d[k] for k in order], [cpr[k] for k in order], CORRELATE_REPOS) == want_corr[j][q]
+    # the same counts in the two other shipped layouts: LaTeX cells that list the non-zero repositories only
+    # (tests_correlate_rq4.csv), and the distinct cases of all repositories together (tests_combined_correlate_rq3.csv)
+    ttex = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_correlate_rq4.csv"), newline="")))
+    tcnt = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_combined_correlate_rq3.csv"), newline="", encoding="utf-8-sig")))
+    assert ttex[0] == tc[0] and tcnt[0] == tc[0] and [r[0] for r in ttex[1:]] == [r[0] for r in tc[1:]] == [r[0] for r in tcnt[1:]]
+    tex_ok = np.zeros_like(corr_ok)
+    cnt_ok = np.zeros_like(corr_ok)
+    for j in range(len(CORRELATE_ROWS)):
+        for q in range(len(CORRELATE_COLS)):
+            d = cout[j * len(CORRELATE_COLS) + q]
+            tex = "".join("$%s:%s\\%%$, " % (n, repr(round(100.0 * int(d[k]) / int(cpr[k]), 2))) for n, k in zip(CORRELATE_REPOS, order) if d[k]) or "0"
+            tex_ok[j, q] = tex == ttex[1 + j][1 + q]
+            cnt_ok[j, q] = str(int(d.sum())) == tcnt[1 + j][1 + q]
     np.savez_compressed(os.path.join(OUT, "g3_reduce.npz"), flags=flags, repo=repo, case_id=case,
                         want_property_cells=np.array(want_prop), property_cell_reproduces=prop_ok,
                         flag_names=np.array(names), repo_names=np.array(repos),
@@ -413,7 +426,9 @@ def golden_g3(ledger):
                         correlate_row_column=np.array([r[1] for r in CORRELATE_ROWS]),
                         correlate_row_value=np.array([r[2] for r in CORRELATE_ROWS]),
                         correlate_col_labels=np.array(["|".join(labels_of[q]) for _, q in CORRELATE_COLS]),
-                        correlate_repo_order=np.array(CORRELATE_REPOS), oracle_correlate_distinct=cout)
+                        correlate_repo_order=np.array(CORRELATE_REPOS), oracle_correlate_distinct=cout,
+                        want_correlate_tex_cells=np.array([r[1:] for r in ttex[1:]]), correlate_tex_cell_reproduces=tex_ok,
+                        want_correlate_count_cells=np.array([r[1:] for r in tcnt[1:]]), correlate_count_cell_reproduces=cnt_ok)
     ledger["G3"] = {"source": "RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/tests_methods_v2.csv",
                     "rows": len(rows), "cases": len(cases), "cases_per_repo": dict(zip(repos, map(int, cpr))),
                     "strategy_cells_bit_identical": [int(cell_ok.sum()), int(cell_ok.size)],
@@ -422,6 +437,8 @@ def golden_g3(ledger):
                     "property_columns_fully_identical": [int((prop_ok.sum(axis=1) == len(repos)).sum()), len(PROPERTIES)],
                     "correlate_cells_bit_identical": [int(corr_ok.sum()), int(corr_ok.size)],
                     "correlate_rows_fully_identical": [int((corr_ok.sum(axis=1) == len(CORRELATE_COLS)).sum()), len(CORRELATE_ROWS)],
+                    "correlate_tex_cells_bit_identical (tests_correlate_rq4.csv)": [int(tex_ok.sum()), int(tex_ok.size)],
+                    "correlate_count_cells_identical (tests_combined_correlate_rq3.csv)": [int(cnt_ok.sum()), int(cnt_ok.size)],
                     "rq4_mismatches": {m[0]: [int(out[len(STRATEGY) + j].sum()), want4[m[0]]]
                                        for j, m in enumerate(METHODS) if not m_ok[j]}}
     print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok), "property cells", int(prop_ok.sum()), prop_ok.size,

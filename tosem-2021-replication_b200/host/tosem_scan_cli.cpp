@@ -16,7 +16,7 @@
 // itself goes through libtosemscan.so (sm_100a kernels); there is no CPU fallback.
 //
 //   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]
-//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F]
+//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F] [--correlate-tex F] [--correlate-counts F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
 //   tosem-scan releases <snapshot-root>=<tag>... [--out F]   |   releases --git <repository> [<revision>...] [--out F]
@@ -557,7 +557,8 @@ static std::string fmt_pyfloat2(double v) {                 // repr(round(v, 2))
 static double round_to(double v, int dec) { const double p = std::pow(10.0, dec); return std::round(v * p) / p; }
 
 static int cmd_reduce(const std::string& path, const std::string& strategy_path, const std::string& methods_path,
-                      const std::string& properties_path, const std::string& correlate_path) {
+                      const std::string& properties_path, const std::string& correlate_path, const std::string& correlate_tex_path,
+                      const std::string& correlate_counts_path) {
   auto rows = csv_read(path);
   if (rows.size() < 2) die("empty taxonomy");
   std::map<std::string, int> col;
@@ -571,7 +572,7 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
   const int nS = sizeof(kStrategy) / sizeof(kStrategy[0]), nM = sizeof(kMethods) / sizeof(kMethods[0]);
   const int nP = sizeof(kProperties) / sizeof(kProperties[0]);
   const int nCR = sizeof(kCorrRows) / sizeof(kCorrRows[0]), nCC = sizeof(kCorrCols) / sizeof(kCorrCols[0]);
-  const bool corr = !correlate_path.empty();
+  const bool corr = !correlate_path.empty() || !correlate_tex_path.empty() || !correlate_counts_path.empty();
   const int nF = nS + nM + nP + (corr ? nCR * nCC : 0);      // the correlate table is 420 more flag columns of the same reduction
   int corr_prop[sizeof(kCorrCols) / sizeof(kCorrCols[0])];
   for (int q = 0; q < nCC; ++q) {
@@ -667,33 +668,43 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
       csv_row(os, row);
     }
   }
-  if (corr) {                                               // layout of RQs/RQ3/tests_correlate_rq3.csv
+  if (corr) {
+    // three shipped layouts of the same 20 x 21 counts: RQs/RQ3/tests_correlate_rq3.csv ("repo:(p%), " for every repository),
+    // tests_correlate_rq4.csv (LaTeX cells "$repo:p\%$, " of the non-zero repositories) and
+    // tests_combined_correlate_rq3.csv (the distinct cases of all repositories together)
     for (const CorrRow& cr : kCorrRows) if (!col.count(cr.col)) die(std::string("taxonomy lacks column ") + cr.col);
-    std::ofstream os(correlate_path, std::ios::binary);
-    std::vector<std::string> h = {"Tests"};
-    for (int q = 0; q < nCC; ++q) h.push_back(kCorrCols[q].name);
-    csv_row(os, h);
     std::vector<std::string> order = {"auto_sklearn", "google_automl", "tpot", "autokeras", "Nupic", "Apollo", "nni", "Ray", "DeepSpeech2"};
     for (auto& r : repos) if (!std::count(order.begin(), order.end(), r)) order.push_back(r);
     const size_t c0 = (size_t)(nS + nM + nP);
-    for (int j = 0; j < nCR; ++j) {
-      std::vector<std::string> row = {kCorrRows[j].name};
-      for (int q = 0; q < nCC; ++q) {
-        const int64_t* d = &out[(c0 + (size_t)j * nCC + q) * n_repos];
-        bool any = false;
-        for (int r = 0; r < n_repos; ++r) any = any || d[r] != 0;
-        std::string cellv = "0";                            // a pairing no case has is the bare string "0" in the shipped table
-        if (any) {
-          cellv.clear();
-          for (auto& name : order) {
-            if (!rid.count(name) || cpr[(size_t)rid[name]] == 0) continue;
-            const int r = rid[name];
-            cellv += name + ":(" + fmt_pyfloat2(100.0 * (double)d[r] / (double)cpr[r]) + "%), ";
+    for (int layout = 0; layout < 3; ++layout) {
+      const std::string& outp = layout == 0 ? correlate_path : layout == 1 ? correlate_tex_path : correlate_counts_path;
+      if (outp.empty()) continue;
+      std::ofstream os(outp, std::ios::binary);
+      std::vector<std::string> h = {"Tests"};
+      for (int q = 0; q < nCC; ++q) h.push_back(kCorrCols[q].name);
+      csv_row(os, h);
+      for (int j = 0; j < nCR; ++j) {
+        std::vector<std::string> row = {kCorrRows[j].name};
+        for (int q = 0; q < nCC; ++q) {
+          const int64_t* d = &out[(c0 + (size_t)j * nCC + q) * n_repos];
+          int64_t all = 0;
+          for (int r = 0; r < n_repos; ++r) all += d[r];
+          std::string cellv = "0";                          // a pairing no case has is the bare string "0" in every layout
+          if (layout == 2) cellv = std::to_string(all);
+          else if (all) {
+            cellv.clear();
+            for (auto& name : order) {
+              if (!rid.count(name) || cpr[(size_t)rid[name]] == 0) continue;
+              const int r = rid[name];
+              const std::string pct = fmt_pyfloat2(100.0 * (double)d[r] / (double)cpr[r]);
+              if (layout == 0) cellv += name + ":(" + pct + "%), ";
+              else if (d[r]) cellv += "$" + name + ":" + pct + "\\%$, ";
+            }
           }
+          row.push_back(cellv);
         }
-        row.push_back(cellv);
+        csv_row(os, row);
       }
-      csv_row(os, row);
     }
   }
   fprintf(stderr, "tosem-scan: reduce %d rows, %d cases, %d repos\n", n_rows, n_cases, n_repos);
@@ -1194,7 +1205,7 @@ static int cmd_history(const std::string& repo, const std::string& rev, int64_t 
 static void usage() {
   fprintf(stderr,
           "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N] [--rev-b]\n"
-          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F]\n"
+          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F] [--correlate-tex F] [--correlate-counts F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
           "       tosem-scan releases <snapshot-root>=<tag>... [--out F]   |   releases --git <repository> [<revision>...] [--out F]\n"
@@ -1218,7 +1229,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
                                         opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30), rev_b); }
-  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"], opt["--correlate"]); }
+  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"], opt["--correlate"], opt["--correlate-tex"], opt["--correlate-counts"]); }
   if (cmd == "releases") { if (pos.empty() && !opt.count("--git")) die("releases needs <root>=<tag>... or --git <repository>"); return cmd_releases(pos, opt["--out"], opt["--git"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
   if (cmd == "history") { if (pos.size() != 1) die("history needs the repository"); return cmd_history(pos[0], opt.count("--rev") ? opt["--rev"] : "HEAD",

@@ -180,6 +180,22 @@ class Corpus:
         self.grp = np.zeros(len(self.len), np.uint16) if grp is None else np.ascontiguousarray(grp, np.uint16)
         self.n_groups = int(n_groups)
         self._keep = keep
+        if keep is not None:                                 # pinned arena: pin the index too (tsm_scan copies it every call;
+            self._pin_index()                               # from pageable memory those copies are staged and block the host)
+
+    def _pin_index(self):
+        pins = []
+        for name in ("off", "len", "ext", "grp"):
+            a = getattr(self, name)
+            try:
+                pin = _Pinned(max(a.nbytes, ALIGN))
+            except MemoryError:
+                return
+            b = pin.array[:a.nbytes].view(a.dtype)
+            b[:] = a
+            setattr(self, name, b)
+            pins.append(pin)
+        self._index_pins = pins
 
     @property
     def n_files(self):
@@ -342,9 +358,19 @@ class Scanner:
         except Exception:
             pass
 
-    def _result(self, n_files, n_groups, flags, event_cap):
-        res = {"stats": np.zeros(n_files, FILE_STAT), "group_counts": np.zeros((n_groups, K), np.int64),
-               "global_counts": np.zeros(K, np.int64)}
+    def _result(self, n_files, n_groups, flags, event_cap, reuse=False):
+        if reuse:                                            # pinned buffers kept by the Scanner: D2H at the link rate, no
+            key = (n_files, n_groups)                        # allocation per call; the arrays are valid until the next such call
+            if getattr(self, "_res_key", None) != key:
+                bufs = [host_buffer(max(n_files, 1) * FILE_STAT.itemsize), host_buffer(n_groups * K * 8), host_buffer(K * 8)]
+                self._res_pins = [b[1] for b in bufs]
+                self._res_bufs = (bufs[0][0][:n_files * FILE_STAT.itemsize].view(FILE_STAT),
+                                  bufs[1][0][:n_groups * K * 8].view(np.int64).reshape(n_groups, K), bufs[2][0][:K * 8].view(np.int64))
+                self._res_key = key
+            res = {"stats": self._res_bufs[0], "group_counts": self._res_bufs[1], "global_counts": self._res_bufs[2]}
+        else:
+            res = {"stats": np.zeros(n_files, FILE_STAT), "group_counts": np.zeros((n_groups, K), np.int64),
+                   "global_counts": np.zeros(K, np.int64)}
         r = _Result(_p(res["stats"]), _p(res["group_counts"]), _p(res["global_counts"]), None, 0, 0, None, 0, 0)
         if flags & SCAN_ASSERT_EVENTS:
             res["assert_events"] = np.zeros(max(event_cap, 1), ASSERT_EVENT)
@@ -363,10 +389,12 @@ class Scanner:
             res["header_events"] = res["header_events"][:r.n_hev]
         return res
 
-    def scan(self, corpus, flags=0, stream=None, event_cap=None):
-        """End-to-end host path: H2D + kernels + D2H (tsm_scan)."""
-        cap = int(event_cap if event_cap is not None else max(corpus.source_bytes // 8 + 16, 1024))
-        res, r = self._result(corpus.n_files, corpus.n_groups, flags, cap)
+    def scan(self, corpus, flags=0, stream=None, event_cap=None, reuse=False):
+        """End-to-end host path: H2D + kernels + D2H (tsm_scan).  reuse=True: the per-file records and count tables land in
+        pinned buffers the Scanner keeps (valid until the next scan with reuse=True)."""
+        want_ev = flags & (SCAN_ASSERT_EVENTS | SCAN_HEADER_EVENTS)
+        cap = int(event_cap if event_cap is not None else (max(corpus.source_bytes // 8 + 16, 1024) if want_ev else 0))
+        res, r = self._result(corpus.n_files, corpus.n_groups, flags, cap, reuse)
         cs = corpus.c_struct()
         rc = lib().tsm_scan(self._ctx, C.byref(cs), C.byref(r), flags, stream)
         if rc:
