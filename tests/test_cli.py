@@ -191,9 +191,9 @@ def test_reduce_reproduces_the_shipped_tables(tmp_path):
     tax = tmp_path / "taxonomy.csv"
     tax.write_bytes(gzip.open(os.path.join(gold, "taxonomy_min.csv.gz"), "rb").read())
     sp, mp, pp, cp = str(tmp_path / "s.csv"), str(tmp_path / "m.csv"), str(tmp_path / "p.csv"), str(tmp_path / "c.csv")
-    ctex, ccnt = str(tmp_path / "ctex.csv"), str(tmp_path / "ccnt.csv")
+    ctex, ccnt, cmer = str(tmp_path / "ctex.csv"), str(tmp_path / "ccnt.csv"), str(tmp_path / "cmer.csv")
     out = subprocess.run([CLI, "reduce", str(tax), "--strategy", sp, "--methods", mp, "--properties", pp, "--correlate", cp,
-                          "--correlate-tex", ctex, "--correlate-counts", ccnt], capture_output=True, text=True)
+                          "--correlate-tex", ctex, "--correlate-counts", ccnt, "--correlate-merged", cmer], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     d = np.load(os.path.join(gold, "g3_reduce.npz"))
     repos = [str(x) for x in d["repo_names"]]
@@ -261,6 +261,17 @@ def test_reduce_reproduces_the_shipped_tables(tmp_path):
                 assert tn[1 + j][1 + q] == str(nwant[j][q]), (j, q)
                 n_cnt += 1
     assert (n_tex, n_cnt) == (394, 382)
+    # the four one-row tables of the merged strategy rows (tests_correlate_{FileError,RuntimeError,assertion,logical}.csv)
+    tm = read_csv(cmer)
+    assert tm[0] == ct[0] and [x[0] for x in tm[1:]] == [str(x) for x in d["merged_row_names"]]
+    mok, mwant, mdist = d["merged_cell_reproduces"], d["want_merged_cells"], d["oracle_merged_distinct"]
+    for j in range(mok.shape[0]):
+        for q in range(mok.shape[1]):
+            dd = [int(mdist[j * mok.shape[1] + q, repos.index(n)]) for n in order]
+            mine = "0" if not any(dd) else "".join("%s:(%s%%), " % (n, repr(round(100.0 * v / cpr[n], 2))) for n, v in zip(order, dd))
+            assert tm[1 + j][1 + q] == mine, (j, q)
+            assert (mine == str(mwant[j][q])) == bool(mok[j, q])
+    assert [int(x) for x in mok.sum(axis=1)] == [21, 16, 21, 20]
 
 
 @pytest.mark.gpu

@@ -185,6 +185,35 @@ def test_g3_correlate_table_from_the_taxonomy_fixture():
     assert int(d["correlate_tex_cell_reproduces"].sum()) == 394 and int(d["correlate_count_cell_reproduces"].sum()) == 382
 
 
+def test_g3_merged_row_tables():
+    """tests_correlate_{FileError,RuntimeError,assertion,logical}.csv: the correlate layout for the merged strategy rows,
+    rebuilt from the committed flag matrix (strategy flag AND property flag), 78 of 84 cells bit-identical."""
+    d = np.load(os.path.join(GOLD, "g3_reduce.npz"))
+    names = [str(x) for x in d["flag_names"]]
+    repos = [str(x) for x in d["repo_names"]]
+    order = [str(x) for x in d["correlate_repo_order"]]
+    props = ["p:" + {"Distribution": "Data Distribution", "Validity": "Data Validity", "Relation": "Data Relation",
+                     "Feature Importance": "Features Importance", "Restoration": "Data Restoration and Recoverability",
+                     "Concurrency": "Concurrency and Parallelism", "uncertainty": "Uncertainty", "Data Loss": "Data Migration Loss and Corruption",
+                     "Bias": "Bias and Fairness", "Security": "Security and Privacy", "Uniqueness": "Data Uniqueness",
+                     "Timeliness": "Data Timeliness", "integration": "Data Integration Integrity",
+                     "Compatibility": "Compatibility and Portability"}.get(str(c), str(c)) for c in d["correlate_col_names"]]
+    F = d["flags"]
+    cols = []
+    for srow in d["merged_strategy_rows"]:
+        for pname in props:
+            cols.append(F[:, names.index(str(srow))] & F[:, names.index(pname)])
+    out, cpr = orc.reduce(np.stack(cols, axis=1).astype(np.uint8), d["repo"], d["case_id"], len(repos), int(d["case_id"].max()) + 1)
+    assert np.array_equal(out, d["oracle_merged_distinct"])
+    ok, want = d["merged_cell_reproduces"], d["want_merged_cells"]
+    for j in range(ok.shape[0]):
+        for q in range(ok.shape[1]):
+            dd = [int(out[j * ok.shape[1] + q, repos.index(n)]) for n in order]
+            cell = "0" if not any(dd) else "".join("%s:(%s%%), " % (n, repr(round(100.0 * v / int(cpr[repos.index(n)]), 2))) for n, v in zip(order, dd))
+            assert (cell == str(want[j][q])) == bool(ok[j, q]), (j, q)
+    assert [int(x) for x in ok.sum(axis=1)] == [21, 16, 21, 20]
+
+
 def test_g3_reduce_golden():
     """Golden G3: RQs/taxonomy_test2.csv -> tests_strategy_rq32.csv / tests_methods_v2.csv."""
     d = np.load(os.path.join(GOLD, "g3_reduce.npz"))

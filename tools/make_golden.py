@@ -413,6 +413,27 @@ def golden_g3(ledger):
             tex = "".join("$%s:%s\\%%$, " % (n, repr(round(100.0 * int(d[k]) / int(cpr[k]), 2))) for n, k in zip(CORRELATE_REPOS, order) if d[k]) or "0"
             tex_ok[j, q] = tex == ttex[1 + j][1 + q]
             cnt_ok[j, q] = str(int(d.sum())) == tcnt[1 + j][1 + q]
+    # four more one-row tables in the correlate layout, for the MERGED strategy rows of tests_strategy_rq32.csv
+    # (tests_correlate_{FileError,RuntimeError,assertion,logical}.csv): the same value sets as STRATEGY above
+    merged_rows = [("FileError", "FileError", "FileError"), ("RuntimeError", "RuntimeError", "runtime_error"),
+                   ("AssertionError", "assertion", "AssertionError"), ("logical", "logical", "logical_condition")]   # (row name, file suffix, STRATEGY row)
+    sidx = {name: j for j, (name, _, _) in enumerate(STRATEGY)}
+    mflags = np.zeros((len(rows), len(merged_rows) * len(CORRELATE_COLS)), np.uint8)
+    for i, r in enumerate(rows):
+        pr = [(r["Data"].strip() in labels_of[q]) or (r["Model"].strip() in labels_of[q]) for _, q in CORRELATE_COLS]
+        for j, (_, _, srow) in enumerate(merged_rows):
+            if flags[i, sidx[srow]]:
+                mflags[i, j * len(CORRELATE_COLS):(j + 1) * len(CORRELATE_COLS)] = pr
+    mout, _ = orc.reduce(mflags, repo, case, len(repos), len(cases))
+    merged_ok = np.zeros((len(merged_rows), len(CORRELATE_COLS)), np.uint8)
+    want_merged = []
+    for j, (rname, suffix, _) in enumerate(merged_rows):
+        tm = list(csv.reader(open(os.path.join(REF, "RQs/RQ3/tests_correlate_%s.csv" % suffix), newline="")))
+        assert tm[0] == tc[0] and len(tm) == 2 and tm[1][0] == rname, (suffix, tm[1][0])
+        want_merged.append(tm[1][1:])
+        for q in range(len(CORRELATE_COLS)):
+            d = mout[j * len(CORRELATE_COLS) + q]
+            merged_ok[j, q] = correlate_cell([d[k] for k in order], [cpr[k] for k in order], CORRELATE_REPOS) == tm[1][1 + q]
     np.savez_compressed(os.path.join(OUT, "g3_reduce.npz"), flags=flags, repo=repo, case_id=case,
                         want_property_cells=np.array(want_prop), property_cell_reproduces=prop_ok,
                         flag_names=np.array(names), repo_names=np.array(repos),
@@ -428,7 +449,9 @@ def golden_g3(ledger):
                         correlate_col_labels=np.array(["|".join(labels_of[q]) for _, q in CORRELATE_COLS]),
                         correlate_repo_order=np.array(CORRELATE_REPOS), oracle_correlate_distinct=cout,
                         want_correlate_tex_cells=np.array([r[1:] for r in ttex[1:]]), correlate_tex_cell_reproduces=tex_ok,
-                        want_correlate_count_cells=np.array([r[1:] for r in tcnt[1:]]), correlate_count_cell_reproduces=cnt_ok)
+                        want_correlate_count_cells=np.array([r[1:] for r in tcnt[1:]]), correlate_count_cell_reproduces=cnt_ok,
+                        merged_row_names=np.array([m[0] for m in merged_rows]), merged_strategy_rows=np.array([m[2] for m in merged_rows]),
+                        want_merged_cells=np.array(want_merged), merged_cell_reproduces=merged_ok, oracle_merged_distinct=mout)
     ledger["G3"] = {"source": "RQs/taxonomy_test2.csv -> RQs/RQ3/tests_strategy_rq32.csv, RQs/RQ4/tests_methods_v2.csv",
                     "rows": len(rows), "cases": len(cases), "cases_per_repo": dict(zip(repos, map(int, cpr))),
                     "strategy_cells_bit_identical": [int(cell_ok.sum()), int(cell_ok.size)],
@@ -439,6 +462,8 @@ def golden_g3(ledger):
                     "correlate_rows_fully_identical": [int((corr_ok.sum(axis=1) == len(CORRELATE_COLS)).sum()), len(CORRELATE_ROWS)],
                     "correlate_tex_cells_bit_identical (tests_correlate_rq4.csv)": [int(tex_ok.sum()), int(tex_ok.size)],
                     "correlate_count_cells_identical (tests_combined_correlate_rq3.csv)": [int(cnt_ok.sum()), int(cnt_ok.size)],
+                    "merged_row_cells_bit_identical (tests_correlate_{FileError,RuntimeError,assertion,logical}.csv)":
+                        {m[0]: [int(merged_ok[j].sum()), len(CORRELATE_COLS)] for j, m in enumerate(merged_rows)},
                     "rq4_mismatches": {m[0]: [int(out[len(STRATEGY) + j].sum()), want4[m[0]]]
                                        for j, m in enumerate(METHODS) if not m_ok[j]}}
     print("G3 cells", int(cell_ok.sum()), cell_ok.size, "rq4", sum(m_ok), len(m_ok), "property cells", int(prop_ok.sum()), prop_ok.size,

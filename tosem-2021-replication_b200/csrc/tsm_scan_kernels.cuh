@@ -71,7 +71,7 @@ __device__ __forceinline__ void line_init(LineState& L, uint32_t s, uint32_t e) 
   L.pos = (s == e) ? e : (s & ~7u);
 }
 
-// One 8-byte block of a lane-per-line walk (long-line slow path, k_hash_lines).  Files without a scannable
+// One 8-byte block of a lane-per-line walk (long-line slow path).  Files without a scannable
 // extension run the same code: their pattern ends are simply never looked at.
 __device__ __forceinline__ void line_block(LineState& L, unsigned long long w, const uint32_t* lut, uint32_t first) {
   const uint32_t pos = L.pos;
@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t line_finish_h(uint32_t s, uint32_t e, unsign
   return fl;
 }
 
-// Same, from the raw (A, B) of a lane-per-line walk (the long-line slow path and k_hash_lines).
+// Same, from the raw (A, B) of a lane-per-line walk (the long-line slow path).
 template <typename LoadByte>
 __device__ __forceinline__ uint32_t line_finish(uint32_t s, uint32_t e, uint32_t A, unsigned long long B, int ext,
                                                 LoadByte lb, Accum& ac) {

@@ -2,7 +2,7 @@
 // Pins: Important-files/ML-Analysis-v4.xlsx!Apollo:R2-R26 = src/apollo/v6.0.0/modules/common/math/
 // aabox2d_test.cc:27-53 (multi-line statements joined while the parentheses are open).
 //
-//   k_count_lines / k_mark_lines   (tsm_diff_kernels.cuh) ordered line ends per file
+//   k_scan (TSM_SCAN_LINE_HASHES) + tsm_lines_kernels.cuh   line records (ordered line ends) per file
 //   k_line_parens   thread per line: SWAR count of '(' minus ')' and blank test            -> delta[], nonblank
 //   k_stmt_kinds    warp per file: clamped running depth d' = max(0, d + delta) as a warp scan
 //                   over the monoid f(d) = max(a, d + b); kind 1 = first line of a statement,

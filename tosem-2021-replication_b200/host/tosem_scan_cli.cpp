@@ -16,7 +16,7 @@
 // itself goes through libtosemscan.so (sm_100a kernels); there is no CPU fallback.
 //
 //   tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N]
-//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F] [--correlate-tex F] [--correlate-counts F]
+//   tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F] [--correlate-tex F] [--correlate-counts F] [--correlate-merged F]
 //   tosem-scan diff   <old-root> <new-root> [--out F]
 //   tosem-scan body   <project-root>... [--out F]
 //   tosem-scan releases <snapshot-root>=<tag>... [--out F]   |   releases --git <repository> [<revision>...] [--out F]
@@ -525,6 +525,12 @@ static const CorrCol kCorrCols[] = {
     {"Security", "Security and Privacy"}, {"Uniqueness", "Data Uniqueness"}, {"Timeliness", "Data Timeliness"},
     {"integration", "Data Integration Integrity"}, {"Compatibility", "Compatibility and Portability"}};
 
+// Four more one-row tables in the same layout for the MERGED rows of the strategy table
+// (RQs/RQ3/tests_correlate_{FileError,RuntimeError,assertion,logical}.csv): row name -> row of kStrategy.
+struct MergedRow { const char* name; const char* strategy; };
+static const MergedRow kMergedRows[] = {{"FileError", "FileError"}, {"RuntimeError", "runtime_error"},
+                                        {"AssertionError", "AssertionError"}, {"logical", "logical_condition"}};
+
 static bool one_of(const std::string& have, const std::string& want) {   // `want` = '|'-separated values
   for (size_t a = 0; a <= want.size();) {
     const size_t b = std::min(want.find('|', a), want.size());
@@ -558,7 +564,7 @@ static double round_to(double v, int dec) { const double p = std::pow(10.0, dec)
 
 static int cmd_reduce(const std::string& path, const std::string& strategy_path, const std::string& methods_path,
                       const std::string& properties_path, const std::string& correlate_path, const std::string& correlate_tex_path,
-                      const std::string& correlate_counts_path) {
+                      const std::string& correlate_counts_path, const std::string& correlate_merged_path) {
   auto rows = csv_read(path);
   if (rows.size() < 2) die("empty taxonomy");
   std::map<std::string, int> col;
@@ -573,7 +579,15 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
   const int nP = sizeof(kProperties) / sizeof(kProperties[0]);
   const int nCR = sizeof(kCorrRows) / sizeof(kCorrRows[0]), nCC = sizeof(kCorrCols) / sizeof(kCorrCols[0]);
   const bool corr = !correlate_path.empty() || !correlate_tex_path.empty() || !correlate_counts_path.empty();
-  const int nF = nS + nM + nP + (corr ? nCR * nCC : 0);      // the correlate table is 420 more flag columns of the same reduction
+  const bool merged = !correlate_merged_path.empty();
+  const int nMR = sizeof(kMergedRows) / sizeof(kMergedRows[0]);
+  const int nF = nS + nM + nP + (corr ? nCR * nCC : 0) + (merged ? nMR * nCC : 0);   // the correlate tables are more flag columns of the same reduction
+  int merged_row[sizeof(kMergedRows) / sizeof(kMergedRows[0])];
+  for (int j = 0; j < nMR; ++j) {
+    merged_row[j] = -1;
+    for (int k = 0; k < nS; ++k) if (!strcmp(kMergedRows[j].strategy, kStrategy[k].name)) merged_row[j] = k;
+    if (merged_row[j] < 0) die(std::string("no strategy row named ") + kMergedRows[j].strategy);
+  }
   int corr_prop[sizeof(kCorrCols) / sizeof(kCorrCols[0])];
   for (int q = 0; q < nCC; ++q) {
     corr_prop[q] = -1;
@@ -589,6 +603,7 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
     const std::string cs = R[col["Cases"]];
     if (!cid.count(cs)) { const int k = (int)cid.size(); cid[cs] = k; }
     repo.push_back(rid[R[col["Repo"]]]); cas.push_back(cid[cs]);
+    const size_t s0 = flags.size();
     for (int j = 0; j < nS; ++j) {
       bool v = one_of(cell(R, kStrategy[j].col), kStrategy[j].val);
       if (kStrategy[j].col2) v = v || cell(R, kStrategy[j].col2) == "1";
@@ -602,6 +617,11 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
     if (corr)
       for (int j = 0; j < nCR; ++j) {
         const bool s_on = cell(R, kCorrRows[j].col) == kCorrRows[j].val;
+        for (int q = 0; q < nCC; ++q) flags.push_back(s_on && flags[p0 + (size_t)corr_prop[q]]);
+      }
+    if (merged)
+      for (int j = 0; j < nMR; ++j) {
+        const bool s_on = flags[s0 + (size_t)merged_row[j]] != 0;
         for (int q = 0; q < nCC; ++q) flags.push_back(s_on && flags[p0 + (size_t)corr_prop[q]]);
       }
   }
@@ -705,6 +725,34 @@ static int cmd_reduce(const std::string& path, const std::string& strategy_path,
         }
         csv_row(os, row);
       }
+    }
+  }
+  if (merged) {                                             // the four one-row tables, as four rows of one file
+    std::ofstream os(correlate_merged_path, std::ios::binary);
+    std::vector<std::string> h = {"Tests"};
+    for (int q = 0; q < nCC; ++q) h.push_back(kCorrCols[q].name);
+    csv_row(os, h);
+    std::vector<std::string> order = {"auto_sklearn", "google_automl", "tpot", "autokeras", "Nupic", "Apollo", "nni", "Ray", "DeepSpeech2"};
+    for (auto& r : repos) if (!std::count(order.begin(), order.end(), r)) order.push_back(r);
+    const size_t c0 = (size_t)(nS + nM + nP + (corr ? nCR * nCC : 0));
+    for (int j = 0; j < nMR; ++j) {
+      std::vector<std::string> row = {kMergedRows[j].name};
+      for (int q = 0; q < nCC; ++q) {
+        const int64_t* d = &out[(c0 + (size_t)j * nCC + q) * n_repos];
+        int64_t all = 0;
+        for (int r = 0; r < n_repos; ++r) all += d[r];
+        std::string cellv = "0";
+        if (all) {
+          cellv.clear();
+          for (auto& name : order) {
+            if (!rid.count(name) || cpr[(size_t)rid[name]] == 0) continue;
+            const int r = rid[name];
+            cellv += name + ":(" + fmt_pyfloat2(100.0 * (double)d[r] / (double)cpr[r]) + "%), ";
+          }
+        }
+        row.push_back(cellv);
+      }
+      csv_row(os, row);
     }
   }
   fprintf(stderr, "tosem-scan: reduce %d rows, %d cases, %d repos\n", n_rows, n_cases, n_repos);
@@ -1205,7 +1253,7 @@ static int cmd_history(const std::string& repo, const std::string& rev, int64_t 
 static void usage() {
   fprintf(stderr,
           "usage: tosem-scan scan   <project-root>... [--rows F] [--summary F] [--gpus N] [--all-files] [--batch-bytes N] [--rev-b]\n"
-          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F] [--correlate-tex F] [--correlate-counts F]\n"
+          "       tosem-scan reduce <taxonomy.csv> [--strategy F] [--methods F] [--properties F] [--correlate F] [--correlate-tex F] [--correlate-counts F] [--correlate-merged F]\n"
           "       tosem-scan diff   <old-root> <new-root> [--out F]\n"
           "       tosem-scan body   <project-root>... [--out F]\n"
           "       tosem-scan releases <snapshot-root>=<tag>... [--out F]   |   releases --git <repository> [<revision>...] [--out F]\n"
@@ -1229,7 +1277,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "scan") { if (pos.empty()) die("scan needs at least one project root"); return cmd_scan(pos, opt["--rows"], opt["--summary"], opt.count("--gpus") ? atoi(opt["--gpus"].c_str()) : 1, all_files,
                                         opt.count("--batch-bytes") ? std::max<int64_t>(4096, atoll(opt["--batch-bytes"].c_str())) : (1ll << 30), rev_b); }
-  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"], opt["--correlate"], opt["--correlate-tex"], opt["--correlate-counts"]); }
+  if (cmd == "reduce") { if (pos.size() != 1) die("reduce needs the taxonomy csv"); return cmd_reduce(pos[0], opt["--strategy"], opt["--methods"], opt["--properties"], opt["--correlate"], opt["--correlate-tex"], opt["--correlate-counts"], opt["--correlate-merged"]); }
   if (cmd == "releases") { if (pos.empty() && !opt.count("--git")) die("releases needs <root>=<tag>... or --git <repository>"); return cmd_releases(pos, opt["--out"], opt["--git"]); }
   if (cmd == "body") { if (pos.empty()) die("body needs at least one project root"); return cmd_body(pos, opt["--out"]); }
   if (cmd == "history") { if (pos.size() != 1) die("history needs the repository"); return cmd_history(pos[0], opt.count("--rev") ? opt["--rev"] : "HEAD",
