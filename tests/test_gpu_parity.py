@@ -209,6 +209,22 @@ def test_errors_are_reported_not_swallowed(scanner):
     with pytest.raises(ts.TsmError) as e:
         scanner.scan(bad)
     assert e.value.status == -2
+    # a broken file behind the first 32 MiB slab: found while the slabs in front of it are already on the wire
+    big = ts.gen_corpus(21, 12000, 0, 4096)
+    sc2 = ts.Scanner(0, int(big.off[-1]) + 4096, big.n_files, 1)
+    good = sc2.scan(big, 0)
+    big.len[11000] = 5000                                    # runs into its neighbour
+    with pytest.raises(ts.TsmError) as e:
+        sc2.scan(big, 0)
+    assert e.value.status == -2
+    big.len[11000] = 4096
+    again = sc2.scan(big, 0)                                 # the ctx is usable afterwards
+    assert np.array_equal(again["stats"], good["stats"]) and np.array_equal(again["global_counts"], good["global_counts"])
+    big.off[9000] = 2 ** 31 - 128                            # an offset far outside the arena, in a later slab
+    with pytest.raises(ts.TsmError) as e:
+        sc2.scan(big, 0)
+    assert e.value.status == -2
+    sc2.close()
     small = ts.Scanner(device=0, max_arena_bytes=4096, max_files=4, max_groups=1)
     with pytest.raises(ts.TsmError) as e:
         small.scan(ts.pack([b"x" * 9000], [1]))

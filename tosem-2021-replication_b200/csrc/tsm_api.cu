@@ -280,23 +280,36 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
   return TSM_OK;
 }
 
-static int check_corpus(const tsm_ctx* c, const tsm_corpus* k) {
+// Layout rules of docs/SPEC.md section 1.  The O(1) part, and the per-file part over [f0, f1) (prev_end carries the end of
+// the file in front): tsm_scan checks a slab's files while the slab in front of it is on the wire.
+static int check_corpus_head(const tsm_ctx* c, const tsm_corpus* k) {
   if (!k || k->n_files < 0 || k->n_groups < 1 || (k->n_files > 0 && (!k->arena || !k->off || !k->len || !k->ext)))
     return TSM_E_ARG;
   if (k->n_files > c->max_files || k->n_groups > c->max_groups) return TSM_E_CAPACITY;
   if (k->n_files == 0) return TSM_OK;
-  int64_t prev_end = 0;
-  for (int32_t i = 0; i < k->n_files; ++i) {
+  const int64_t total = k->off[k->n_files];
+  if (total < 0 || (total & (TSM_ALIGN - 1))) return TSM_E_LAYOUT;
+  if (total > c->max_arena) return TSM_E_CAPACITY;
+  return TSM_OK;
+}
+static int check_files(const tsm_corpus* k, int32_t f0, int32_t f1, int64_t& prev_end) {
+  const int64_t total = k->off[k->n_files];
+  for (int32_t i = f0; i < f1; ++i) {
     const int64_t o = k->off[i], l = k->len[i];
-    if (o < prev_end || (o & (TSM_ALIGN - 1)) || l < 0 || o + l > (int64_t)k->off[i + 1]) return TSM_E_LAYOUT;
+    if (o < prev_end || (o & (TSM_ALIGN - 1)) || l < 0 || o + l > (int64_t)k->off[i + 1] || (int64_t)k->off[i + 1] > total) return TSM_E_LAYOUT;
     if (k->grp && k->grp[i] >= k->n_groups) return TSM_E_LAYOUT;
     if (k->ext[i] > TSM_EXT_H) return TSM_E_LAYOUT;
     prev_end = o + l;
   }
-  const int64_t total = k->off[k->n_files];
-  if (total & (TSM_ALIGN - 1)) return TSM_E_LAYOUT;
-  if (total > c->max_arena) return TSM_E_CAPACITY;
   return TSM_OK;
+}
+static int check_corpus(const tsm_ctx* c, const tsm_corpus* k) {
+  int rc = check_corpus_head(c, k);
+  if (rc != TSM_OK || k->n_files == 0) return rc;
+  int64_t prev_end = 0;
+  rc = check_files(k, 0, k->n_files, prev_end);
+  if (rc == TSM_OK && prev_end > (int64_t)k->off[k->n_files]) rc = TSM_E_LAYOUT;
+  return rc;
 }
 
 extern "C" int tsm_upload(tsm_ctx* c, const tsm_corpus* k, void* stream) {
@@ -347,7 +360,7 @@ static ScanParams make_params(const tsm_ctx* c, uint32_t flags) {
 // the arena slabs are copied on the ctx's copy stream and each slab's kernels wait for its copy only,
 // so the H2D of slab s+1 overlaps the scan of slab s (the e2e path); with host == NULL the arena is
 // already resident and there is a single slab.
-static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_corpus* host) {
+static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_corpus* host, bool check_files_here = false) {
   int rc = ensure_event_buffers(c, flags);
   if (rc != TSM_OK) return rc;
   ScanParams p = make_params(c, flags);
@@ -368,19 +381,29 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       CU(cudaStreamWaitEvent(c->copy_stream, c->ready_ev, 0));
     }
     cut.push_back(n);
+    if ((int)cut.size() - 1 > tsm_ctx::kMaxSlabs) return TSM_E_LAYOUT;   // (only offsets that break the layout rules can cut this often)
     const int es = c->ev_next;
     c->ev_next = (es + 1) % tsm_ctx::kRing;
     fold_events(c, es);                                  // only blocks when 32 scans are in flight
     cudaEvent_t* ev = c->ev[es];
     CU(cudaEventRecord(ev[0], st));
     const int n_slabs = (int)cut.size() - 1;
+    int64_t prev_end = 0;
     for (int s = 0; s < n_slabs; ++s) {
       const int32_t f0 = cut[(size_t)s], f1 = cut[(size_t)s + 1];
       if (host) {
+        if (check_files_here && s == 0) {                  // the first slab's files before anything of them is used ...
+          const int rc0 = check_files(host, f0, f1, prev_end);
+          if (rc0 != TSM_OK) return rc0;
+        }
         const size_t b0 = (size_t)host->off[f0], b1 = (size_t)host->off[f1];
         CU(cudaMemcpyAsync(c->d_arena + b0, host->arena + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->slab_ev[s], c->copy_stream));
         CU(cudaStreamWaitEvent(st, c->slab_ev[s], 0));
+        if (check_files_here && s + 1 < n_slabs) {         // ... the next slab's while this one is on the wire
+          const int rc1 = check_files(host, f1, cut[(size_t)s + 2], prev_end);
+          if (rc1 != TSM_OK) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(st); return rc1; }
+        }
       }
       p.slab = c->d_slab + s; p.f_begin = f0; p.f_end = f1;
       // units of earlier slabs are bounded by (arena bytes before f0) / CH + f0
@@ -493,7 +516,7 @@ extern "C" int tsm_download(tsm_ctx* c, tsm_result* r, void* stream) {
 
 extern "C" int tsm_scan(tsm_ctx* c, const tsm_corpus* k, tsm_result* r, uint32_t flags, void* stream) {
   if (!c || !r) return TSM_E_ARG;
-  int rc = check_corpus(c, k);
+  int rc = check_corpus_head(c, k);                       // (the per-file rules are checked slab by slab, under the copies)
   if (rc != TSM_OK) return rc;
   flags &= TSM_SCAN_ASSERT_EVENTS | TSM_SCAN_HEADER_EVENTS | TSM_SCAN_REV_B;
   CU(cudaSetDevice(c->device));
@@ -510,8 +533,8 @@ extern "C" int tsm_scan(tsm_ctx* c, const tsm_corpus* k, tsm_result* r, uint32_t
     else CU(cudaMemsetAsync(c->d_grp, 0, sizeof(uint16_t) * (size_t)n, st));
   }
   c->resident = true;
-  rc = launch_scan(c, flags, st, k);
-  if (rc != TSM_OK) return rc;
+  rc = launch_scan(c, flags, st, k, true);
+  if (rc != TSM_OK) { c->resident = false; c->scanned = false; return rc; }
   return tsm_download(c, r, stream);
 }
 
