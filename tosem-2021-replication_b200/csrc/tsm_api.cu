@@ -352,7 +352,7 @@ static ScanParams make_params(const tsm_ctx* c, uint32_t flags) {
   p.cand = c->d_cand; p.cand_cap = (uint32_t)c->max_events;
   p.hev = c->d_hev; p.hev_cap = (uint32_t)c->max_events;
   p.aev = c->d_aev; p.aev_cap = (uint32_t)c->max_events;
-  p.counts = c->d_counts; p.flags = flags; p.four = 4;
+  p.counts = c->d_counts; p.flags = flags; p.four = 4; p.cls_last = 1;
   return p;
 }
 
@@ -388,6 +388,13 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     cudaEvent_t* ev = c->ev[es];
     CU(cudaEventRecord(ev[0], st));
     const int n_slabs = (int)cut.size() - 1;
+    const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
+    if (c->cls_smem != hist) {                           // one resident wave of k_classify (grid-stride inside): measured
+      int per_sm = 0;                                    // -7 % on C2 against 8 blocks per SM, equal on C4
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify_t<false>, 256, hist) != cudaSuccess || per_sm < 1) per_sm = 4;
+      c->cls_grid = c->sms * per_sm;
+      c->cls_smem = hist;
+    }
     int64_t prev_end = 0;
     for (int s = 0; s < n_slabs; ++s) {
       const int32_t f0 = cut[(size_t)s], f1 = cut[(size_t)s + 1];
@@ -414,16 +421,16 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
       if (flags & TSM_SCAN_REV_B) k_scan_t<true><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM_B, st>>>(p);
       else k_scan_t<false><<<c->sms * SCAN2_CTAS_PER_SM, SCAN2_WARPS * 32, SCAN2_SMEM, st>>>(p);
       CU(cudaGetLastError());
+      if (s + 1 < n_slabs) {                               // streamed scan: this slab's candidates are classified under the next
+        p.cls_last = 0;                                    // slab's copy, so that only the last slab's are left behind the last copy
+        if (flags & TSM_SCAN_REV_B) k_classify_t<true><<<c->cls_grid, 256, hist, st>>>(p);
+        else k_classify_t<false><<<c->cls_grid, 256, hist, st>>>(p);
+        CU(cudaGetLastError());
+        p.cls_last = 1;
+      }
     }
     if (n_slabs > 1) CU(cudaEventRecord(ev[1], st));      // per-kernel split is only meaningful for one slab
     CU(cudaEventRecord(ev[2], st));
-    const size_t hist = CLS_SMEM_BASE + sizeof(uint32_t) * (c->n_groups <= 16 ? (size_t)c->n_groups * TSM_K : 0);
-    if (c->cls_smem != hist) {                           // one resident wave of k_classify (grid-stride inside): measured
-      int per_sm = 0;                                    // -7 % on C2 against 8 blocks per SM, equal on C4
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify_t<false>, 256, hist) != cudaSuccess || per_sm < 1) per_sm = 4;
-      c->cls_grid = c->sms * per_sm;
-      c->cls_smem = hist;
-    }
     if (flags & TSM_SCAN_REV_B) k_classify_t<true><<<c->cls_grid, 256, hist, st>>>(p);
     else k_classify_t<false><<<c->cls_grid, 256, hist, st>>>(p);
     CU(cudaGetLastError());
@@ -431,7 +438,7 @@ static int launch_scan(tsm_ctx* c, uint32_t flags, cudaStream_t st, const tsm_co
     CU(cudaEventRecord(ev[4], st));                           // (slot of the former k_totals, now fused into k_classify)
     c->ev_used[es] = (n_slabs == 1);
     c->ev_last = es;
-    c->launches = 2 * n_slabs + 1;
+    c->launches = 3 * n_slabs;                             // k_plan + k_scan + k_classify per slab
     CU(cudaGetLastError());
   }
   c->last_flags = flags;

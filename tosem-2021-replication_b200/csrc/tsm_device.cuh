@@ -47,6 +47,7 @@ struct Ctrl {                     // device control block, zeroed before every s
   uint32_t overflow;              // some list hit its capacity
   uint32_t n_lh;                  // line-record slots reserved by k_scan (TSM_SCAN_LINE_HASHES)
   uint32_t lh_overflow;           // ... and whether the staging arrays were too small for them
+  uint32_t cls_done;              // candidates already classified (streamed scans classify slab by slab); set by k_plan
 };
 
 // tsm_diff_pairs_detail keeps (D+1)(D+2)/2 ints per pair for the backtrack: at most 2^28 (1 GiB), i.e. D <= 23 168
@@ -89,6 +90,7 @@ struct ScanParams {
   uint32_t* unit_lines;           // [unit slots]
   uint32_t* unit_out;             // [unit slots]
   uint32_t four;                  // 4 (a multiplier the compiler must not see: tsm_scan_walk.cuh, lut_at)
+  uint32_t cls_last;              // k_classify: 1 = the last launch of the scan (adds the totals of the per-file records)
 };
 
 // ---- hashing (SPEC section 3) -------------------------------------------------------------------------

@@ -28,6 +28,7 @@ __device__ char c_cat_blob[TSM_CAT_BLOB_LEN + 1];
 __global__ void k_plan(ScanParams p) {
   const int f = p.f_begin + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.ctrl->cls_done = p.ctrl->n_cand;   // everything found so far has been classified
   uint32_t nu = 0;
   if (f < p.f_end) {
     nu = ((uint32_t)p.len[f] + CH - 1) / CH;
@@ -418,10 +419,10 @@ __global__ void __launch_bounds__(256, TSM_CLS_MINB) k_classify_t(ScanParams p) 
       atomicAdd(&p.counts[(size_t)p.n_groups * TSM_K + cat], 1ull);
     }
   };
-  const uint32_t n = min(p.ctrl->n_cand, p.cand_cap);
+  const uint32_t n = min(p.ctrl->n_cand, p.cand_cap), n0 = min(p.ctrl->cls_done, n);   // this launch: candidates [n0, n)
   const bool want_ev = (p.flags & TSM_SCAN_ASSERT_EVENTS) != 0;
   constexpr bool revb = REVB;                            // (two instantiations: the Rev-B rules stay out of the canonical kernel)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (uint32_t i = n0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long cd = p.cand[i];
     const uint32_t f = (uint32_t)(cd >> 32), line_off = (uint32_t)cd;
     const uint32_t size = (uint32_t)p.len[f];
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(256, TSM_CLS_MINB) k_classify_t(ScanParams p) 
     }
   }
   // ---- totals of the per-file records (lines, assertion lines, headers, fixture headers) behind the table
-  {
+  if (p.cls_last) {
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_files; f += gridDim.x * blockDim.x) {
       const tsm_file_stat s = p.stats[f];
