@@ -42,3 +42,24 @@ def test_bench_line_on_all_gpus(config):
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+
+
+def test_two_contexts_on_two_devices_in_one_process():
+    """One process, a ctx per device: every ctx sets up its own device (kernel attributes, tables); scan and diff on the
+    second device give the first device's numbers."""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tosem-2021-replication_b200"))
+    import tosemscan as ts
+    c = ts.gen_corpus(31, 600, 1, n_groups=3, pinned=False)
+    a, b = ts.gen_pairs(0x7053454D0005, 400)
+    outs = []
+    for dev in (0, 1):
+        sc = ts.Scanner(dev, int(c.off[-1]) + 4096, c.n_files, 4)
+        res = sc.scan(c, ts.SCAN_ASSERT_EVENTS)
+        add, rem, det = sc.diff_pairs(a, b, detail=True)
+        outs.append((res["stats"].copy(), res["group_counts"].copy(), len(res["assert_events"]), add.copy(), rem.copy(), det.copy()))
+        sc.close()
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y)

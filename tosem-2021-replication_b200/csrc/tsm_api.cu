@@ -268,7 +268,15 @@ extern "C" int tsm_create(tsm_ctx** out, int device, int64_t max_arena_bytes, in
         cudaMemset(c->d_arena, 0, (size_t)c->max_arena + 4096) != cudaSuccess ||
         cudaMemcpyToSymbol(c_lut_b, lutb, sizeof lutb) != cudaSuccess ||
         cudaFuncSetAttribute(k_scan_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_scan_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM_B) != cudaSuccess)
+        cudaFuncSetAttribute(k_scan_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM_B) != cudaSuccess ||
+        cudaFuncSetAttribute(k_diff_small<DS1_HCAP, DS1_DCAP, DS1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(DS1_WARPS * ds_warp_bytes(DS1_HCAP, DS1_DCAP))) != cudaSuccess ||
+        cudaFuncSetAttribute(k_diff_small<DS2_HCAP, DS2_DCAP, DS2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(DS2_WARPS * ds_warp_bytes(DS2_HCAP, DS2_DCAP))) != cudaSuccess ||
+        cudaFuncSetAttribute(k_diff_small<DS3_HCAP, DS3_DCAP, DS3_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(DS3_WARPS * ds_warp_bytes(DS3_HCAP, DS3_DCAP))) != cudaSuccess ||
+        cudaFuncSetAttribute(k_diff_small<DS4_HCAP, DS4_DCAP, DS4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(DS4_WARPS * ds_warp_bytes(DS4_HCAP, DS4_DCAP))) != cudaSuccess)
       rc = TSM_E_CUDA;
   }
   if (rc != TSM_OK) {
@@ -808,14 +816,7 @@ static int diff_core(tsm_ctx* c, HostSide& A, HostSide& B, int32_t n, int64_t* a
                      kSmem3 = DS3_WARPS * ds_warp_bytes(DS3_HCAP, DS3_DCAP), kSmem4 = DS4_WARPS * ds_warp_bytes(DS4_HCAP, DS4_DCAP);
   static_assert(kSmem1 * 4 + 4 * 1024 <= 233472 && kSmem2 * 6 + 6 * 1024 <= 233472 && kSmem3 * 5 + 5 * 1024 <= 233472 &&
                 kSmem4 * 3 + 3 * 1024 <= 233472, "pairs per SM");
-  static bool smem_set = false;
-  if (!smem_set) {
-    CU(cudaFuncSetAttribute(k_diff_small<DS1_HCAP, DS1_DCAP, DS1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1));
-    CU(cudaFuncSetAttribute(k_diff_small<DS2_HCAP, DS2_DCAP, DS2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
-    CU(cudaFuncSetAttribute(k_diff_small<DS3_HCAP, DS3_DCAP, DS3_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3));
-    CU(cudaFuncSetAttribute(k_diff_small<DS4_HCAP, DS4_DCAP, DS4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem4));
-    smem_set = true;
-  }
+  // (the kernels' dynamic shared memory limits are raised per device in tsm_create)
   CU(cudaMemsetAsync(d_ntodo.p, 0, 64, st));
   uint32_t* cnt = d_ntodo.as<uint32_t>();                  // [0..3] pairs each size left over, [4..7] the sizes' work counters
   const uint8_t* fa = detail ? A.d.line_flag : nullptr;
