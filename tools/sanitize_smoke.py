@@ -28,4 +28,8 @@ r4 = s.scan(ts.pack(files, exts, grps, 5), 3 | ts.SCAN_REV_B)
 print(s.statements(c)[0][-1])
 fl = (np.random.default_rng(1).random((500, 7)) < 0.3).astype(np.uint8)
 print(s.reduce(fl, np.arange(500) % 3, np.arange(500) % 41, 3, 41)[1])
+big = ts.gen_corpus(9, 9000, 0, 4096, n_groups=2)           # 37 MB through the host path: two slabs, classified slab by slab
+s2 = ts.Scanner(0, int(big.off[-1]) + 4096, big.n_files, 2)
+r5 = s2.scan(big, 0, reuse=True)
+print("streamed", r5["totals"], int(r5["global_counts"].sum()))
 print("totals", r["totals"], r2["totals"], r3["totals"])

@@ -818,6 +818,9 @@ static int diff_core(tsm_ctx* c, HostSide& A, HostSide& B, int32_t n, int64_t* a
                 kSmem4 * 3 + 3 * 1024 <= 233472, "pairs per SM");
   // (the kernels' dynamic shared memory limits are raised per device in tsm_create)
   CU(cudaMemsetAsync(d_ntodo.p, 0, 64, st));
+  CU(cudaMemsetAsync(d_add.p, 0, sizeof(long long) * (size_t)n, st));     // (the first copy back covers every pair, also the ones
+  CU(cudaMemsetAsync(d_rem.p, 0, sizeof(long long) * (size_t)n, st));     //  the four sizes leave to k_myers / k_myers_trace)
+  if (detail) CU(cudaMemsetAsync(d_detail.p, 0, sizeof(tsm_diff_detail) * (size_t)n, st));
   uint32_t* cnt = d_ntodo.as<uint32_t>();                  // [0..3] pairs each size left over, [4..7] the sizes' work counters
   const uint8_t* fa = detail ? A.d.line_flag : nullptr;
   const uint8_t* fb = detail ? B.d.line_flag : nullptr;
