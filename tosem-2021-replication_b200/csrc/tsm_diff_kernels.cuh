@@ -7,8 +7,9 @@
 //   k_diff_small    warp per pair, the common case in ONE kernel: common prefix / suffix trim by ballots, the middle
 //                   hash sequences staged in shared memory, the greedy furthest-reaching D-path search with the
 //                   diagonals of one D across the lanes and V in REGISTERS (neighbour diagonals by shuffle), the rows
-//                   of V kept in shared memory, the canonical backtrack by lane 0.  A pair whose middle does not fit
-//                   (more than DS_HCAP lines) or whose distance exceeds DS_DCAP is left to the two kernels below
+//                   of V kept in shared memory, the canonical backtrack by lane 0.  Four sizes (DS1 .. DS4: staged lines,
+//                   largest distance, pairs per SM), each fed by the list the size before it leaves; a pair none of
+//                   them holds (middle above 4 096 lines, distance above 127) is left to the two kernels below
 //   k_myers         warp per pair: the same search with V in global scratch (any size)
 //   k_myers_trace   the same with one row of V kept per D in global memory, then the backtrack
 #pragma once
